@@ -1,0 +1,119 @@
+"""
+CPU: the oracle port against the golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  Integer outputs bit-exact; float outputs bit-exact where
+the port uses the same numpy/cv2 calls, else within the stated tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_port, model_port, trimap_port
+from helpers import golden_cases, golden_inputs, load_golden
+
+CASES = golden_cases()
+
+
+def test_fixtures_present():
+    assert len(CASES) >= 5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_graph_port_matches_reference(name):
+    g = load_golden(name)
+    img, seg = golden_inputs(g, name)
+    out = graph_port.build_graph(img, seg, int(g["connectivity"]), int(g["n_nonlocal"]))
+    assert out.n_nodes == int(g["n_nodes"]) and out.n_edges == int(g["n_edges"])
+    assert np.array_equal(out.edge_index, g["edge_index"])                 # bit-exact structure
+    assert out.edge_index.dtype == np.int64
+    for key, mine in (("node_features", out.node_features), ("edge_attr", out.edge_attr),
+                      ("prior_features", out.prior_features),
+                      ("node_centroids", out.node_centroids), ("node_areas", out.node_areas)):
+        assert mine.dtype == np.float32
+        assert np.array_equal(mine, g[key]), f"{key}: max|d|={np.abs(mine - g[key]).max()}"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_model_port_matches_reference(name):
+    g = load_golden(name)
+    state = model_port.random_state_dict(int(g["hidden"]), int(g["n_layers"]), seed=int(g["seed"]))
+    x = torch.tensor(np.concatenate([g["node_features"], g["prior_features"]], 1))
+    ei = torch.tensor(g["edge_index"])
+    ea = torch.tensor(g["edge_attr"])
+    logits = model_port.resgcn_forward(state, x, ei, ea).numpy()
+    # same torch ops in a different order of residual bookkeeping: fp32 tolerance
+    np.testing.assert_allclose(logits, g["logits"], rtol=1e-5, atol=2e-6)
+    probs = model_port.predict_probs(state, x, ei, ea)
+    np.testing.assert_allclose(probs, g["probs"], rtol=1e-5, atol=1e-6)
+
+    # batched: [graph, permuted graph, graph]
+    n = x.shape[0]
+    perm = torch.tensor(g["perm"])
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n)
+    xb = torch.cat([x, x[perm], x])
+    eib = torch.cat([ei, inv[ei] + n, ei + 2 * n], 1)
+    eab = torch.cat([ea, ea, ea])
+    batch = torch.arange(3).repeat_interleave(n)
+    lb = model_port.resgcn_forward(state, xb, eib, eab, batch).numpy()
+    np.testing.assert_allclose(lb, g["logits_batched"], rtol=1e-5, atol=2e-6)
+    # the reference's own invariant (tests/test.py:294-306): batched == one by one @1e-4
+    np.testing.assert_allclose(lb[:n], logits, atol=1e-4)
+    np.testing.assert_allclose(lb[n:2 * n], logits[perm.numpy()], atol=1e-4)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_trimap_port_matches_reference(name):
+    g = load_golden(name)
+    img, seg = golden_inputs(g, name)
+    tri = trimap_port.refine_trimap(g["probs"], seg, img, 0.55, 0.55, radius=8)
+    assert tri.dtype == np.uint8 and np.array_equal(tri, g["trimap_refined"])
+    tri4 = trimap_port.refine_trimap(g["probs"], seg, img, 0.4, 0.45, radius=4, eps=1e-2)
+    assert np.array_equal(tri4, g["trimap_r4"])
+    direct = model_port.probs_to_trimap(g["probs"], seg, 0.55, 0.55)
+    assert np.array_equal(direct, g["trimap_direct"])
+    assert set(np.unique(tri)).issubset({0, 1, 2, 3})
+
+
+@pytest.mark.parametrize("name", CASES[:3])
+def test_box_mean_restatement_matches_cv2(name):
+    """cv2.blur(float32) == float64 window sum * 1/k^2 -> float32."""
+    import cv2
+    g = load_golden(name)
+    img, seg = golden_inputs(g, name)
+    guide = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY).astype(np.float32) / np.float32(255.0)
+    for r in (1, 4, 8):
+        if 2 * r + 1 > min(guide.shape):
+            continue
+        ref = cv2.blur(guide, (2 * r + 1, 2 * r + 1))
+        mine = trimap_port.box_mean_f64(guide, r)
+        frac = np.mean(ref == mine)
+        assert frac > 0.999, f"r={r}: only {frac:.4f} of pixels bit-identical"
+        np.testing.assert_allclose(mine, ref, rtol=0, atol=1e-7)
+
+
+def test_thirdparty_colour_known_answers():
+    """Known CIELAB / HSV values of sRGB primaries (D65, 2 deg)."""
+    from oracle.thirdparty import rgb2lab, rgb2hsv
+    px = np.array([[[255, 255, 255], [0, 0, 0], [255, 0, 0], [0, 255, 0], [0, 0, 255],
+                    [128, 128, 128]]], dtype=np.uint8)
+    lab = rgb2lab(px)[0]
+    np.testing.assert_allclose(lab[0], [100.0, 0.0, 0.0], atol=2e-2)
+    np.testing.assert_allclose(lab[1], [0.0, 0.0, 0.0], atol=1e-9)
+    np.testing.assert_allclose(lab[2], [53.24, 80.09, 67.20], atol=2e-2)
+    np.testing.assert_allclose(lab[3], [87.73, -86.18, 83.18], atol=2e-2)
+    np.testing.assert_allclose(lab[4], [32.30, 79.19, -107.86], atol=2e-2)
+    np.testing.assert_allclose(lab[5][0], 53.585, atol=2e-2)
+    hsv = rgb2hsv(px)[0]
+    np.testing.assert_allclose(hsv[2], [0.0, 1.0, 1.0])
+    np.testing.assert_allclose(hsv[3], [1 / 3, 1.0, 1.0])
+    np.testing.assert_allclose(hsv[4], [2 / 3, 1.0, 1.0])
+    np.testing.assert_allclose(hsv[5], [0.0, 0.0, 128 / 255])
+
+
+def test_find_boundaries_label0_quirk():
+    """mode='inner' treats label 0 as background: region 0 never owns boundary pixels."""
+    from oracle.thirdparty import find_boundaries
+    seg = np.zeros((6, 8), np.int32)
+    seg[:, 4:] = 1
+    b = find_boundaries(seg, mode="inner")
+    assert not b[:, :4].any() and b[:, 4].all() and not b[:, 5:].any()
