@@ -1,0 +1,365 @@
+// C ABI of libgcn_grabcut_b200.so (see include/gcn_grabcut_b200.h).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "graph_build.cuh"
+#include "pixel_math.cuh"
+#include "resgcn.cuh"
+#include "trimap.cuh"
+
+namespace gg {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int Arena::reserve(size_t bytes) {
+  off = 0;
+  if (bytes <= cap) return GG_OK;
+  if (base) {
+    GG_CUDA_OK(cudaDeviceSynchronize());   // the old buffer may still be in use by queued work
+    GG_CUDA_OK(cudaFree(base));
+    base = nullptr;
+    cap = 0;
+  }
+  const size_t want = bytes + bytes / 8 + (1u << 20);
+  GG_CUDA_OK(cudaMalloc((void**)&base, want));
+  cap = want;
+  return GG_OK;
+}
+
+void Arena::release() {
+  if (base) cudaFree(base);
+  base = nullptr;
+  cap = off = 0;
+}
+
+__global__ void k_status_or(const int* __restrict__ word, int* __restrict__ sticky) {
+  if (*word) atomicOr(sticky, *word);
+}
+
+static gg_graph_config norm_cfg(const gg_graph_config& c) {
+  gg_graph_config o = c;
+  if (o.pair_cap <= 0) o.pair_cap = 8 * o.node_cap;
+  return o;
+}
+
+// workspace slice of the whole path for `B` images (graph + network + trimap), plus the
+// ragged graph arrays that the device-pointer API would otherwise receive from the caller.
+struct PathBuffers {
+  gg_graph_out g;
+  float* probs;
+};
+
+static size_t path_graph_arrays_bytes(int B, const gg_graph_config& cfg) {
+  const size_t SN = (size_t)B * cfg.node_cap, SE = (size_t)2 * B * cfg.pair_cap;
+  size_t s = 0;
+  s += Arena::padded(B, 4) * 2 + Arena::padded(B + 1, 8) * 2;
+  s += Arena::padded(SN * 19, 4) + Arena::padded(SE * 2, 8) + Arena::padded(SE * 5, 4);
+  s += Arena::padded(SN + 1, 4) + Arena::padded(SE, 4) * 2;
+  s += Arena::padded(SN * 3, 4);
+  return s + 1024;
+}
+
+static PathBuffers take_path_buffers(Arena& ar, int B, const gg_graph_config& cfg) {
+  const size_t SN = (size_t)B * cfg.node_cap, SE = (size_t)2 * B * cfg.pair_cap;
+  PathBuffers pb{};
+  pb.g.n_nodes = ar.take<int32_t>(B);
+  pb.g.n_edges = ar.take<int32_t>(B);
+  pb.g.node_off = ar.take<int64_t>(B + 1);
+  pb.g.edge_off = ar.take<int64_t>(B + 1);
+  pb.g.x = ar.take<float>(SN * 19);
+  pb.g.edge_index = ar.take<int64_t>(SE * 2);
+  pb.g.edge_attr = ar.take<float>(SE * 5);
+  pb.g.csr_rowptr = ar.take<int32_t>(SN + 1);
+  pb.g.csr_src = ar.take<int32_t>(SE);
+  pb.g.csr_eid = ar.take<int32_t>(SE);
+  pb.probs = ar.take<float>(SN * 3);
+  return pb;
+}
+
+static size_t path_workspace_bytes(gg_context* ctx, int B, int H, int W, const gg_path_config& pc) {
+  const gg_graph_config cfg = norm_cfg(pc.graph);
+  const long long SN = (long long)B * cfg.node_cap, SE = 2ll * B * cfg.pair_cap;
+  return path_graph_arrays_bytes(B, cfg) + graph_workspace_bytes(B, H, W, cfg) +
+         resgcn_workspace_bytes(ctx->net, SN, SE, B) + trimap_workspace_bytes(B, H, W, false);
+}
+
+// graph build -> network -> trimap for B images whose inputs are on the device.
+static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* labels, int B,
+                    int H, int W, const gg_path_config& pc, uint8_t* trimap, float* probs_out,
+                    int64_t* node_off_out, int32_t* n_nodes_out, int32_t* n_edges_out,
+                    cudaStream_t st) {
+  const gg_graph_config cfg = norm_cfg(pc.graph);
+  const long long SN = (long long)B * cfg.node_cap, SE = 2ll * B * cfg.pair_cap;
+  PathBuffers pb = take_path_buffers(ar, B, cfg);
+  const uint8_t* gray = nullptr;
+  GG_TRY(build_graphs(ctx, ar, bgr, labels, B, H, W, cfg, pb.g, st, &gray));
+  GG_TRY(resgcn_forward(ctx, ar, pb.g.x, pb.g.csr_rowptr, pb.g.csr_src, pb.g.csr_eid, pb.g.edge_attr,
+                        pb.g.node_off, B, SN, SE, nullptr, pb.probs, st));
+  if (pc.edge_aware) {
+    GG_TRY(refine_trimap(ctx, ar, bgr, gray, labels, pb.probs, pb.g.node_off, B, H, W, pc.radius,
+                         pc.eps, pc.thr_fg, pc.thr_bg, trimap, nullptr, nullptr, st));
+  } else {
+    GG_TRY(project_trimap(ctx, labels, pb.probs, pb.g.node_off, B, H, W, pc.thr_fg, pc.thr_bg, trimap, st));
+  }
+  if (probs_out)
+    GG_CUDA_OK(cudaMemcpyAsync(probs_out, pb.probs, (size_t)SN * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (node_off_out)
+    GG_CUDA_OK(cudaMemcpyAsync(node_off_out, pb.g.node_off, (size_t)(B + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (n_nodes_out)
+    GG_CUDA_OK(cudaMemcpyAsync(n_nodes_out, pb.g.n_nodes, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (n_edges_out)
+    GG_CUDA_OK(cudaMemcpyAsync(n_edges_out, pb.g.n_edges, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return GG_OK;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gg_abi_version(void) { return GG_ABI_VERSION; }
+const char* gg_last_error(void) { return g_err; }
+
+int gg_create(gg_handle* out, int device) {
+  GG_REQUIRE(out != nullptr, "gg_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("gg_create: no CUDA device (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return GG_ERR_CUDA;
+  }
+  GG_REQUIRE(device >= 0 && device < n, "gg_create: device %d out of range (%d devices)", device, n);
+  GG_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GG_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("gg_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+              device, prop.major, prop.minor);
+    return GG_ERR_CUDA;
+  }
+  gg_context* c = new gg_context();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  GG_CUDA_OK(cudaMalloc((void**)&c->d_status, 64));
+  GG_CUDA_OK(cudaMemset(c->d_status, 0, 64));
+  double lin[256];
+  for (int v = 0; v < 256; ++v) lin[v] = srgb_linear(v);
+  GG_CUDA_OK(cudaMalloc((void**)&c->d_lin, sizeof(lin)));
+  GG_CUDA_OK(cudaMemcpy(c->d_lin, lin, sizeof(lin), cudaMemcpyHostToDevice));
+  GG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  GG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
+  GG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  c->ev.resize(16);
+  for (auto& ev : c->ev) GG_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  const char* impl = getenv("GG_GEMM_IMPL");
+  c->gemm_impl = 1;
+  if (impl && !strcmp(impl, "simt")) c->gemm_impl = 0;
+  *out = c;
+  return GG_OK;
+}
+
+void gg_destroy(gg_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  h->arena.release();
+  h->host_arena.release();
+  if (h->net.blob) cudaFree(h->net.blob);
+  if (h->net.tc_blob) cudaFree(h->net.tc_blob);
+  if (h->d_status) cudaFree(h->d_status);
+  if (h->d_lin) cudaFree(h->d_lin);
+  for (auto& ev : h->ev) cudaEventDestroy(ev);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_run) cudaStreamDestroy(h->s_run);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
+  delete h;
+}
+
+int gg_set_option(gg_handle h, const char* key, int value) {
+  GG_REQUIRE(h && key, "gg_set_option: null");
+  if (!strcmp(key, "gemm_impl")) { h->gemm_impl = value; return GG_OK; }
+  set_error("gg_set_option: unknown key %s", key);
+  return GG_ERR_INVALID;
+}
+
+int gg_check_device_status(gg_handle h, void* stream, int* status_bits) {
+  GG_REQUIRE(h && status_bits, "gg_check_device_status: null");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_CUDA_OK(cudaMemcpyAsync(status_bits, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  GG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (*status_bits) {
+    set_error("device status 0x%x:%s%s%s", *status_bits,
+              (*status_bits & ST_LABEL_RANGE) ? " label/index out of range (>= node_cap)" : "",
+              (*status_bits & ST_PAIR_TABLE) ? " adjacency table overflow" : "",
+              (*status_bits & ST_EDGE_CAP) ? " pair/edge capacity exceeded" : "");
+    return GG_ERR_CAPACITY;
+  }
+  return GG_OK;
+}
+
+int gg_build_graphs(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, int B, int H, int W,
+                    const gg_graph_config* cfg, const gg_graph_out* out, void* stream) {
+  GG_REQUIRE(h && bgr_dev && labels_dev && cfg && out, "gg_build_graphs: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  const gg_graph_config c = norm_cfg(*cfg);
+  GG_REQUIRE(c.node_cap > 0 && B > 0 && H > 0 && W > 0, "gg_build_graphs: bad sizes");
+  GG_TRY(h->arena.reserve(graph_workspace_bytes(B, H, W, c)));
+  return build_graphs(h, h->arena, bgr_dev, labels_dev, B, H, W, c, *out, (cudaStream_t)stream, nullptr);
+}
+
+int gg_pixel_planes(gg_handle h, const uint8_t* bgr_dev, int B, int H, int W, float* lab_dev,
+                    float* hsv_dev, float* gray_dev, float* grad_dev, void* stream) {
+  GG_REQUIRE(h && bgr_dev, "gg_pixel_planes: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  return pixel_planes(h, h->arena, bgr_dev, B, H, W, lab_dev, hsv_dev, gray_dev, grad_dev, (cudaStream_t)stream);
+}
+
+int gg_load_weights(gg_handle h, const gg_resgcn_weights* w) {
+  GG_REQUIRE(h && w, "gg_load_weights: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  return load_weights(h, w);
+}
+
+int gg_coo_to_csr(gg_handle h, const int64_t* edge_index_dev, int64_t n_edges, int64_t n_nodes,
+                  int32_t* csr_rowptr_dev, int32_t* csr_src_dev, int32_t* csr_eid_dev, void* stream) {
+  GG_REQUIRE(h && csr_rowptr_dev && (n_edges == 0 || (edge_index_dev && csr_src_dev && csr_eid_dev)),
+             "gg_coo_to_csr: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_TRY(h->arena.reserve(Arena::padded((size_t)n_nodes, 4) + 4096));
+  return coo_to_csr(h, h->arena, edge_index_dev, n_edges, n_nodes, csr_rowptr_dev, csr_src_dev, csr_eid_dev,
+                    (cudaStream_t)stream);
+}
+
+int gg_resgcn_forward(gg_handle h, const float* x_dev, const int32_t* csr_rowptr_dev,
+                      const int32_t* csr_src_dev, const int32_t* csr_eid_dev, const float* edge_attr_dev,
+                      const int64_t* graph_off_dev, int n_graphs, int64_t node_cap_total,
+                      int64_t edge_cap_total, float* logits_dev, float* probs_dev, void* stream) {
+  GG_REQUIRE(h && x_dev && csr_rowptr_dev && graph_off_dev, "gg_resgcn_forward: null argument");
+  GG_REQUIRE(logits_dev || probs_dev, "gg_resgcn_forward: no output requested");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  if (!h->net.loaded) { set_error("gg_resgcn_forward: call gg_load_weights first"); return GG_ERR_STATE; }
+  GG_TRY(h->arena.reserve(resgcn_workspace_bytes(h->net, node_cap_total, edge_cap_total, n_graphs)));
+  GG_CUDA_OK(cudaMemsetAsync(h->d_status, 0, sizeof(int), (cudaStream_t)stream));
+  return resgcn_forward(h, h->arena, x_dev, csr_rowptr_dev, csr_src_dev, csr_eid_dev, edge_attr_dev,
+                        graph_off_dev, n_graphs, node_cap_total, edge_cap_total, logits_dev, probs_dev,
+                        (cudaStream_t)stream);
+}
+
+int gg_refine_trimap(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, const float* probs_dev,
+                     const int64_t* node_off_dev, int B, int H, int W, int radius, float eps, float thr_fg,
+                     float thr_bg, uint8_t* trimap_dev, float* p_bg_dev, float* p_fg_dev, void* stream) {
+  GG_REQUIRE(h && bgr_dev && labels_dev && probs_dev && node_off_dev && trimap_dev, "gg_refine_trimap: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_TRY(h->arena.reserve(trimap_workspace_bytes(B, H, W, true)));
+  return refine_trimap(h, h->arena, bgr_dev, nullptr, labels_dev, probs_dev, node_off_dev, B, H, W, radius, eps,
+                       thr_fg, thr_bg, trimap_dev, p_bg_dev, p_fg_dev, (cudaStream_t)stream);
+}
+
+int gg_project_trimap(gg_handle h, const int32_t* labels_dev, const float* probs_dev,
+                      const int64_t* node_off_dev, int B, int H, int W, float thr_fg, float thr_bg,
+                      uint8_t* trimap_dev, void* stream) {
+  GG_REQUIRE(h && labels_dev && probs_dev && node_off_dev && trimap_dev, "gg_project_trimap: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  return project_trimap(h, labels_dev, probs_dev, node_off_dev, B, H, W, thr_fg, thr_bg, trimap_dev,
+                        (cudaStream_t)stream);
+}
+
+int gg_guided_filter(gg_handle h, const float* guide_dev, const float* src_dev, int H, int W, int radius,
+                     float eps, float* out_dev, void* stream) {
+  GG_REQUIRE(h && guide_dev && src_dev && out_dev, "gg_guided_filter: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_TRY(h->arena.reserve(Arena::padded((size_t)H * W * 2, 4) + 4096));
+  return guided_filter_plane(h, h->arena, guide_dev, src_dev, H, W, radius, eps, out_dev, (cudaStream_t)stream);
+}
+
+int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, int B, int H, int W,
+                          const gg_path_config* cfg, uint8_t* trimap_dev, float* probs_dev,
+                          int64_t* node_off_dev, void* stream) {
+  GG_REQUIRE(h && bgr_dev && labels_dev && cfg && trimap_dev, "gg_trimap_path_device: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  if (!h->net.loaded) { set_error("gg_trimap_path_device: call gg_load_weights first"); return GG_ERR_STATE; }
+  GG_TRY(h->arena.reserve(path_workspace_bytes(h, B, H, W, *cfg)));
+  return run_path(h, h->arena, bgr_dev, labels_dev, B, H, W, *cfg, trimap_dev, probs_dev, node_off_dev,
+                  nullptr, nullptr, (cudaStream_t)stream);
+}
+
+// Host buffers in, host trimaps out.  The batch is cut into chunks; chunk i+1 is copied in
+// (stream s_in) and chunk i-1 copied out (s_out) while chunk i runs (s_run).  Two chunk
+// slots (inputs + workspace + trimaps) alternate.
+int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H, int W,
+                        const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
+                        int32_t* n_edges_host) {
+  GG_REQUIRE(h && bgr_host && labels_host && cfg && trimap_host, "gg_trimap_path_host: null argument");
+  GG_REQUIRE(B > 0 && H >= 2 && W >= 2, "gg_trimap_path_host: bad shape");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  if (!h->net.loaded) { set_error("gg_trimap_path_host: call gg_load_weights first"); return GG_ERR_STATE; }
+  const size_t npx = (size_t)H * W;
+  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)((48u << 20) / (npx * 7) + 1)));
+  chunk = std::min(chunk, B);
+  const int n_chunks = (B + chunk - 1) / chunk;
+  const int n_slots = n_chunks > 1 ? 2 : 1;
+  const size_t in_bytes = Arena::padded((size_t)chunk * npx * 3, 1) + Arena::padded((size_t)chunk * npx, 4) +
+                          Arena::padded((size_t)chunk * npx, 1);
+  const size_t slot_bytes = in_bytes + path_workspace_bytes(h, chunk, H, W, *cfg) + 4096;
+  GG_TRY(h->host_arena.reserve(slot_bytes * n_slots));
+  char* base = h->host_arena.base;
+  cudaEvent_t* ev_in = &h->ev[0];     // [2] input of slot s landed
+  cudaEvent_t* ev_run = &h->ev[2];    // [2] compute of slot s done
+  cudaEvent_t* ev_out = &h->ev[4];    // [2] output of slot s copied out
+  GG_CUDA_OK(cudaMemsetAsync(h->d_status + 1, 0, sizeof(int), h->s_run));
+  for (int ci = 0; ci < n_chunks; ++ci) {
+    const int s = ci % n_slots;
+    const int b0 = ci * chunk, nb = std::min(chunk, B - b0);
+    Arena ar;
+    ar.base = base + (size_t)s * slot_bytes;
+    ar.cap = slot_bytes;
+    uint8_t* d_bgr = ar.take<uint8_t>((size_t)chunk * npx * 3);
+    int32_t* d_lab = ar.take<int32_t>((size_t)chunk * npx);
+    uint8_t* d_tri = ar.take<uint8_t>((size_t)chunk * npx);
+    // the slot is free again once its previous trimaps have been copied out
+    if (ci >= n_slots) GG_CUDA_OK(cudaStreamWaitEvent(h->s_in, ev_out[s], 0));
+    GG_CUDA_OK(cudaMemcpyAsync(d_bgr, bgr_host + (size_t)b0 * npx * 3, (size_t)nb * npx * 3, cudaMemcpyHostToDevice, h->s_in));
+    GG_CUDA_OK(cudaMemcpyAsync(d_lab, labels_host + (size_t)b0 * npx, (size_t)nb * npx * 4, cudaMemcpyHostToDevice, h->s_in));
+    GG_CUDA_OK(cudaEventRecord(ev_in[s], h->s_in));
+    GG_CUDA_OK(cudaStreamWaitEvent(h->s_run, ev_in[s], 0));
+    int st = run_path(h, ar, d_bgr, d_lab, nb, H, W, *cfg, d_tri, nullptr, nullptr,
+                      n_nodes_host ? n_nodes_host + b0 : nullptr, n_edges_host ? n_edges_host + b0 : nullptr,
+                      h->s_run);
+    if (st != GG_OK) { cudaDeviceSynchronize(); return st; }
+    // accumulate the per-chunk device status (run_path's build resets word 0)
+    GG_LAUNCH(h, k_status_or, 1, 1, 0, h->s_run, h->d_status, h->d_status + 1);
+    GG_CUDA_OK(cudaEventRecord(ev_run[s], h->s_run));
+    GG_CUDA_OK(cudaStreamWaitEvent(h->s_out, ev_run[s], 0));
+    GG_CUDA_OK(cudaMemcpyAsync(trimap_host + (size_t)b0 * npx, d_tri, (size_t)nb * npx, cudaMemcpyDeviceToHost, h->s_out));
+    GG_CUDA_OK(cudaEventRecord(ev_out[s], h->s_out));
+  }
+  GG_CUDA_OK(cudaStreamSynchronize(h->s_run));
+  GG_CUDA_OK(cudaStreamSynchronize(h->s_out));
+  GG_CUDA_OK(cudaStreamSynchronize(h->s_in));
+  int bits = 0;
+  GG_CUDA_OK(cudaMemcpy(&bits, h->d_status + 1, sizeof(int), cudaMemcpyDeviceToHost));
+  if (bits) {
+    set_error("gg_trimap_path_host: device status 0x%x (label >= node_cap or pair capacity exceeded)", bits);
+    return GG_ERR_CAPACITY;
+  }
+  return GG_OK;
+}
+
+int64_t gg_kernel_launch_count(gg_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,1176 @@
+// Graph construction: label map + BGR image -> attributed region graph (batched).
+//
+// Replaces graph_builder.py:142-154, 190-350, 357-454 of the reference.  Stages:
+//   k_gray_gradmax     grey plane (uint8) + per-image max of the squared Sobel magnitude
+//   k_coord_tables     y/H, x/W in the two precisions the reference uses
+//   k_region_stats     ONE pass over pixels: per-region sums (fp64) + adjacency transitions
+//   k_finalize_regions region sums -> means / std / centroids ...
+//   k_adj_sort         adjacency hash table -> (lo,hi)-sorted pair list + shared lengths
+//   k_knn / k_nl_pairs non-local colour edges
+//   k_offsets          ragged offsets (prefix sums over the batch)
+//   k_node_features, k_prior_contrast, k_prior_finish, k_edge_attrs, k_csr
+//
+// Float32 epilogues use explicit round-to-nearest intrinsics (never contracted to FMA) so
+// that, given identical region sums, every feature is bit-identical to numpy's.
+#include "common.cuh"
+#include "pixel_math.cuh"
+#include "graph_build.cuh"
+
+namespace gg {
+
+// ============================================================================ K0
+// Tile of TY x TX pixels (+1 halo): grey values to shared memory, interior written to the
+// grey plane, Sobel 3x3 (BORDER_REFLECT_101) squared magnitude max-reduced per image.
+constexpr int K0_TY = 16, K0_TX = 128;
+
+__global__ void __launch_bounds__(256)
+k_gray_gradmax(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray,
+               int* __restrict__ gradmax_sq, int H, int W) {
+  __shared__ uint8_t sg[K0_TY + 2][K0_TX + 2];
+  __shared__ int sred[32];
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * K0_TY, x0 = blockIdx.x * K0_TX;
+  const uint8_t* img = bgr + (size_t)b * H * W * 3;
+  for (int i = threadIdx.x; i < (K0_TY + 2) * (K0_TX + 2); i += blockDim.x) {
+    const int ty = i / (K0_TX + 2), tx = i - ty * (K0_TX + 2);
+    const int y = reflect101(y0 + ty - 1, H), x = reflect101(x0 + tx - 1, W);
+    const uint8_t* p = img + ((size_t)y * W + x) * 3;
+    sg[ty][tx] = (uint8_t)gray_u8(p[0], p[1], p[2]);
+  }
+  __syncthreads();
+  int m = 0;
+  for (int i = threadIdx.x; i < K0_TY * K0_TX; i += blockDim.x) {
+    const int ty = i / K0_TX, tx = i - ty * K0_TX;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y < H && x < W) {
+      const int a00 = sg[ty][tx], a01 = sg[ty][tx + 1], a02 = sg[ty][tx + 2];
+      const int a10 = sg[ty + 1][tx], a11 = sg[ty + 1][tx + 1], a12 = sg[ty + 1][tx + 2];
+      const int a20 = sg[ty + 2][tx], a21 = sg[ty + 2][tx + 1], a22 = sg[ty + 2][tx + 2];
+      const int gx = (a02 + 2 * a12 + a22) - (a00 + 2 * a10 + a20);
+      const int gy = (a20 + 2 * a21 + a22) - (a00 + 2 * a01 + a02);
+      m = max(m, gx * gx + gy * gy);
+      gray[((size_t)b * H + y) * W + x] = (uint8_t)a11;
+    }
+  }
+  m = block_reduce<int>(m, 0, OpMaxI(), sred);
+  if (threadIdx.x == 0 && m > 0) atomicMax(&gradmax_sq[b], m);
+}
+
+// ============================================================================ coordinate tables
+// tab[0..H)      double(float(y)/float(H))   graph_builder.py:207  (float32 coordinates)
+// tab[H..2H)     double(y)/double(H)         graph_builder.py:401  (float64 coordinates)
+// tab[2H..2H+W)  double(float(x)/float(W));  tab[2H+W..2H+2W)  double(x)/double(W)
+__global__ void k_coord_tables(double* __restrict__ tab, int H, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H) {
+    tab[i] = (double)__fdiv_rn((float)i, (float)H);
+    tab[H + i] = (double)i / (double)H;
+  }
+  if (i < W) {
+    tab[2 * H + i] = (double)__fdiv_rn((float)i, (float)W);
+    tab[2 * H + W + i] = (double)i / (double)W;
+  }
+}
+
+// ============================================================================ K1
+// One warp walks down a strip of 32 columns x RS_ROWS rows, lane = column.  Each lane
+// keeps fp64 register accumulators for the vertical run of its current label and hands
+// them to a per-warp shared-memory table when the label changes (plain read-modify-write,
+// no atomics: 64-bit shared atomics are CAS loops on sm_100).  Table slots go to the global
+// per-region accumulators with one RED.F64 per field when evicted / at the end of the strip.
+constexpr int RS_ROWS = 64;
+constexpr int RS_WARPS = 8;
+constexpr int RS_SLOTS = 16;
+constexpr int RS_STAGE_LD = 17;  // doubles per lane in the staging area (padded)
+constexpr size_t RS_SMEM_BYTES =
+    (256 + RS_WARPS * RS_SLOTS * 16 + RS_WARPS * 32 * RS_STAGE_LD) * sizeof(double) +
+    RS_WARPS * RS_SLOTS * sizeof(int);
+
+struct RegionStatsParams {
+  const uint8_t* bgr;
+  const uint8_t* gray;
+  const int32_t* labels;
+  const int* gradmax_sq;   // [B]
+  const double* coord;     // k_coord_tables
+  const double* lin_lut;   // [256]
+  double* acc;             // [B][node_cap][16]
+  int* label_max;          // [B]
+  unsigned long long* pair_keys;  // [B][table_cap]
+  int* pair_cnts;                 // [B][table_cap]
+  int* status;
+  int B, H, W, node_cap, table_cap, connectivity;
+  int n_sx, n_sy;
+  LabMatrix lab;
+};
+
+GG_D uint32_t pair_hash(uint32_t lo, uint32_t hi) {
+  uint32_t h = lo * 0x9E3779B1u ^ (hi + 0x7F4A7C15u) * 0x85EBCA6Bu;
+  h ^= h >> 15;
+  return h;
+}
+
+// Insert / increment an undirected pair in the per-image open-addressing table.
+GG_D void pair_emit(unsigned long long* keys, int* cnts, int cap, int a, int b, int count,
+                    int* status) {
+  const uint32_t lo = (uint32_t)min(a, b), hi = (uint32_t)max(a, b);
+  const unsigned long long key = ((unsigned long long)lo << 32) | hi;
+  const unsigned long long EMPTY = ~0ull;
+  uint32_t h = pair_hash(lo, hi) & (uint32_t)(cap - 1);
+  for (int probe = 0; probe < cap; ++probe) {
+    unsigned long long cur = keys[h];
+    if (cur == EMPTY) cur = atomicCAS(&keys[h], EMPTY, key);
+    if (cur == EMPTY || cur == key) {
+      atomicAdd(&cnts[h], count);
+      return;
+    }
+    h = (h + 1) & (uint32_t)(cap - 1);
+  }
+  atomicOr(status, ST_PAIR_TABLE);
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32, 2)
+k_region_stats(const RegionStatsParams p) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  double* s_lin = reinterpret_cast<double*>(rs_smem);                       // [256]
+  double* s_vals_all = s_lin + 256;                                         // [W][SLOTS][16]
+  double* s_stage_all = s_vals_all + RS_WARPS * RS_SLOTS * 16;              // [W][32*LD]
+  int* s_tags_all = reinterpret_cast<int*>(s_stage_all + RS_WARPS * 32 * RS_STAGE_LD);
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* vals = s_vals_all + wid * RS_SLOTS * 16;
+  double* stage = s_stage_all + wid * 32 * RS_STAGE_LD;
+  int* tags = s_tags_all + wid * RS_SLOTS;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lin[i] = p.lin_lut[i];
+  for (int i = lane; i < RS_SLOTS * 16; i += 32) vals[i] = 0.0;
+  if (lane < RS_SLOTS) tags[lane] = -1;
+  __syncthreads();
+
+  const long long task = (long long)blockIdx.x * RS_WARPS + wid;
+  const long long n_tasks = (long long)p.B * p.n_sy * p.n_sx;
+  if (task >= n_tasks) return;
+  const int sx = (int)(task % p.n_sx);
+  const int sy = (int)((task / p.n_sx) % p.n_sy);
+  const int b = (int)(task / ((long long)p.n_sx * p.n_sy));
+  const int H = p.H, W = p.W;
+  const int x = sx * 32 + lane;
+  const bool valid = x < W;
+  const int xc = valid ? x : W - 1;
+  const int y_begin = sy * RS_ROWS, y_end = min(H, y_begin + RS_ROWS);
+
+  const uint8_t* img = p.bgr + (size_t)b * H * W * 3;
+  const uint8_t* gry = p.gray + (size_t)b * H * W;
+  const int32_t* lab = p.labels + (size_t)b * H * W;
+  double* acc_g = p.acc + (size_t)b * p.node_cap * 16;
+  unsigned long long* keys = p.pair_keys + (size_t)b * p.table_cap;
+  int* cnts = p.pair_cnts + (size_t)b * p.table_cap;
+
+  const int xl = reflect101(xc - 1, W), xr = reflect101(xc + 1, W);
+  const double xtf = p.coord[2 * H + xc], xtd = p.coord[2 * H + W + xc];
+  const int gm = p.gradmax_sq[b];
+  const float gden = __fadd_rn(__fsqrt_rn((float)gm), 1e-6f);  // grad.max() + 1e-6 (float32)
+
+  // horizontal Sobel partials of a grey row: hs = g[x-1]+2g[x]+g[x+1], hd = g[x+1]-g[x-1]
+  auto row_partials = [&](int yy, int& hs, int& hd) {
+    const uint8_t* r = gry + (size_t)reflect101(yy, H) * W;
+    const int gl = r[xl], gc = r[xc], gr = r[xr];
+    hs = gl + 2 * gc + gr;
+    hd = gr - gl;
+  };
+  auto load_label = [&](int yy, int xx) -> int {
+    return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? lab[(size_t)yy * W + xx] : -1;
+  };
+
+  int hs_m, hd_m, hs_c, hd_c, hs_p, hd_p;
+  row_partials(y_begin - 1, hs_m, hd_m);
+  row_partials(y_begin, hs_c, hd_c);
+  int lab_up = valid ? load_label(y_begin - 1, x) : -1;
+  int lab_c = valid ? load_label(y_begin, x) : -1;
+
+  // per-lane run accumulators
+  int cur = -1, cnt = 0, bnd = 0, brd = 0;
+  double aL = 0, aA = 0, aB = 0, aL2 = 0, aA2 = 0, aB2 = 0, aH = 0, aS = 0, aV = 0;
+  double aYf = 0, aG = 0, aGs = 0, aYd = 0;
+  // vertical-boundary pair run (right neighbour)
+  int rp_a = -1, rp_b = -1, rp_cnt = 0;
+  int lmax = -1;
+
+  auto evict_slot = [&](int slot) {  // warp-uniform
+    const int tag = tags[slot];
+    if (tag >= 0 && lane < 16) {
+      double* g = acc_g + (size_t)tag * 16 + lane;
+      if (lane < 15) {
+        const double v = vals[slot * 16 + lane];
+        if (v != 0.0) atomicAdd(g, v);
+      } else {
+        const unsigned long long v = ((unsigned long long*)vals)[slot * 16 + 15];
+        if (v) atomicAdd((unsigned long long*)g, v);
+      }
+      vals[slot * 16 + lane] = 0.0;
+    }
+  };
+
+  auto flush_lanes = [&](unsigned mask) {  // warp-uniform mask of lanes whose run ends
+    if (mask >> lane & 1u) {
+      double* st = stage + lane * RS_STAGE_LD;
+      st[0] = aL; st[1] = aA; st[2] = aB; st[3] = aL2; st[4] = aA2; st[5] = aB2;
+      st[6] = aH; st[7] = aS; st[8] = aV; st[9] = aYf; st[10] = (double)cnt * xtf;
+      st[11] = aG; st[12] = aGs; st[13] = aYd; st[14] = (double)cnt * xtd;
+      ((unsigned long long*)st)[15] = (unsigned long long)cnt | ((unsigned long long)bnd << 24) |
+                                      ((unsigned long long)brd << 48);
+      cnt = bnd = brd = 0;
+      aL = aA = aB = aL2 = aA2 = aB2 = aH = aS = aV = aYf = aG = aGs = aYd = 0.0;
+    }
+    __syncwarp();
+    unsigned m = mask;
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int L = __shfl_sync(0xffffffffu, cur, src);
+      const int slot = (int)(((uint32_t)L * 0x9E3779B1u) >> 28) & (RS_SLOTS - 1);
+      if (tags[slot] != L) {
+        evict_slot(slot);
+        __syncwarp();
+        if (lane == 0) tags[slot] = L;
+        __syncwarp();
+      }
+      if (lane < 15) {
+        vals[slot * 16 + lane] += stage[src * RS_STAGE_LD + lane];
+      } else if (lane == 15) {
+        ((unsigned long long*)vals)[slot * 16 + 15] +=
+            ((unsigned long long*)stage)[src * RS_STAGE_LD + 15];
+      }
+      __syncwarp();
+    }
+  };
+
+  // BGR of the first row
+  uint8_t pb = 0, pg = 0, pr = 0;
+  if (valid) {
+    const uint8_t* px = img + ((size_t)y_begin * W + x) * 3;
+    pb = px[0]; pg = px[1]; pr = px[2];
+  }
+
+  for (int y = y_begin; y < y_end; ++y) {
+    // ---- look ahead: next grey row partials, next label row, next BGR
+    row_partials(y + 1, hs_p, hd_p);
+    const int lab_dn = valid ? load_label(y + 1, x) : -1;
+    uint8_t nb_ = 0, ng_ = 0, nr_ = 0;
+    if (valid && y + 1 < y_end) {
+      const uint8_t* px = img + ((size_t)(y + 1) * W + x) * 3;
+      nb_ = px[0]; ng_ = px[1]; nr_ = px[2];
+    }
+    // ---- horizontal neighbours of the label row
+    int lab_r = __shfl_down_sync(0xffffffffu, lab_c, 1);
+    int lab_l = __shfl_up_sync(0xffffffffu, lab_c, 1);
+    if (lane == 31) lab_r = valid ? load_label(y, x + 1) : -1;
+    if (lane == 0) lab_l = valid ? load_label(y, x - 1) : -1;
+
+    bool in_range = valid && lab_c >= 0 && lab_c < p.node_cap;
+    if (valid && !in_range) atomicOr(p.status, ST_LABEL_RANGE);
+
+    // ---- run bookkeeping: hand finished runs to the warp table
+    const bool ends = in_range && cnt > 0 && lab_c != cur;
+    const unsigned fm = __ballot_sync(0xffffffffu, ends);
+    if (fm) flush_lanes(fm);
+    if (in_range) {
+      cur = lab_c;
+      lmax = max(lmax, lab_c);
+      // ---- per-pixel quantities
+      float L, A, Bv, hh, ss, vv;
+      bgr_to_lab(s_lin, p.lab.m, pb, pg, pr, L, A, Bv);
+      bgr_to_hsv(pb, pg, pr, hh, ss, vv);
+      const int gx = hd_m + 2 * hd_c + hd_p;
+      const int gy = hs_p - hs_m;
+      const float g = __fsqrt_rn((float)(gx * gx + gy * gy));
+      const float gs = __fdiv_rn(g, gden);
+      aL += (double)L; aA += (double)A; aB += (double)Bv;
+      aL2 += (double)__fmul_rn(L, L); aA2 += (double)__fmul_rn(A, A); aB2 += (double)__fmul_rn(Bv, Bv);
+      aH += (double)hh; aS += (double)ss; aV += (double)vv;
+      aYf += p.coord[y]; aYd += p.coord[H + y];
+      aG += (double)g; aGs += (double)gs;
+      cnt += 1;
+      // find_boundaries(mode="inner"): differs from an in-bounds 4-neighbour and label != 0
+      const bool diff = (lab_up >= 0 && lab_up != lab_c) || (lab_dn >= 0 && lab_dn != lab_c) ||
+                        (lab_l >= 0 && lab_l != lab_c) || (lab_r >= 0 && lab_r != lab_c);
+      bnd += (diff && lab_c != 0) ? 1 : 0;
+      brd += (y == 0) + (y == H - 1) + (x == 0) + (x == W - 1);   // corners count twice
+    }
+
+    // ---- adjacency transitions (graph_builder.py:267-281)
+    // right neighbour: aggregated down the column in registers
+    if (in_range && lab_r >= 0 && lab_r != lab_c && lab_r < p.node_cap) {
+      if (lab_c == rp_a && lab_r == rp_b) {
+        rp_cnt += 1;
+      } else {
+        if (rp_cnt > 0) pair_emit(keys, cnts, p.table_cap, rp_a, rp_b, rp_cnt, p.status);
+        rp_a = lab_c; rp_b = lab_r; rp_cnt = 1;
+      }
+    }
+    // down neighbour (and the two diagonals for connectivity 8): aggregated across lanes
+    {
+      const bool t = in_range && lab_dn >= 0 && lab_dn != lab_c && lab_dn < p.node_cap;
+      const unsigned tm = __ballot_sync(0xffffffffu, t);
+      if (t) {
+        const unsigned long long key =
+            ((unsigned long long)(uint32_t)min(lab_c, lab_dn) << 32) | (uint32_t)max(lab_c, lab_dn);
+        const unsigned grp = __match_any_sync(tm, key);
+        if ((__ffs(grp) - 1) == lane)
+          pair_emit(keys, cnts, p.table_cap, lab_c, lab_dn, __popc(grp), p.status);
+      }
+    }
+    if (p.connectivity == 8) {
+      int dn_r = __shfl_down_sync(0xffffffffu, lab_dn, 1);
+      int dn_l = __shfl_up_sync(0xffffffffu, lab_dn, 1);
+      if (lane == 31) dn_r = valid ? load_label(y + 1, x + 1) : -1;
+      if (lane == 0) dn_l = valid ? load_label(y + 1, x - 1) : -1;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int o = s ? dn_l : dn_r;
+        const bool t = in_range && o >= 0 && o != lab_c && o < p.node_cap;
+        const unsigned tm = __ballot_sync(0xffffffffu, t);
+        if (t) {
+          const unsigned long long key =
+              ((unsigned long long)(uint32_t)min(lab_c, o) << 32) | (uint32_t)max(lab_c, o);
+          const unsigned grp = __match_any_sync(tm, key);
+          if ((__ffs(grp) - 1) == lane)
+            pair_emit(keys, cnts, p.table_cap, lab_c, o, __popc(grp), p.status);
+        }
+      }
+    }
+
+    // ---- roll
+    hs_m = hs_c; hd_m = hd_c; hs_c = hs_p; hd_c = hd_p;
+    lab_up = lab_c; lab_c = lab_dn;
+    pb = nb_; pg = ng_; pr = nr_;
+  }
+
+  // ---- end of strip: flush runs, pairs, table, label max
+  const unsigned fm = __ballot_sync(0xffffffffu, cnt > 0);
+  if (fm) flush_lanes(fm);
+  if (rp_cnt > 0) pair_emit(keys, cnts, p.table_cap, rp_a, rp_b, rp_cnt, p.status);
+  __syncwarp();
+  for (int s = 0; s < RS_SLOTS; ++s) evict_slot(s);
+  lmax = warp_max_i(lmax);
+  if (lane == 0 && lmax >= 0) atomicMax(&p.label_max[b], lmax);
+}
+
+// ============================================================================ S1
+// Region sums -> per-region statistics (graph_builder.py:194-226 and :391-403).
+__global__ void k_finalize_regions(const double* __restrict__ acc, const int* __restrict__ label_max,
+                                   float* __restrict__ st, int B, int H, int W, int node_cap) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = label_max[b] + 1;
+  if (i >= n || i >= node_cap) return;
+  const double* a = acc + ((size_t)b * node_cap + i) * 16;
+  const unsigned long long pk = ((const unsigned long long*)a)[15];
+  const float counts = (float)(int)(pk & 0xFFFFFFull);
+  const float bnd = (float)(int)((pk >> 24) & 0xFFFFFFull);
+  const float brd = (float)(int)(pk >> 48);
+  const float safe = fmaxf(counts, 1.0f);
+  float* s = st + (size_t)b * ST_FIELDS * node_cap + i;
+  auto put = [&](int f, float v) { s[(size_t)f * node_cap] = v; };
+  put(ST_COUNT, counts);
+  put(ST_SAFE, safe);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float mean = __fdiv_rn((float)a[c], safe);
+    const float sq = __fdiv_rn((float)a[3 + c], safe);
+    const float var = fmaxf(__fsub_rn(sq, __fmul_rn(mean, mean)), 0.0f);
+    put(ST_MEAN_L + c, mean);
+    put(ST_STD_L + c, __fsqrt_rn(var));
+    put(ST_MEAN_H + c, __fdiv_rn((float)a[6 + c], safe));
+  }
+  put(ST_CY, __fdiv_rn((float)a[9], safe));
+  put(ST_CX, __fdiv_rn((float)a[10], safe));
+  put(ST_BND, bnd);
+  put(ST_AREA, __fdiv_rn(counts, (float)((double)H * (double)W)));
+  put(ST_MGRAD, __fdiv_rn((float)a[11], safe));
+  put(ST_MGRADN, __fdiv_rn((float)a[12], safe));
+  // compute_auto_prior: float64 sum / float32 safe -> float64 -> float32 (…:401-403)
+  put(ST_PCY, (float)(a[13] / (double)safe));
+  put(ST_PCX, (float)(a[14] / (double)safe));
+  put(ST_BORDER, brd);
+}
+
+// ============================================================================ S2
+// Per image: hash table -> pairs sorted by (lo, hi) via counting sort on lo + per-lo
+// insertion sort on hi.  start[] (node_cap+1 ints) is kept for adjacency lookups.
+__global__ void __launch_bounds__(512)
+k_adj_sort(const unsigned long long* __restrict__ keys_all, const int* __restrict__ cnts_all,
+           const int* __restrict__ label_max, int2* __restrict__ pairs_all,
+           int* __restrict__ shared_all, int* __restrict__ start_all, int* __restrict__ cursor_all,
+           int* __restrict__ n_adj, int* __restrict__ max_shared, int* __restrict__ status,
+           int node_cap, int table_cap, int pair_cap) {
+  __shared__ int scratch[40];
+  const int b = blockIdx.x;
+  const int n = min(label_max[b] + 1, node_cap);
+  const unsigned long long* keys = keys_all + (size_t)b * table_cap;
+  const int* cnts = cnts_all + (size_t)b * table_cap;
+  int2* pairs = pairs_all + (size_t)b * pair_cap;
+  int* shared = shared_all + (size_t)b * pair_cap;
+  int* start = start_all + (size_t)b * (node_cap + 1);
+  int* cursor = cursor_all + (size_t)b * node_cap;
+  const unsigned long long EMPTY = ~0ull;
+
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { start[i] = 0; cursor[i] = 0; }
+  __syncthreads();
+  for (int s = threadIdx.x; s < table_cap; s += blockDim.x) {
+    const unsigned long long k = keys[s];
+    if (k != EMPTY) atomicAdd(&start[(int)(k >> 32)], 1);
+  }
+  __syncthreads();
+  int carry = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < n) ? start[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, scratch, &total);
+    if (i < n) start[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  const int n_pairs = carry;
+  if (threadIdx.x == 0) {
+    start[n] = n_pairs;
+    n_adj[b] = n_pairs > pair_cap ? 0 : n_pairs;
+    if (n_pairs > pair_cap) { atomicOr(status, ST_EDGE_CAP); max_shared[b] = 0; }
+  }
+  __syncthreads();
+  if (n_pairs > pair_cap) return;
+  int mx = 0;
+  for (int s = threadIdx.x; s < table_cap; s += blockDim.x) {
+    const unsigned long long k = keys[s];
+    if (k != EMPTY) {
+      const int lo = (int)(k >> 32), hi = (int)(k & 0xFFFFFFFFull);
+      const int pos = start[lo] + atomicAdd(&cursor[lo], 1);
+      pairs[pos] = make_int2(lo, hi);
+      shared[pos] = cnts[s];
+      mx = max(mx, cnts[s]);
+    }
+  }
+  mx = block_reduce<int>(mx, 0, OpMaxI(), scratch);
+  if (threadIdx.x == 0) max_shared[b] = mx;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int s0 = start[i], s1 = start[i + 1];
+    for (int a = s0 + 1; a < s1; ++a) {
+      const int2 pv = pairs[a];
+      const int cv = shared[a];
+      int j = a - 1;
+      while (j >= s0 && pairs[j].y > pv.y) {
+        pairs[j + 1] = pairs[j];
+        shared[j + 1] = shared[j];
+        --j;
+      }
+      pairs[j + 1] = pv;
+      shared[j + 1] = cv;
+    }
+  }
+}
+
+// ============================================================================ S3
+// k nearest neighbours in mean-Lab space, self and spatially adjacent regions excluded
+// (graph_builder.py:333-347).  One warp per region; ties on distance -> lower index.
+GG_D bool knn_less(float d, int j, float bd, int bj) { return d < bd || (d == bd && j < bj); }
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_knn(const float* __restrict__ st_all, const int* __restrict__ label_max,
+      const int2* __restrict__ pairs_all, const int* __restrict__ start_all,
+      int* __restrict__ picks_all, int node_cap, int pair_cap, int k) {
+  const int b = blockIdx.y;
+  const int n = min(label_max[b] + 1, node_cap);
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
+  const float* mL = st + (size_t)ST_MEAN_L * node_cap;
+  const float* mA = mL + node_cap;
+  const float* mB = mA + node_cap;
+  const int2* pairs = pairs_all + (size_t)b * pair_cap;
+  const int* start = start_all + (size_t)b * (node_cap + 1);
+  const float INF = __int_as_float(0x7f800000);
+
+  float bd[K];
+  int bj[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) { bd[t] = INF; bj[t] = 0x7fffffff; }
+  const float li = mL[i], ai = mA[i], bi = mB[i];
+  for (int j = lane; j < n; j += 32) {
+    if (j == i) continue;
+    const float dx = __fsub_rn(li, mL[j]), dy = __fsub_rn(ai, mA[j]), dz = __fsub_rn(bi, mB[j]);
+    const float d = __fsqrt_rn(
+        __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    if (!(d < INF)) continue;   // inf / nan never selected (np.isfinite filter, …:346)
+    // only the k best of a lane can make the warp's k best
+    bool cand = false;
+#pragma unroll
+    for (int t = 0; t < K; ++t)
+      if (t == k - 1) cand = knn_less(d, j, bd[t], bj[t]);
+    if (!cand) continue;
+    const int lo = min(i, j), hi = max(i, j);
+    bool adjacent = false;
+    for (int q = start[lo]; q < start[lo + 1]; ++q)
+      if (pairs[q].y == hi) { adjacent = true; break; }
+    if (adjacent) continue;
+    float cd = d;
+    int cj = j;
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+      if (knn_less(cd, cj, bd[t], bj[t])) {
+        const float td = bd[t]; const int tj = bj[t];
+        bd[t] = cd; bj[t] = cj;
+        cd = td; cj = tj;
+      }
+    }
+  }
+  // merge the 32 sorted lists: k rounds of warp arg-min on (d, j)
+  int* out = picks_all + ((size_t)b * node_cap + i) * k;
+  for (int r = 0; r < k; ++r) {
+    float d = bd[0];
+    int j = bj[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+      if (knn_less(od, oj, d, j)) { d = od; j = oj; }
+    }
+    if (lane == 0) out[r] = (d < INF) ? j : -1;
+    if (bj[0] == j && bd[0] == d && d < INF) {   // the winner pops its head
+#pragma unroll
+      for (int t = 0; t + 1 < K; ++t) { bd[t] = bd[t + 1]; bj[t] = bj[t + 1]; }
+      bd[K - 1] = INF; bj[K - 1] = 0x7fffffff;
+    }
+  }
+}
+
+// ============================================================================ S4
+// Symmetrise the picks into sorted unique (lo,hi) pairs (graph_builder.py:348-350).
+__global__ void __launch_bounds__(512)
+k_nl_pairs(const int* __restrict__ picks_all, const int* __restrict__ label_max,
+           const int* __restrict__ n_adj, int2* __restrict__ pairs_all,
+           int* __restrict__ start_all, int* __restrict__ cursor_all, int* __restrict__ n_nl,
+           int* __restrict__ status, int node_cap, int pair_cap, int k) {
+  __shared__ int scratch[40];
+  const int b = blockIdx.x;
+  const int n = min(label_max[b] + 1, node_cap);
+  const int* picks = picks_all + (size_t)b * node_cap * k;
+  const int base_adj = n_adj[b];
+  int2* out = pairs_all + (size_t)b * pair_cap + base_adj;   // appended after the adjacency pairs
+  int* start = start_all + (size_t)b * (node_cap + 1);
+  int* cursor = cursor_all + (size_t)b * node_cap;
+
+  if (k <= 0 || n <= k + 1) {                                   // graph_builder.py:291
+    if (threadIdx.x == 0) n_nl[b] = 0;
+    return;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { start[i] = 0; cursor[i] = 0; }
+  __syncthreads();
+  // keep (i -> j) if i is the smaller id, or if the smaller id did not pick i itself
+  auto keeps = [&](int i, int j) -> bool {
+    if (j < 0) return false;
+    if (i < j) return true;
+    for (int t = 0; t < k; ++t)
+      if (picks[(size_t)j * k + t] == i) return false;
+    return true;
+  };
+  for (int e = threadIdx.x; e < n * k; e += blockDim.x) {
+    const int i = e / k, j = picks[e];
+    if (keeps(i, j)) atomicAdd(&start[min(i, j)], 1);
+  }
+  __syncthreads();
+  int carry = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < n) ? start[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, scratch, &total);
+    if (i < n) start[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  const int n_pairs = carry;
+  if (threadIdx.x == 0) {
+    start[n] = n_pairs;
+    const bool over = base_adj + n_pairs > pair_cap;
+    n_nl[b] = over ? 0 : n_pairs;
+    if (over) atomicOr(status, ST_EDGE_CAP);
+  }
+  __syncthreads();
+  if (base_adj + n_pairs > pair_cap) return;
+  for (int e = threadIdx.x; e < n * k; e += blockDim.x) {
+    const int i = e / k, j = picks[e];
+    if (keeps(i, j)) {
+      const int lo = min(i, j), hi = max(i, j);
+      out[start[lo] + atomicAdd(&cursor[lo], 1)] = make_int2(lo, hi);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int s0 = start[i], s1 = start[i + 1];
+    for (int a = s0 + 1; a < s1; ++a) {
+      const int2 pv = out[a];
+      int j = a - 1;
+      while (j >= s0 && out[j].y > pv.y) { out[j + 1] = out[j]; --j; }
+      out[j + 1] = pv;
+    }
+  }
+}
+
+// ============================================================================ S5
+// Ragged offsets over the batch (single block).
+__global__ void __launch_bounds__(1024)
+k_offsets(const int* __restrict__ label_max, const int* __restrict__ n_adj,
+          const int* __restrict__ n_nl, int B, int node_cap, int32_t* __restrict__ n_nodes,
+          int32_t* __restrict__ n_edges, int64_t* __restrict__ node_off,
+          int64_t* __restrict__ edge_off, int32_t* __restrict__ o_n_adj,
+          int32_t* __restrict__ o_n_nl) {
+  __shared__ int scratch[40];
+  int carry_n = 0, carry_e = 0;
+  for (int base = 0; base < B; base += blockDim.x) {
+    const int b = base + threadIdx.x;
+    const int nn = (b < B) ? min(label_max[b] + 1, node_cap) : 0;
+    const int ne = (b < B) ? 2 * (n_adj[b] + n_nl[b]) : 0;
+    int tn, te;
+    const int en = block_exclusive_scan(nn, scratch, &tn);
+    const int ee = block_exclusive_scan(ne, scratch, &te);
+    if (b < B) {
+      n_nodes[b] = nn;
+      n_edges[b] = ne;
+      node_off[b] = carry_n + en;
+      edge_off[b] = carry_e + ee;
+      if (o_n_adj) o_n_adj[b] = n_adj[b];
+      if (o_n_nl) o_n_nl[b] = n_nl[b];
+    }
+    carry_n += tn;
+    carry_e += te;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    node_off[B] = carry_n;
+    edge_off[B] = carry_e;
+  }
+}
+
+// ============================================================================ S6
+// The 16 image-derived node attributes (graph_builder.py:228-255).
+GG_D float nan_to_num(float v) {
+  if (isnan(v)) return 0.0f;
+  if (isinf(v)) return v > 0 ? 1.0f : 0.0f;
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_node_features(const float* __restrict__ st_all, const int* __restrict__ label_max,
+                const int64_t* __restrict__ node_off, float* __restrict__ x,
+                float* __restrict__ centroids, float* __restrict__ areas, int node_cap) {
+  __shared__ float sred[32];
+  __shared__ float s_mn[6], s_mx[6];
+  const int b = blockIdx.x;
+  const int n = min(label_max[b] + 1, node_cap);
+  const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
+  auto S = [&](int f, int i) { return st[(size_t)f * node_cap + i]; };
+  const int64_t no = node_off[b];
+  const float INF = __int_as_float(0x7f800000);
+
+  float mn[6], mx[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) { mn[c] = INF; mx[c] = -INF; }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float m = S(ST_MEAN_L + c, i), sd = S(ST_STD_L + c, i);
+      mn[c] = fminf(mn[c], m); mx[c] = fmaxf(mx[c], m);
+      mn[3 + c] = fminf(mn[3 + c], sd); mx[3 + c] = fmaxf(mx[3 + c], sd);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const float a = block_reduce<float>(mn[c], INF, OpMinF(), sred);
+    const float z = block_reduce<float>(mx[c], -INF, OpMaxF(), sred);
+    if (threadIdx.x == 0) { s_mn[c] = a; s_mx[c] = z; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float* f = x + (size_t)(no + i) * GG_N_NODE_FEATS;
+    const float counts = S(ST_COUNT, i), safe = S(ST_SAFE, i), bnd = S(ST_BND, i);
+    const float cy = S(ST_CY, i), cx = S(ST_CX, i);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float den0 = __fadd_rn(__fsub_rn(s_mx[c], s_mn[c]), 1e-6f);
+      const float den1 = __fadd_rn(__fsub_rn(s_mx[3 + c], s_mn[3 + c]), 1e-6f);
+      f[c] = nan_to_num(__fdiv_rn(__fsub_rn(S(ST_MEAN_L + c, i), s_mn[c]), den0));
+      f[3 + c] = nan_to_num(__fdiv_rn(__fsub_rn(S(ST_STD_L + c, i), s_mn[3 + c]), den1));
+      f[6 + c] = nan_to_num(S(ST_MEAN_H + c, i));
+    }
+    f[9] = nan_to_num(cy);
+    f[10] = nan_to_num(cx);
+    f[11] = nan_to_num(S(ST_AREA, i));
+    const float perim = fmaxf(bnd, 1.0f);
+    const float iso = __fdiv_rn(__fmul_rn(12.566370614359172f, counts), __fmul_rn(perim, perim));
+    f[12] = nan_to_num(fminf(fmaxf(iso, 0.0f), 1.0f));
+    f[13] = nan_to_num(__fdiv_rn(S(ST_MGRAD, i), 255.0f));
+    f[14] = nan_to_num(__fdiv_rn(bnd, safe));
+    const float dy = __fsub_rn(cy, 0.5f), dx = __fsub_rn(cx, 0.5f);
+    f[15] = nan_to_num(__fdiv_rn(
+        __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx))), 0.707f));
+    if (centroids) { centroids[(size_t)(no + i) * 2] = cy; centroids[(size_t)(no + i) * 2 + 1] = cx; }
+    if (areas) areas[no + i] = S(ST_AREA, i);
+  }
+}
+
+// ============================================================================ S7
+// Global colour contrast (graph_builder.py:405-412): one warp per region.
+__global__ void __launch_bounds__(256)
+k_prior_contrast(const float* __restrict__ st_all, const int* __restrict__ label_max,
+                 float* __restrict__ contrast_all, int node_cap, float inv_unused) {
+  const int b = blockIdx.y;
+  const int n = min(label_max[b] + 1, node_cap);
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
+  const float* mL = st + (size_t)ST_MEAN_L * node_cap;
+  const float* mA = mL + node_cap;
+  const float* mB = mA + node_cap;
+  const float* pcy = st + (size_t)ST_PCY * node_cap;
+  const float* pcx = st + (size_t)ST_PCX * node_cap;
+  const float* cnt = st + (size_t)ST_COUNT * node_cap;
+  // counts.sum() is exact in float32 (integers < 2^24); recompute it per warp
+  float tot = 0.0f;
+  for (int j = lane; j < n; j += 32) tot += cnt[j];
+  tot = fmaxf(warp_sum(tot), 1.0f);
+  const float two_sig2 = (float)(2 * 0.40 * 0.40);   // 2*contrast_sigma**2 as float32
+  const float li = mL[i], ai = mA[i], bi = mB[i], yi = pcy[i], xi = pcx[i];
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) {
+    const float dl = __fsub_rn(li, mL[j]), da = __fsub_rn(ai, mA[j]), db = __fsub_rn(bi, mB[j]);
+    const float cd = __fsqrt_rn(
+        __fadd_rn(__fadd_rn(__fmul_rn(dl, dl), __fmul_rn(da, da)), __fmul_rn(db, db)));
+    const float dy = __fsub_rn(yi, pcy[j]), dx = __fsub_rn(xi, pcx[j]);
+    const float sd = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+    const float sw = expf(__fdiv_rn(-__fmul_rn(sd, sd), two_sig2));
+    const float aw = __fdiv_rn(cnt[j], tot);
+    s += (double)__fmul_rn(__fmul_rn(cd, sw), aw);
+  }
+  s = warp_sum(s);
+  if (lane == 0) contrast_all[(size_t)b * node_cap + i] = (float)s;
+}
+
+// Block-wide unit-norm helpers: min and max of v over [0,n) strided by the block.
+template <typename F>
+GG_D void block_minmax(int n, F value, float* sred, float& mn, float& mx) {
+  const float INF = __int_as_float(0x7f800000);
+  float a = INF, z = -INF;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = value(i);
+    a = fminf(a, v);
+    z = fmaxf(z, v);
+  }
+  mn = block_reduce<float>(a, INF, OpMinF(), sred);
+  mx = block_reduce<float>(z, -INF, OpMaxF(), sred);
+}
+// _unit_norm (graph_builder.py:447-454): (v - mn) / float32(mx - mn), zeros if flat.
+GG_D float unit_norm_apply(float v, float mn, float mx) {
+  if ((double)mx - (double)mn < 1e-8) return 0.0f;
+  return __fdiv_rn(__fsub_rn(v, mn), (float)((double)mx - (double)mn));
+}
+
+// Centre prior, border colour model, ambiguity (graph_builder.py:414-444).
+__global__ void __launch_bounds__(256)
+k_prior_finish(const float* __restrict__ st_all, const int* __restrict__ label_max,
+               const float* __restrict__ contrast_all, float* __restrict__ tmp_all,
+               const int64_t* __restrict__ node_off, float* __restrict__ x, int node_cap) {
+  __shared__ float sred[32];
+  __shared__ double sredd[32];
+  const int b = blockIdx.x;
+  const int n = min(label_max[b] + 1, node_cap);
+  const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
+  auto S = [&](int f, int i) { return st[(size_t)f * node_cap + i]; };
+  const float* contrast = contrast_all + (size_t)b * node_cap;
+  float* fgv = tmp_all + (size_t)b * 2 * node_cap;   // fg-ness then bg-ness scratch
+  float* bgv = fgv + node_cap;
+  const int64_t no = node_off[b];
+  const float two_c2 = (float)(2 * 0.45 * 0.45);
+
+  float cmn, cmx;
+  block_minmax(n, [&](int i) { return contrast[i]; }, sred, cmn, cmx);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float cn = unit_norm_apply(contrast[i], cmn, cmx);
+    const float dy = __fsub_rn(S(ST_PCY, i), 0.5f), dx = __fsub_rn(S(ST_PCX, i), 0.5f);
+    const float cd = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+    const float cw = expf(__fdiv_rn(-__fmul_rn(cd, cd), two_c2));
+    fgv[i] = __fmul_rn(cn, cw);
+  }
+  __syncthreads();
+  float fmn, fmx;
+  block_minmax(n, [&](int i) { return fgv[i]; }, sred, fmn, fmx);
+
+  // border colour model
+  double bs = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) bs += (double)S(ST_BORDER, i);
+  bs = block_reduce<double>(bs, 0.0, OpAdd(), sredd);
+  const float bsum = (float)bs;   // exact: integer < 2^24
+  float mu[3] = {0.f, 0.f, 0.f};
+  float den = 1.0f;
+  if (bsum > 0.0f) {
+    double m[3] = {0, 0, 0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float w = __fdiv_rn(S(ST_BORDER, i), bsum);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) m[c] += (double)__fmul_rn(S(ST_MEAN_L + c, i), w);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mu[c] = (float)block_reduce<double>(m[c], 0.0, OpAdd(), sredd);
+    double v[3] = {0, 0, 0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float w = __fdiv_rn(S(ST_BORDER, i), bsum);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float d = __fsub_rn(S(ST_MEAN_L + c, i), mu[c]);
+        v[c] += (double)__fmul_rn(__fmul_rn(d, d), w);
+      }
+    }
+    float var = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      var = __fadd_rn(var, (float)block_reduce<double>(v[c], 0.0, OpAdd(), sredd));
+    // sigma_bg = float(np.sqrt(max(var_bg, 1e-6)))
+    const double sigma = ((double)var > 1e-6) ? (double)__fsqrt_rn(var) : sqrt(1e-6);
+    den = (float)(2.0 * (sigma + 1e-6) * (sigma + 1e-6));
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float bg = 0.0f;
+    if (bsum > 0.0f) {
+      const float dl = __fsub_rn(S(ST_MEAN_L, i), mu[0]), da = __fsub_rn(S(ST_MEAN_L + 1, i), mu[1]),
+                  db = __fsub_rn(S(ST_MEAN_L + 2, i), mu[2]);
+      const float d = __fsqrt_rn(
+          __fadd_rn(__fadd_rn(__fmul_rn(dl, dl), __fmul_rn(da, da)), __fmul_rn(db, db)));
+      bg = expf(__fdiv_rn(-__fmul_rn(d, d), den));
+    }
+    const float ratio = __fdiv_rn(S(ST_BORDER, i), S(ST_SAFE, i));
+    const float touch = fminf(fmaxf(__fmul_rn(ratio, 4.0f), 0.0f), 1.0f);
+    bgv[i] = fmaxf(bg, touch);
+  }
+  __syncthreads();
+  float bmn, bmx;
+  block_minmax(n, [&](int i) { return bgv[i]; }, sred, bmn, bmx);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float fg = unit_norm_apply(fgv[i], fmn, fmx);
+    const float bg = unit_norm_apply(bgv[i], bmn, bmx);
+    float* f = x + (size_t)(no + i) * GG_N_NODE_FEATS + GG_N_IMAGE_FEATS;
+    f[0] = nan_to_num(fg);
+    f[1] = nan_to_num(bg);
+    f[2] = nan_to_num(__fsub_rn(1.0f, fabsf(__fsub_rn(fg, bg))));
+  }
+}
+
+// ============================================================================ S8
+// Edge attributes + COO emission in the reference order (graph_builder.py:288-322).
+__global__ void __launch_bounds__(256)
+k_edge_attrs(const float* __restrict__ st_all, const int2* __restrict__ pairs_all,
+             const int* __restrict__ shared_all, const int* __restrict__ n_adj,
+             const int* __restrict__ n_nl, const int* __restrict__ max_shared,
+             const int64_t* __restrict__ edge_off, int64_t* __restrict__ edge_index,
+             int64_t edge_index_stride, float* __restrict__ edge_attr, int node_cap, int pair_cap) {
+  __shared__ float sred[32];
+  const int b = blockIdx.x;
+  const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
+  auto S = [&](int f, int i) { return st[(size_t)f * node_cap + i]; };
+  const int2* pairs = pairs_all + (size_t)b * pair_cap;
+  const int* shared = shared_all + (size_t)b * pair_cap;
+  const int na = n_adj[b], nn = n_nl[b], P = na + nn;
+  const int64_t eo = edge_off[b];
+
+  // pass 1: raw colour / centroid distances, parked in the forward rows; per-set maxima
+  float mde[2] = {0.f, 0.f}, mdx[2] = {0.f, 0.f};
+  for (int q = threadIdx.x; q < P; q += blockDim.x) {
+    const int i = pairs[q].x, j = pairs[q].y;
+    const float dl = __fsub_rn(S(ST_MEAN_L, i), S(ST_MEAN_L, j));
+    const float da = __fsub_rn(S(ST_MEAN_L + 1, i), S(ST_MEAN_L + 1, j));
+    const float db = __fsub_rn(S(ST_MEAN_L + 2, i), S(ST_MEAN_L + 2, j));
+    const float de = __fsqrt_rn(
+        __fadd_rn(__fadd_rn(__fmul_rn(dl, dl), __fmul_rn(da, da)), __fmul_rn(db, db)));
+    const float dy = __fsub_rn(S(ST_CY, i), S(ST_CY, j)), dx = __fsub_rn(S(ST_CX, i), S(ST_CX, j));
+    const float dxy = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+    float* r = edge_attr + (size_t)(eo + q) * GG_N_EDGE_FEATS;
+    r[0] = de;
+    r[1] = dxy;
+    const int set = q < na ? 0 : 1;
+    mde[set] = fmaxf(mde[set], de);
+    mdx[set] = fmaxf(mdx[set], dxy);
+  }
+  float den_de[2], den_dx[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    den_de[s] = __fadd_rn(block_reduce<float>(mde[s], 0.f, OpMaxF(), sred), 1e-6f);
+    den_dx[s] = __fadd_rn(block_reduce<float>(mdx[s], 0.f, OpMaxF(), sred), 1e-6f);
+  }
+  __syncthreads();
+  const double den_sh = (double)max_shared[b] + 1e-6;   // float64 division (…:286)
+  for (int q = threadIdx.x; q < P; q += blockDim.x) {
+    const int i = pairs[q].x, j = pairs[q].y;
+    const int set = q < na ? 0 : 1;
+    float* r = edge_attr + (size_t)(eo + q) * GG_N_EDGE_FEATS;
+    float* rr = edge_attr + (size_t)(eo + P + q) * GG_N_EDGE_FEATS;
+    const float a0 = __fdiv_rn(r[0], den_de[set]);
+    const float a1 = __fdiv_rn(r[1], den_dx[set]);
+    const float a2 = set == 0 ? (float)((double)(float)shared[q] / den_sh) : 0.0f;
+    const float a3 = fabsf(__fsub_rn(S(ST_MGRADN, i), S(ST_MGRADN, j)));
+    const float a4 = set == 0 ? 0.0f : 1.0f;
+    r[0] = a0; r[1] = a1; r[2] = a2; r[3] = a3; r[4] = a4;
+    rr[0] = a0; rr[1] = a1; rr[2] = a2; rr[3] = a3; rr[4] = a4;
+    edge_index[eo + q] = i;
+    edge_index[edge_index_stride + eo + q] = j;
+    edge_index[eo + P + q] = j;
+    edge_index[edge_index_stride + eo + P + q] = i;
+  }
+}
+
+// ============================================================================ S9
+// Destination-sorted CSR over the directed edges, global ids (consumed by the network).
+__global__ void __launch_bounds__(512)
+k_csr(const int2* __restrict__ pairs_all, const int* __restrict__ n_adj,
+      const int* __restrict__ n_nl, const int* __restrict__ label_max,
+      const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off,
+      int* __restrict__ cursor_all, int32_t* __restrict__ rowptr, int32_t* __restrict__ csr_src,
+      int32_t* __restrict__ csr_eid, int node_cap, int pair_cap, int B) {
+  __shared__ int scratch[40];
+  const int b = blockIdx.x;
+  const int n = min(label_max[b] + 1, node_cap);
+  const int2* pairs = pairs_all + (size_t)b * pair_cap;
+  const int P = n_adj[b] + n_nl[b];
+  const int64_t no = node_off[b], eo = edge_off[b];
+  int* cursor = cursor_all + (size_t)b * node_cap;
+  int32_t* rp = rowptr + no;
+
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { rp[i] = 0; cursor[i] = 0; }
+  __syncthreads();
+  for (int q = threadIdx.x; q < P; q += blockDim.x) {
+    atomicAdd(&rp[pairs[q].x], 1);
+    atomicAdd(&rp[pairs[q].y], 1);
+  }
+  __syncthreads();
+  int carry = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < n) ? rp[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, scratch, &total);
+    __syncthreads();
+    if (i < n) rp[i] = (int)eo + carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (b == B - 1 && threadIdx.x == 0) rp[n] = (int)eo + carry;   // rowptr[total nodes]
+  __syncthreads();
+  for (int q = threadIdx.x; q < P; q += blockDim.x) {
+    const int lo = pairs[q].x, hi = pairs[q].y;
+    int pos = rp[hi] + atomicAdd(&cursor[hi], 1);      // edge lo -> hi  (forward row q)
+    csr_src[pos] = (int)no + lo;
+    csr_eid[pos] = (int)eo + q;
+    pos = rp[lo] + atomicAdd(&cursor[lo], 1);          // edge hi -> lo  (reversed row P+q)
+    csr_src[pos] = (int)no + hi;
+    csr_eid[pos] = (int)eo + P + q;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int s0 = rp[i], s1 = s0 + cursor[i];
+    for (int a = s0 + 1; a < s1; ++a) {
+      const int sv = csr_src[a], ev = csr_eid[a];
+      int j = a - 1;
+      while (j >= s0 && csr_src[j] > sv) {
+        csr_src[j + 1] = csr_src[j];
+        csr_eid[j + 1] = csr_eid[j];
+        --j;
+      }
+      csr_src[j + 1] = sv;
+      csr_eid[j + 1] = ev;
+    }
+  }
+}
+
+// ============================================================================ debug planes
+// GraphBuilder.__init__ planes (_lab, _hsv, _gray, _grad) for parity tests.
+__global__ void k_pixel_planes(const uint8_t* __restrict__ bgr, const double* __restrict__ lin_lut,
+                               LabMatrix lab, int H, int W, float* __restrict__ o_lab,
+                               float* __restrict__ o_hsv, float* __restrict__ o_gray,
+                               float* __restrict__ o_grad) {
+  __shared__ double s_lin[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lin[i] = lin_lut[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)H * W) return;
+  const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+  const uint8_t* img = bgr + (size_t)b * H * W * 3;
+  const uint8_t* px = img + i * 3;
+  const size_t o = (size_t)b * H * W + i;
+  float L, A, Bv, hh, ss, vv;
+  bgr_to_lab(s_lin, lab.m, px[0], px[1], px[2], L, A, Bv);
+  bgr_to_hsv(px[0], px[1], px[2], hh, ss, vv);
+  if (o_lab) { o_lab[o * 3] = L; o_lab[o * 3 + 1] = A; o_lab[o * 3 + 2] = Bv; }
+  if (o_hsv) { o_hsv[o * 3] = hh; o_hsv[o * 3 + 1] = ss; o_hsv[o * 3 + 2] = vv; }
+  auto G = [&](int yy, int xx) {
+    const uint8_t* q = img + ((size_t)reflect101(yy, H) * W + reflect101(xx, W)) * 3;
+    return gray_u8(q[0], q[1], q[2]);
+  };
+  if (o_gray) o_gray[o] = (float)G(y, x);
+  if (o_grad) {
+    const int gx = (G(y - 1, x + 1) + 2 * G(y, x + 1) + G(y + 1, x + 1)) -
+                   (G(y - 1, x - 1) + 2 * G(y, x - 1) + G(y + 1, x - 1));
+    const int gy = (G(y + 1, x - 1) + 2 * G(y + 1, x) + G(y + 1, x + 1)) -
+                   (G(y - 1, x - 1) + 2 * G(y - 1, x) + G(y - 1, x + 1));
+    o_grad[o] = __fsqrt_rn((float)(gx * gx + gy * gy));
+  }
+}
+
+// ============================================================================ host driver
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+size_t graph_workspace_bytes(int B, int H, int W, const gg_graph_config& cfg) {
+  const int nc = cfg.node_cap, pc = cfg.pair_cap, tc = next_pow2(4 * pc);
+  const int k = cfg.n_nonlocal > 0 ? cfg.n_nonlocal : 1;
+  size_t s = 0;
+  s += Arena::padded((size_t)B * H * W, 1);                 // gray
+  s += Arena::padded(2 * (size_t)(H + W), 8);               // coord tables
+  s += Arena::padded((size_t)B * nc * 16, 8);               // acc
+  s += Arena::padded((size_t)B * tc, 8);                    // pair keys
+  s += Arena::padded((size_t)B * tc, 4);                    // pair counts
+  s += Arena::padded((size_t)B * 4, 4) * 6;                 // per-image ints
+  s += Arena::padded((size_t)B * ST_FIELDS * nc, 4);        // stats
+  s += Arena::padded((size_t)B * pc, 8);                    // pairs
+  s += Arena::padded((size_t)B * pc, 4);                    // shared counts
+  s += Arena::padded((size_t)B * (nc + 1), 4) * 2;          // start arrays (adj, nl)
+  s += Arena::padded((size_t)B * nc, 4);                    // cursor
+  s += Arena::padded((size_t)B * nc * k, 4);                // picks
+  s += Arena::padded((size_t)B * nc, 4) * 3;                // contrast + 2 tmp
+  return s + 4096;
+}
+
+template <int K>
+static int launch_knn(gg_context* ctx, cudaStream_t st, dim3 grid, const float* stats,
+                      const int* label_max, const int2* pairs, const int* start, int* picks,
+                      int node_cap, int pair_cap, int k) {
+  GG_LAUNCH(ctx, k_knn<K>, grid, 256, 0, st, stats, label_max, pairs, start, picks, node_cap,
+            pair_cap, k);
+  return GG_OK;
+}
+
+int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* labels, int B,
+                 int H, int W, const gg_graph_config& cfg_in, const gg_graph_out& out,
+                 cudaStream_t st, const uint8_t** gray_out) {
+  gg_graph_config cfg = cfg_in;
+  if (cfg.pair_cap <= 0) cfg.pair_cap = 8 * cfg.node_cap;
+  GG_REQUIRE(B > 0 && H >= 2 && W >= 2, "build_graphs: need B>0, H,W>=2 (got %d,%d,%d)", B, H, W);
+  GG_REQUIRE((long long)H * W < (1ll << 24), "build_graphs: H*W must be < 2^24");
+  GG_REQUIRE(cfg.connectivity == 4 || cfg.connectivity == 8, "connectivity must be 4 or 8");
+  GG_REQUIRE(cfg.n_nonlocal >= 0 && cfg.n_nonlocal <= 32, "n_nonlocal must be in [0,32]");
+  GG_REQUIRE(cfg.node_cap > 0, "node_cap must be > 0");
+  GG_REQUIRE(out.n_nodes && out.n_edges && out.node_off && out.edge_off && out.x &&
+                 out.edge_index && out.edge_attr && out.csr_rowptr && out.csr_src && out.csr_eid,
+             "build_graphs: a mandatory output pointer is NULL");
+  GG_REQUIRE((long long)B * 2 * cfg.pair_cap < (1ll << 31) && (long long)B * cfg.node_cap < (1ll << 31),
+             "build_graphs: batch too large for 32-bit CSR ids");
+  const int nc = cfg.node_cap, pc = cfg.pair_cap, tc = next_pow2(4 * pc);
+  const int k = cfg.n_nonlocal;
+
+  uint8_t* gray = ar.take<uint8_t>((size_t)B * H * W);
+  double* coord = ar.take<double>(2 * (size_t)(H + W));
+  const double* lin = ctx->d_lin;
+  double* acc = ar.take<double>((size_t)B * nc * 16);
+  unsigned long long* pkeys = ar.take<unsigned long long>((size_t)B * tc);
+  int* pcnts = ar.take<int>((size_t)B * tc);
+  int* gradmax = ar.take<int>((size_t)B * 4);
+  int* label_max = ar.take<int>((size_t)B * 4);
+  int* n_adj = ar.take<int>((size_t)B * 4);
+  int* n_nl = ar.take<int>((size_t)B * 4);
+  int* max_shared = ar.take<int>((size_t)B * 4);
+  (void)ar.take<int>((size_t)B * 4);
+  float* stats = ar.take<float>((size_t)B * ST_FIELDS * nc);
+  int2* pairs = ar.take<int2>((size_t)B * pc);
+  int* shared = ar.take<int>((size_t)B * pc);
+  int* start_adj = ar.take<int>((size_t)B * (nc + 1));
+  int* start_nl = ar.take<int>((size_t)B * (nc + 1));
+  int* cursor = ar.take<int>((size_t)B * nc);
+  int* picks = ar.take<int>((size_t)B * nc * (k > 0 ? k : 1));
+  float* contrast = ar.take<float>((size_t)B * nc);
+  float* tmp2 = ar.take<float>((size_t)B * nc * 2);
+  if (gray_out) *gray_out = gray;
+
+  GG_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)B * nc * 16 * sizeof(double), st));
+  GG_CUDA_OK(cudaMemsetAsync(pkeys, 0xFF, (size_t)B * tc * sizeof(unsigned long long), st));
+  GG_CUDA_OK(cudaMemsetAsync(pcnts, 0, (size_t)B * tc * sizeof(int), st));
+  GG_CUDA_OK(cudaMemsetAsync(gradmax, 0, (size_t)B * 4 * sizeof(int), st));
+  GG_CUDA_OK(cudaMemsetAsync(label_max, 0xFF, (size_t)B * 4 * sizeof(int), st));
+  GG_CUDA_OK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));
+
+  {
+    dim3 grid(ceil_div(W, K0_TX), ceil_div(H, K0_TY), B);
+    GG_LAUNCH(ctx, k_gray_gradmax, grid, 256, 0, st, bgr, gray, gradmax, H, W);
+    GG_LAUNCH(ctx, k_coord_tables, ceil_div(H > W ? H : W, 256), 256, 0, st, coord, H, W);
+  }
+  {
+    RegionStatsParams p;
+    p.bgr = bgr; p.gray = gray; p.labels = labels; p.gradmax_sq = gradmax; p.coord = coord;
+    p.lin_lut = lin; p.acc = acc; p.label_max = label_max; p.pair_keys = pkeys;
+    p.pair_cnts = pcnts; p.status = ctx->d_status; p.B = B; p.H = H; p.W = W; p.node_cap = nc;
+    p.table_cap = tc; p.connectivity = cfg.connectivity;
+    p.n_sx = ceil_div(W, 32); p.n_sy = ceil_div(H, RS_ROWS);
+    p.lab = make_lab_matrix();
+    const long long tasks = (long long)B * p.n_sx * p.n_sy;
+    GG_CUDA_OK(cudaFuncSetAttribute(k_region_stats, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)RS_SMEM_BYTES));
+    GG_LAUNCH(ctx, k_region_stats, ceil_div(tasks, RS_WARPS), RS_WARPS * 32, RS_SMEM_BYTES, st, p);
+  }
+  {
+    dim3 grid(ceil_div(nc, 256), B);
+    GG_LAUNCH(ctx, k_finalize_regions, grid, 256, 0, st, acc, label_max, stats, B, H, W, nc);
+  }
+  GG_LAUNCH(ctx, k_adj_sort, B, 512, 0, st, pkeys, pcnts, label_max, pairs, shared, start_adj,
+            cursor, n_adj, max_shared, ctx->d_status, nc, tc, pc);
+  if (k > 0) {
+    dim3 grid(ceil_div(nc, 8), B);
+    if (k <= 4) GG_TRY(launch_knn<4>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
+    else if (k <= 8) GG_TRY(launch_knn<8>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
+    else if (k <= 16) GG_TRY(launch_knn<16>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
+    else GG_TRY(launch_knn<32>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
+  }
+  GG_LAUNCH(ctx, k_nl_pairs, B, 512, 0, st, picks, label_max, n_adj, pairs, start_nl, cursor, n_nl,
+            ctx->d_status, nc, pc, k);
+  GG_LAUNCH(ctx, k_offsets, 1, 1024, 0, st, label_max, n_adj, n_nl, B, nc, out.n_nodes,
+            out.n_edges, out.node_off, out.edge_off, out.n_adj_pairs, out.n_nl_pairs);
+  GG_LAUNCH(ctx, k_node_features, B, 256, 0, st, stats, label_max, out.node_off, out.x,
+            out.centroids, out.areas, nc);
+  {
+    dim3 grid(ceil_div(nc, 8), B);
+    GG_LAUNCH(ctx, k_prior_contrast, grid, 256, 0, st, stats, label_max, contrast, nc, 0.0f);
+  }
+  GG_LAUNCH(ctx, k_prior_finish, B, 256, 0, st, stats, label_max, contrast, tmp2, out.node_off,
+            out.x, nc);
+  GG_LAUNCH(ctx, k_edge_attrs, B, 256, 0, st, stats, pairs, shared, n_adj, n_nl, max_shared,
+            out.edge_off, out.edge_index, (int64_t)2 * B * pc, out.edge_attr, nc, pc);
+  GG_LAUNCH(ctx, k_csr, B, 512, 0, st, pairs, n_adj, n_nl, label_max, out.node_off, out.edge_off,
+            cursor, out.csr_rowptr, out.csr_src, out.csr_eid, nc, pc, B);
+  if (out.shared_cnt)
+    GG_CUDA_OK(cudaMemcpyAsync(out.shared_cnt, shared, (size_t)B * pc * sizeof(int),
+                               cudaMemcpyDeviceToDevice, st));
+  return GG_OK;
+}
+
+int pixel_planes(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, int W, float* lab,
+                 float* hsv, float* gray, float* grad, cudaStream_t st) {
+  (void)ar;
+  const double* lin = ctx->d_lin;
+  dim3 grid(ceil_div((long long)H * W, 256), B);
+  GG_LAUNCH(ctx, k_pixel_planes, grid, 256, 0, st, bgr, lin, make_lab_matrix(), H, W, lab, hsv,
+            gray, grad);
+  return GG_OK;
+}
+
+}  // namespace gg

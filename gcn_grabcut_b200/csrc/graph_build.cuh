@@ -1,0 +1,29 @@
+// Internal interface of graph_build.cu
+#pragma once
+#include "common.cuh"
+
+namespace gg {
+
+// per-region statistics, struct-of-arrays [B][ST_FIELDS][node_cap] (float32)
+enum : int {
+  ST_COUNT = 0, ST_SAFE,
+  ST_MEAN_L, ST_MEAN_A, ST_MEAN_B,
+  ST_STD_L, ST_STD_A, ST_STD_B,
+  ST_MEAN_H, ST_MEAN_S, ST_MEAN_V,
+  ST_CY, ST_CX, ST_BND, ST_AREA, ST_MGRAD, ST_MGRADN,
+  ST_PCY, ST_PCX, ST_BORDER,
+  ST_FIELDS
+};
+
+size_t graph_workspace_bytes(int B, int H, int W, const gg_graph_config& cfg);
+
+// gray_out (optional): receives the device pointer of the uint8 grey plane [B,H,W] that
+// the builder produced inside `ar` (re-used by the trimap stage).
+int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* labels, int B,
+                 int H, int W, const gg_graph_config& cfg, const gg_graph_out& out,
+                 cudaStream_t st, const uint8_t** gray_out);
+
+int pixel_planes(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, int W, float* lab,
+                 float* hsv, float* gray, float* grad, cudaStream_t st);
+
+}  // namespace gg

@@ -1,0 +1,724 @@
+// ResGCNNet forward (eval mode, fp32 semantics) over a batch of region graphs.
+//
+// Replaces model.py:449-546 of the reference (ResGCNNet.forward / predict_probs) together
+// with the PyG GCNConv / SAGEConv layers it calls and the helpers _scatter_mean,
+// _graph_softmax, EdgeContext, GlobalContextModule, InputNorm (model.py:69-213).
+//
+// Layout: all node tensors are row-major [nodes, D] fp32 over the whole batch (ragged,
+// graph g owns rows [graph_off[g], graph_off[g+1])); message passing walks the
+// destination-sorted CSR (no atomics, deterministic summation order); the dense per-node
+// transforms go through gemm() -- tcgen05 tensor cores (bf16x3 split, fp32 accumulate in
+// TMEM; gemm_tc.cu) or the SIMT fp32 kernel below (validation path).
+//
+// Row counts are only known on the device: every kernel reads sizes[0] = total nodes,
+// sizes[1] = total directed edges and is launched for the capacity.
+#include "common.cuh"
+#include "resgcn.cuh"
+
+namespace gg {
+
+GG_D float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+GG_D float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void k_sizes(const int64_t* __restrict__ graph_off, int n_graphs,
+                        const int32_t* __restrict__ rowptr, int* __restrict__ sizes,
+                        long long node_cap, long long edge_cap, int* status) {
+  long long nt = graph_off[n_graphs];
+  if (nt > node_cap) { nt = node_cap; atomicOr(status, ST_EDGE_CAP); }
+  long long et = nt > 0 ? rowptr[nt] : 0;
+  if (et > edge_cap) { et = edge_cap; atomicOr(status, ST_EDGE_CAP); }
+  sizes[0] = (int)nt;
+  sizes[1] = (int)et;
+}
+
+// node -> graph id, and GCN normalisation dinv[v] = (1 + #in-edges with src != v)^-1/2
+__global__ void k_node_meta(const int64_t* __restrict__ graph_off, int n_graphs,
+                            const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
+                            const int* __restrict__ sizes, int* __restrict__ node_graph,
+                            float* __restrict__ dinv) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= sizes[0]) return;
+  int lo = 0, hi = n_graphs;            // last g with graph_off[g] <= v
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (graph_off[mid] <= v) lo = mid; else hi = mid;
+  }
+  node_graph[v] = lo;
+  int deg = 1;
+  for (int e = rowptr[v]; e < rowptr[v + 1]; ++e) deg += (src[e] != v);
+  dinv[v] = 1.0f / sqrtf((float)deg);
+}
+
+// ------------------------------------------------------------------ input stage
+// h = GELU(LN(W_in BN(x) + b)) * (1 + sigmoid(W2 GELU(W1 prior + b1) + b2)); z = w0 h
+// (model.py:516-518, 191-213, 465-476).  One warp per node, lane owns channels lane+32j.
+template <int CPL>   // channels per lane = D/32
+__global__ void __launch_bounds__(256)
+k_input_stage(const float* __restrict__ x, const float* __restrict__ wb, NetOffsets o,
+              const int* __restrict__ sizes, float* __restrict__ h, float* __restrict__ z) {
+  extern __shared__ float sw[];
+  const int D = CPL * 32, q = o.q;
+  float* s_win = sw;                    // [D][19]
+  float* s_pb0 = s_win + D * 19;        // [q][3]
+  float* s_pb2 = s_pb0 + q * 3;         // [q][D] (transposed: conflict-free across lanes)
+  for (int i = threadIdx.x; i < D * 19; i += blockDim.x) s_win[i] = wb[o.w_in + i];
+  for (int i = threadIdx.x; i < q * 3; i += blockDim.x) s_pb0[i] = wb[o.pb0_w + i];
+  for (int i = threadIdx.x; i < D * q; i += blockDim.x) s_pb2[(i % q) * D + i / q] = wb[o.pb2_w + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int nt = sizes[0];
+  const float jk0 = wb[o.jk_w];
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nt; v += warps) {
+    float xv = 0.0f, xraw = 0.0f;
+    if (lane < 19) {
+      xraw = x[(size_t)v * 19 + lane];
+      xv = xraw * wb[o.bn_scale + lane] + wb[o.bn_shift + lane];
+    }
+    float t[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) t[j] = wb[o.b_in + lane + 32 * j];
+    for (int kk = 0; kk < 19; ++kk) {
+      const float xk = __shfl_sync(0xffffffffu, xv, kk);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) t[j] = fmaf(s_win[(lane + 32 * j) * 19 + kk], xk, t[j]);
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) sum += t[j];
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { const float d = t[j] - mean; sq += d * d; }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + 1e-5f);
+    // prior booster: q hidden units, lane owns units lane, lane+32, ...
+    const float p0 = __shfl_sync(0xffffffffu, xraw, 16), p1 = __shfl_sync(0xffffffffu, xraw, 17),
+                p2 = __shfl_sync(0xffffffffu, xraw, 18);
+    float boost[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) boost[j] = wb[o.pb2_b + lane + 32 * j];
+    for (int u0 = 0; u0 < q; u0 += 32) {
+      const int u = u0 + lane;
+      float hu = 0.0f;
+      if (u < q)
+        hu = gelu_erf(fmaf(s_pb0[u * 3 + 2], p2, fmaf(s_pb0[u * 3 + 1], p1,
+                      fmaf(s_pb0[u * 3], p0, wb[o.pb0_b + u]))));
+      const int lim = min(32, q - u0);
+      for (int s = 0; s < lim; ++s) {
+        const float hs = __shfl_sync(0xffffffffu, hu, s);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) boost[j] = fmaf(s_pb2[(u0 + s) * D + lane + 32 * j], hs, boost[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int c = lane + 32 * j;
+      const float ln = (t[j] - mean) * rstd * wb[o.ln_in_g + c] + wb[o.ln_in_b + c];
+      const float hv = gelu_erf(ln) * (1.0f + sigmoidf(boost[j]));
+      h[(size_t)v * D + c] = hv;
+      z[(size_t)v * D + c] = jk0 * hv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ edge context
+// e1 = GELU(W0 attr + b0)  [E, c]   (model.py:124-128, first layer; K = 5)
+__global__ void k_edge_enc1(const float* __restrict__ attr, const float* __restrict__ wb,
+                            NetOffsets o, const int* __restrict__ sizes, float* __restrict__ e1) {
+  const int c = o.c;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)sizes[1] * c;
+  if (i >= total) return;
+  const int e = (int)(i / c), u = (int)(i - (long long)e * c);
+  const float* a = attr + (size_t)e * 5;
+  const float* w = wb + o.ee0_w + (size_t)u * 5;
+  float s = wb[o.ee0_b + u];
+#pragma unroll
+  for (int kk = 0; kk < 5; ++kk) s = fmaf(w[kk], a[kk], s);
+  e1[i] = gelu_erf(s);
+}
+
+// ctx_v = LN_c(mean_{e: dst = v} enc_e)   (model.py:69-74, 129-139); warp per node
+__global__ void __launch_bounds__(256)
+k_edge_ctx(const float* __restrict__ enc, const int32_t* __restrict__ rowptr,
+           const int32_t* __restrict__ eid, const float* __restrict__ wb, NetOffsets o,
+           const int* __restrict__ sizes, float* __restrict__ ctx) {
+  const int c = o.c, lane = threadIdx.x & 31;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= sizes[0]) return;
+  const int e0 = rowptr[v], e1 = rowptr[v + 1];
+  const float inv = 1.0f / (float)max(e1 - e0, 1);
+  // c <= 256: up to 8 channels per lane
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  for (int e = e0; e < e1; ++e) {
+    const float* row = enc + (size_t)eid[e] * c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int ch = lane + 32 * j; if (ch < c) acc[j] += row[ch]; }
+  }
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[j] *= inv; if (lane + 32 * j < c) sum += acc[j]; }
+  const float mean = warp_sum(sum) / (float)c;
+  float sq = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) if (lane + 32 * j < c) { const float d = acc[j] - mean; sq += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)c + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < c) ctx[(size_t)v * c + ch] = (acc[j] - mean) * rstd * wb[o.eg_ln_g + ch] + wb[o.eg_ln_b + ch];
+  }
+}
+
+// ------------------------------------------------------------------ row LayerNorm
+// out = LN(in [* scale_rows[node_graph]]) with affine (g, b); warp per row.
+template <int CPL>
+__global__ void __launch_bounds__(256)
+k_layernorm(const float* __restrict__ in, const float* __restrict__ g, const float* __restrict__ bta,
+            const float* __restrict__ gvec, const int* __restrict__ node_graph,
+            const int* __restrict__ sizes, float* __restrict__ out) {
+  constexpr int D = CPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= sizes[0]) return;
+  float t[CPL];
+  const float* gv = gvec ? gvec + (size_t)node_graph[v] * D : nullptr;
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    t[j] = in[(size_t)v * D + lane + 32 * j];
+    if (gv) t[j] *= gv[lane + 32 * j];
+    sum += t[j];
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.0f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { const float d = t[j] - mean; sq += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    out[(size_t)v * D + c] = (t[j] - mean) * rstd * g[c] + bta[c];
+  }
+}
+
+// ------------------------------------------------------------------ GCN aggregation
+// u_v = sum_{j in N(v), j != v} dinv_v dinv_j xw_j + dinv_v^2 xw_v + bias
+// h_v += GELU(u_v * gate_v);  z_v += w_l h_v          (model.py:523-528; GCNConv defaults)
+template <int CPL>
+__global__ void __launch_bounds__(256)
+k_gcn_aggregate(const float* __restrict__ xw, const int32_t* __restrict__ rowptr,
+                const int32_t* __restrict__ src, const float* __restrict__ dinv,
+                const float* __restrict__ bias, const float* __restrict__ gate, float jkw,
+                const int* __restrict__ sizes, float* __restrict__ h, float* __restrict__ z) {
+  constexpr int D = CPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= sizes[0]) return;
+  const float dv = dinv[v];
+  float acc[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) acc[j] = dv * dv * xw[(size_t)v * D + lane + 32 * j];
+  for (int e = rowptr[v]; e < rowptr[v + 1]; ++e) {
+    const int s = src[e];
+    if (s == v) continue;
+    const float w = dv * dinv[s];
+    const float* row = xw + (size_t)s * D;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) acc[j] = fmaf(w, row[lane + 32 * j], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const size_t idx = (size_t)v * D + lane + 32 * j;
+    const float u = acc[j] + bias[lane + 32 * j];
+    const float hv = h[idx] + gelu_erf(u * gate[idx]);
+    h[idx] = hv;
+    z[idx] += jkw * hv;
+  }
+}
+
+// SAGE mean aggregation: m_v = mean_{j -> v} h_j (self loops kept, empty -> 0)
+template <int CPL>
+__global__ void __launch_bounds__(256)
+k_sage_mean(const float* __restrict__ h, const int32_t* __restrict__ rowptr,
+            const int32_t* __restrict__ src, const int* __restrict__ sizes, float* __restrict__ m) {
+  constexpr int D = CPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= sizes[0]) return;
+  const int e0 = rowptr[v], e1 = rowptr[v + 1];
+  float acc[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) acc[j] = 0.0f;
+  for (int e = e0; e < e1; ++e) {
+    const float* row = h + (size_t)src[e] * D;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) acc[j] += row[lane + 32 * j];
+  }
+  const float inv = 1.0f / (float)max(e1 - e0, 1);
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) m[(size_t)v * D + lane + 32 * j] = acc[j] * inv;
+}
+
+// s = GELU(LN(t)); z += w s      (model.py:530-533)
+template <int CPL>
+__global__ void __launch_bounds__(256)
+k_sage_finish(const float* __restrict__ t_in, const float* __restrict__ g, const float* __restrict__ bta,
+              float jkw, const int* __restrict__ sizes, float* __restrict__ z) {
+  constexpr int D = CPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= sizes[0]) return;
+  float t[CPL];
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { t[j] = t_in[(size_t)v * D + lane + 32 * j]; sum += t[j]; }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.0f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { const float d = t[j] - mean; sq += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = lane + 32 * j;
+    const float s = gelu_erf((t[j] - mean) * rstd * g[c] + bta[c]);
+    z[(size_t)v * D + c] += jkw * s;
+  }
+}
+
+// ------------------------------------------------------------------ global context
+// One block per graph: a = softmax_graph(u.z + c); g = sum a_i z_i;
+// gvec = sigmoid(W_e relu(W_c g + b_c) + b_e)          (model.py:165-188, 90-108)
+__global__ void __launch_bounds__(256)
+k_graph_context(const float* __restrict__ z, const int64_t* __restrict__ graph_off,
+                const float* __restrict__ wb, NetOffsets o, int n_graphs,
+                float* __restrict__ score, float* __restrict__ gvec) {
+  extern __shared__ float sm[];
+  const int D = o.D, Dh = D / 2;
+  float* s_g = sm;            // [D]
+  float* s_c = sm + D;        // [Dh]
+  __shared__ float sred[32];
+  const int g = blockIdx.x;
+  const int v0 = (int)graph_off[g], v1 = (int)graph_off[g + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float INF = __int_as_float(0x7f800000);
+  // scores
+  float mx = -INF;
+  for (int v = v0 + wid; v < v1; v += nw) {
+    float s = 0.0f;
+    for (int c = lane; c < D; c += 32) s = fmaf(wb[o.attn_w + c], z[(size_t)v * D + c], s);
+    s = warp_sum(s) + wb[o.attn_b];
+    if (lane == 0) score[v] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_reduce<float>(mx, -INF, OpMaxF(), sred);
+  __syncthreads();
+  float tot = 0.0f;
+  for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+    const float e = expf(score[v] - mx);
+    score[v] = e;
+    tot += e;
+  }
+  tot = block_reduce<float>(tot, 0.0f, OpAdd(), sred);
+  const float inv = 1.0f / (n_graphs > 1 ? tot + 1e-12f : tot);
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float a = 0.0f;
+    for (int v = v0; v < v1; ++v) a = fmaf(score[v] * inv, z[(size_t)v * D + c], a);
+    s_g[c] = a;
+  }
+  __syncthreads();
+  for (int u = wid; u < Dh; u += nw) {
+    float s = 0.0f;
+    for (int c = lane; c < D; c += 32) s = fmaf(wb[o.cmp_w + (size_t)u * D + c], s_g[c], s);
+    s = warp_sum(s);
+    if (lane == 0) s_c[u] = fmaxf(s + wb[o.cmp_b + u], 0.0f);
+  }
+  __syncthreads();
+  for (int c = wid; c < D; c += nw) {
+    float s = 0.0f;
+    for (int u = lane; u < Dh; u += 32) s = fmaf(wb[o.exp_w + (size_t)c * Dh + u], s_c[u], s);
+    s = warp_sum(s);
+    if (lane == 0) gvec[(size_t)g * D + c] = sigmoidf(s + wb[o.exp_b + c]);
+  }
+}
+
+// ------------------------------------------------------------------ head
+// logits = W_h f + b_h; probs = softmax(logits)   (model.py:536, 543-546); warp per node
+__global__ void __launch_bounds__(256)
+k_head(const float* __restrict__ f, const float* __restrict__ wb, NetOffsets o,
+       const int* __restrict__ sizes, float* __restrict__ logits, float* __restrict__ probs) {
+  const int D = o.D, lane = threadIdx.x & 31;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= sizes[0]) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float fv = f[(size_t)v * D + c];
+    s0 = fmaf(wb[o.head_w + c], fv, s0);
+    s1 = fmaf(wb[o.head_w + D + c], fv, s1);
+    s2 = fmaf(wb[o.head_w + 2 * D + c], fv, s2);
+  }
+  s0 = warp_sum(s0) + wb[o.head_b];
+  s1 = warp_sum(s1) + wb[o.head_b + 1];
+  s2 = warp_sum(s2) + wb[o.head_b + 2];
+  if (lane == 0) {
+    if (logits) { logits[(size_t)v * 3] = s0; logits[(size_t)v * 3 + 1] = s1; logits[(size_t)v * 3 + 2] = s2; }
+    if (probs) {
+      const float m = fmaxf(s0, fmaxf(s1, s2));
+      const float e0 = expf(s0 - m), e1 = expf(s1 - m), e2 = expf(s2 - m);
+      const float inv = 1.0f / (e0 + e1 + e2);
+      probs[(size_t)v * 3] = e0 * inv; probs[(size_t)v * 3 + 1] = e1 * inv; probs[(size_t)v * 3 + 2] = e2 * inv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ SIMT fp32 GEMM (validation path)
+// C[M,N] (+)= act(A[M,K] W[N,K]^T + bias).  64x64 tiles, 256 threads, 4x4 micro-tiles.
+template <int ACT>   // 0 none, 1 gelu, 2 sigmoid
+__global__ void __launch_bounds__(256)
+k_gemm_simt(const float* __restrict__ A, const float* __restrict__ Wt, const float* __restrict__ bias,
+            float* __restrict__ C, const int* __restrict__ m_ptr, int N, int K, int accumulate) {
+  __shared__ float sA[16][64 + 4];
+  __shared__ float sB[16][64 + 4];
+  const int M = *m_ptr;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  if (m0 >= M) return;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, kk = i & 15;
+      const int m = m0 + r, n = n0 + r, k = k0 + kk;
+      sA[kk][r] = (m < M && k < K) ? A[(size_t)m * K + k] : 0.0f;
+      sB[kk][r] = (n < N && k < K) ? Wt[(size_t)n * K + k] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.0f);
+      if (accumulate) v += C[(size_t)m * N + n];
+      if (ACT == 1) v = gelu_erf(v);
+      if (ACT == 2) v = sigmoidf(v);
+      C[(size_t)m * N + n] = v;
+    }
+  }
+}
+
+int gemm_simt(gg_context* ctx, cudaStream_t st, const float* A, const float* W, const float* bias,
+              float* C, const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate) {
+  dim3 grid(ceil_div(m_cap, 64), ceil_div(N, 64));
+  if (act == 0) GG_LAUNCH(ctx, k_gemm_simt<0>, grid, 256, 0, st, A, W, bias, C, m_ptr, N, K, accumulate);
+  else if (act == 1) GG_LAUNCH(ctx, k_gemm_simt<1>, grid, 256, 0, st, A, W, bias, C, m_ptr, N, K, accumulate);
+  else GG_LAUNCH(ctx, k_gemm_simt<2>, grid, 256, 0, st, A, W, bias, C, m_ptr, N, K, accumulate);
+  return GG_OK;
+}
+
+int gemm(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* W,
+         const float* bias, float* C, const int* m_ptr, long long m_cap, int N, int K, int act,
+         int accumulate) {
+  if (ctx->gemm_impl == 1 && gemm_tc_supported(ctx, which, N, K))
+    return gemm_tc(ctx, st, which, A, bias, C, m_ptr, m_cap, N, K, act, accumulate);
+  return gemm_simt(ctx, st, A, W, bias, C, m_ptr, m_cap, N, K, act, accumulate);
+}
+
+// ------------------------------------------------------------------ weights
+static size_t push(std::vector<float>& blob, const float* p, size_t n) {
+  size_t off = blob.size();
+  off = (off + 3) & ~size_t(3);
+  blob.resize(off + n);
+  memcpy(blob.data() + off, p, n * sizeof(float));
+  return off;
+}
+
+int load_weights(gg_context* ctx, const gg_resgcn_weights* w) {
+  GG_REQUIRE(w != nullptr, "load_weights: null");
+  const int D = w->hidden, n = w->n_layers;
+  GG_REQUIRE(D >= 32 && D <= 256 && D % 32 == 0, "load_weights: hidden must be a multiple of 32 in [32,256] (got %d)", D);
+  GG_REQUIRE(n >= 0 && n <= 64, "load_weights: n_layers out of range");
+  NetWeights& nw = ctx->net;
+  nw.loaded = false;
+  nw.D = D; nw.n_layers = n; nw.q = D / 4 > 8 ? D / 4 : 8; nw.c = D / 2 > 8 ? D / 2 : 8;
+  const int q = nw.q, c = nw.c;
+  std::vector<float> blob;
+  // softmax(jk_logits)   (model.py:532)
+  {
+    std::vector<float> jk(n + 2);
+    float mx = -1e30f;
+    for (int i = 0; i < n + 2; ++i) mx = fmaxf(mx, w->jk_logits[i]);
+    float tot = 0.f;
+    for (int i = 0; i < n + 2; ++i) { jk[i] = expf(w->jk_logits[i] - mx); tot += jk[i]; }
+    for (int i = 0; i < n + 2; ++i) jk[i] /= tot;
+    nw.jk_w = push(blob, jk.data(), n + 2);
+  }
+  // eval BatchNorm folded to scale/shift (model.py:191-213; eps 1e-5)
+  {
+    float sc[19], sh[19];
+    for (int i = 0; i < 19; ++i) {
+      sc[i] = w->in_norm_weight[i] / sqrtf(w->in_norm_var[i] + 1e-5f);
+      sh[i] = w->in_norm_bias[i] - w->in_norm_mean[i] * sc[i];
+    }
+    nw.bn_scale = push(blob, sc, 19);
+    nw.bn_shift = push(blob, sh, 19);
+  }
+  nw.w_in = push(blob, w->input_proj_0_weight, (size_t)D * 19);
+  nw.b_in = push(blob, w->input_proj_0_bias, D);
+  nw.ln_in_g = push(blob, w->input_proj_1_weight, D);
+  nw.ln_in_b = push(blob, w->input_proj_1_bias, D);
+  nw.pb0_w = push(blob, w->prior_booster_0_weight, (size_t)q * 3);
+  nw.pb0_b = push(blob, w->prior_booster_0_bias, q);
+  nw.pb2_w = push(blob, w->prior_booster_2_weight, (size_t)D * q);
+  nw.pb2_b = push(blob, w->prior_booster_2_bias, D);
+  nw.ee0_w = push(blob, w->edge_enc_0_weight, (size_t)c * 5);
+  nw.ee0_b = push(blob, w->edge_enc_0_bias, c);
+  nw.ee2_w = push(blob, w->edge_enc_2_weight, (size_t)c * c);
+  nw.ee2_b = push(blob, w->edge_enc_2_bias, c);
+  nw.eg_ln_g = push(blob, w->edge_gate_0_weight, c);
+  nw.eg_ln_b = push(blob, w->edge_gate_0_bias, c);
+  nw.eg_w = push(blob, w->edge_gate_1_weight, (size_t)D * c);
+  nw.eg_b = push(blob, w->edge_gate_1_bias, D);
+  nw.gcn_w.resize(n); nw.gcn_b.resize(n); nw.norm_g.resize(n); nw.norm_b.resize(n);
+  for (int i = 0; i < n; ++i) {
+    nw.gcn_w[i] = push(blob, w->gcn_lin_weight[i], (size_t)D * D);
+    nw.gcn_b[i] = push(blob, w->gcn_bias[i], D);
+    nw.norm_g[i] = push(blob, w->norm_weight[i], D);
+    nw.norm_b[i] = push(blob, w->norm_bias[i], D);
+  }
+  nw.sage_wl = push(blob, w->sage_lin_l_weight, (size_t)D * D);
+  nw.sage_bl = push(blob, w->sage_lin_l_bias, D);
+  nw.sage_wr = push(blob, w->sage_lin_r_weight, (size_t)D * D);
+  nw.sage_ln_g = push(blob, w->sage_norm_weight, D);
+  nw.sage_ln_b = push(blob, w->sage_norm_bias, D);
+  nw.attn_w = push(blob, w->ctx_attn_weight, D);
+  nw.attn_b = push(blob, w->ctx_attn_bias, 1);
+  nw.cmp_w = push(blob, w->ctx_compress_weight, (size_t)(D / 2) * D);
+  nw.cmp_b = push(blob, w->ctx_compress_bias, D / 2);
+  nw.exp_w = push(blob, w->ctx_expand_weight, (size_t)D * (D / 2));
+  nw.exp_b = push(blob, w->ctx_expand_bias, D);
+  nw.fuse_ln_g = push(blob, w->fuse_0_weight, D);
+  nw.fuse_ln_b = push(blob, w->fuse_0_bias, D);
+  nw.fuse_w = push(blob, w->fuse_1_weight, (size_t)D * D);
+  nw.fuse_b = push(blob, w->fuse_1_bias, D);
+  nw.head_w = push(blob, w->head_weight, (size_t)3 * D);
+  nw.head_b = push(blob, w->head_bias, 3);
+
+  GG_CUDA_OK(cudaSetDevice(ctx->device));
+  if (nw.blob) { cudaFree(nw.blob); nw.blob = nullptr; }
+  GG_CUDA_OK(cudaMalloc(&nw.blob, blob.size() * sizeof(float)));
+  GG_CUDA_OK(cudaMemcpy(nw.blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  nw.blob_floats = blob.size();
+  nw.h_jk.assign(blob.begin() + nw.jk_w, blob.begin() + nw.jk_w + n + 2);
+  GG_TRY(gemm_tc_prepare_weights(ctx, blob));
+  nw.loaded = true;
+  return GG_OK;
+}
+
+static NetOffsets make_offsets(const NetWeights& nw) {
+  NetOffsets o;
+  o.D = nw.D; o.q = nw.q; o.c = nw.c;
+  o.jk_w = nw.jk_w; o.bn_scale = nw.bn_scale; o.bn_shift = nw.bn_shift;
+  o.w_in = nw.w_in; o.b_in = nw.b_in; o.ln_in_g = nw.ln_in_g; o.ln_in_b = nw.ln_in_b;
+  o.pb0_w = nw.pb0_w; o.pb0_b = nw.pb0_b; o.pb2_w = nw.pb2_w; o.pb2_b = nw.pb2_b;
+  o.ee0_w = nw.ee0_w; o.ee0_b = nw.ee0_b; o.eg_ln_g = nw.eg_ln_g; o.eg_ln_b = nw.eg_ln_b;
+  o.attn_w = nw.attn_w; o.attn_b = nw.attn_b; o.cmp_w = nw.cmp_w; o.cmp_b = nw.cmp_b;
+  o.exp_w = nw.exp_w; o.exp_b = nw.exp_b; o.head_w = nw.head_w; o.head_b = nw.head_b;
+  return o;
+}
+
+size_t resgcn_workspace_bytes(const NetWeights& nw, long long node_cap, long long edge_cap, int n_graphs) {
+  const int D = nw.D, c = nw.c;
+  size_t s = 0;
+  s += Arena::padded((size_t)node_cap * D, 4) * 5;      // h, z, gate, t0, t1
+  s += Arena::padded((size_t)edge_cap * c, 4) * 2;      // e1, enc
+  s += Arena::padded((size_t)node_cap * c, 4);          // ctx
+  s += Arena::padded((size_t)node_cap, 4) * 3;          // node_graph, dinv, score
+  s += Arena::padded((size_t)n_graphs * D, 4);          // gvec
+  s += 4096;
+  return s;
+}
+
+// dispatch on D/32
+#define GG_CPL_SWITCH(D, CALL)                      \
+  switch ((D) / 32) {                               \
+    case 1: { constexpr int CPL = 1; CALL; } break; \
+    case 2: { constexpr int CPL = 2; CALL; } break; \
+    case 3: { constexpr int CPL = 3; CALL; } break; \
+    case 4: { constexpr int CPL = 4; CALL; } break; \
+    case 5: { constexpr int CPL = 5; CALL; } break; \
+    case 6: { constexpr int CPL = 6; CALL; } break; \
+    case 7: { constexpr int CPL = 7; CALL; } break; \
+    case 8: { constexpr int CPL = 8; CALL; } break; \
+    default: GG_REQUIRE(false, "unsupported hidden width %d", (D)); \
+  }
+
+int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* rowptr,
+                   const int32_t* src, const int32_t* eid, const float* edge_attr,
+                   const int64_t* graph_off, int n_graphs, long long node_cap, long long edge_cap,
+                   float* logits, float* probs, cudaStream_t st) {
+  NetWeights& nw = ctx->net;
+  if (!nw.loaded) { set_error("resgcn_forward: no weights loaded (gg_load_weights)"); return GG_ERR_STATE; }
+  GG_REQUIRE(n_graphs > 0 && node_cap > 0 && edge_cap >= 0, "resgcn_forward: bad sizes");
+  GG_REQUIRE(node_cap < (1ll << 31) && edge_cap < (1ll << 31), "resgcn_forward: batch too large");
+  const int D = nw.D, c = nw.c, n = nw.n_layers;
+  const NetOffsets o = make_offsets(nw);
+  const float* wb = nw.blob;
+
+  float* h = ar.take<float>((size_t)node_cap * D);
+  float* z = ar.take<float>((size_t)node_cap * D);
+  float* gate = ar.take<float>((size_t)node_cap * D);
+  float* t0 = ar.take<float>((size_t)node_cap * D);
+  float* t1 = ar.take<float>((size_t)node_cap * D);
+  float* e1 = ar.take<float>((size_t)(edge_cap > 0 ? edge_cap : 1) * c);
+  float* enc = ar.take<float>((size_t)(edge_cap > 0 ? edge_cap : 1) * c);
+  float* ctxv = ar.take<float>((size_t)node_cap * c);
+  int* node_graph = ar.take<int>((size_t)node_cap);
+  float* dinv = ar.take<float>((size_t)node_cap);
+  float* score = ar.take<float>((size_t)node_cap);
+  float* gvec = ar.take<float>((size_t)n_graphs * D);
+  int* sizes = ar.take<int>(64);
+  const int* n_nodes_p = sizes;
+  const int* n_edges_p = sizes + 1;
+
+  const int warp_blocks = ceil_div(node_cap, 8);   // warp-per-node kernels, 8 warps per block
+  GG_LAUNCH(ctx, k_sizes, 1, 1, 0, st, graph_off, n_graphs, rowptr, sizes, node_cap, edge_cap, ctx->d_status);
+  GG_LAUNCH(ctx, k_node_meta, ceil_div(node_cap, 256), 256, 0, st, graph_off, n_graphs, rowptr, src,
+            sizes, node_graph, dinv);
+
+  // ---- input stage
+  {
+    const size_t smem = ((size_t)D * 19 + (size_t)nw.q * 3 + (size_t)D * nw.q) * sizeof(float);
+    const int blocks = min(warp_blocks, ctx->sm_count * 8);
+    GG_CPL_SWITCH(D, {
+      GG_CUDA_OK(cudaFuncSetAttribute(k_input_stage<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GG_LAUNCH(ctx, k_input_stage<CPL>, blocks, 256, smem, st, x, wb, o, sizes, h, z);
+    });
+  }
+  // ---- edge context -> gate
+  if (edge_cap > 0) {
+    GG_LAUNCH(ctx, k_edge_enc1, ceil_div(edge_cap * c, 256), 256, 0, st, edge_attr, wb, o, sizes, e1);
+    GG_TRY(gemm(ctx, st, GEMM_ENC2, e1, wb + nw.ee2_w, wb + nw.ee2_b, enc, n_edges_p, edge_cap, c, c, 0, 0));
+  }
+  GG_LAUNCH(ctx, k_edge_ctx, warp_blocks, 256, 0, st, enc, rowptr, eid, wb, o, sizes, ctxv);
+  GG_TRY(gemm(ctx, st, GEMM_GATE, ctxv, wb + nw.eg_w, wb + nw.eg_b, gate, n_nodes_p, node_cap, D, c, 2, 0));
+
+  // ---- residual GCN blocks
+  for (int l = 0; l < n; ++l) {
+    GG_CPL_SWITCH(D, {
+      GG_LAUNCH(ctx, k_layernorm<CPL>, warp_blocks, 256, 0, st, h, wb + nw.norm_g[l], wb + nw.norm_b[l],
+                (const float*)nullptr, (const int*)nullptr, sizes, t0);
+    });
+    GG_TRY(gemm(ctx, st, GEMM_GCN0 + l, t0, wb + nw.gcn_w[l], nullptr, t1, n_nodes_p, node_cap, D, D, 0, 0));
+    GG_CPL_SWITCH(D, {
+      GG_LAUNCH(ctx, k_gcn_aggregate<CPL>, warp_blocks, 256, 0, st, t1, rowptr, src, dinv,
+                wb + nw.gcn_b[l], gate, nw.h_jk[l + 1], sizes, h, z);
+    });
+  }
+  // ---- SAGE branch
+  GG_CPL_SWITCH(D, { GG_LAUNCH(ctx, k_sage_mean<CPL>, warp_blocks, 256, 0, st, h, rowptr, src, sizes, t0); });
+  GG_TRY(gemm(ctx, st, GEMM_SAGE_L, t0, wb + nw.sage_wl, wb + nw.sage_bl, t1, n_nodes_p, node_cap, D, D, 0, 0));
+  GG_TRY(gemm(ctx, st, GEMM_SAGE_R, h, wb + nw.sage_wr, nullptr, t1, n_nodes_p, node_cap, D, D, 0, 1));
+  GG_CPL_SWITCH(D, {
+    GG_LAUNCH(ctx, k_sage_finish<CPL>, warp_blocks, 256, 0, st, t1, wb + nw.sage_ln_g, wb + nw.sage_ln_b,
+              nw.h_jk[n + 1], sizes, z);
+  });
+  // ---- global context, fuse, head
+  {
+    const size_t smem = (size_t)(D + D / 2) * sizeof(float);
+    GG_LAUNCH(ctx, k_graph_context, n_graphs, 256, smem, st, z, graph_off, wb, o, n_graphs, score, gvec);
+  }
+  GG_CPL_SWITCH(D, {
+    GG_LAUNCH(ctx, k_layernorm<CPL>, warp_blocks, 256, 0, st, z, wb + nw.fuse_ln_g, wb + nw.fuse_ln_b,
+              (const float*)gvec, (const int*)node_graph, sizes, t0);
+  });
+  GG_TRY(gemm(ctx, st, GEMM_FUSE, t0, wb + nw.fuse_w, wb + nw.fuse_b, t1, n_nodes_p, node_cap, D, D, 1, 0));
+  GG_LAUNCH(ctx, k_head, warp_blocks, 256, 0, st, t1, wb, o, sizes, logits, probs);
+  return GG_OK;
+}
+
+// ------------------------------------------------------------------ COO -> CSR
+__global__ void k_coo_count(const int64_t* __restrict__ ei, long long E, long long N, int* __restrict__ cnt,
+                            int* status) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const long long d = ei[E + e], s = ei[e];
+  if (d < 0 || d >= N || s < 0 || s >= N) { atomicOr(status, ST_LABEL_RANGE); return; }
+  atomicAdd(&cnt[d], 1);
+}
+__global__ void __launch_bounds__(1024)
+k_coo_scan(int* __restrict__ cnt, int32_t* __restrict__ rowptr, long long N) {
+  __shared__ int scratch[40];
+  int carry = 0;
+  for (long long base = 0; base < N; base += blockDim.x) {
+    const long long i = base + threadIdx.x;
+    const int v = (i < N) ? cnt[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, scratch, &total);
+    if (i < N) { rowptr[i] = carry + ex; cnt[i] = 0; }
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rowptr[N] = carry;
+}
+__global__ void k_coo_fill(const int64_t* __restrict__ ei, long long E, long long N,
+                           const int32_t* __restrict__ rowptr, int* __restrict__ cursor,
+                           int32_t* __restrict__ src, int32_t* __restrict__ eid) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const long long d = ei[E + e], s = ei[e];
+  if (d < 0 || d >= N || s < 0 || s >= N) return;
+  const int pos = rowptr[d] + atomicAdd(&cursor[d], 1);
+  src[pos] = (int)s;
+  eid[pos] = (int)e;
+}
+__global__ void k_coo_sort_rows(const int32_t* __restrict__ rowptr, long long N, int32_t* __restrict__ src,
+                                int32_t* __restrict__ eid) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  const int s0 = rowptr[v], s1 = rowptr[v + 1];
+  for (int a = s0 + 1; a < s1; ++a) {
+    const int sv = src[a], ev = eid[a];
+    int j = a - 1;
+    while (j >= s0 && (src[j] > sv || (src[j] == sv && eid[j] > ev))) {
+      src[j + 1] = src[j]; eid[j + 1] = eid[j]; --j;
+    }
+    src[j + 1] = sv; eid[j + 1] = ev;
+  }
+}
+
+int coo_to_csr(gg_context* ctx, Arena& ar, const int64_t* ei, long long E, long long N,
+               int32_t* rowptr, int32_t* src, int32_t* eid, cudaStream_t st) {
+  GG_REQUIRE(N > 0 && E >= 0 && N < (1ll << 31) && E < (1ll << 31), "coo_to_csr: bad sizes");
+  int* cnt = ar.take<int>((size_t)N);
+  GG_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)N * sizeof(int), st));
+  GG_CUDA_OK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));
+  if (E > 0) GG_LAUNCH(ctx, k_coo_count, ceil_div(E, 256), 256, 0, st, ei, E, N, cnt, ctx->d_status);
+  GG_LAUNCH(ctx, k_coo_scan, 1, 1024, 0, st, cnt, rowptr, N);
+  if (E > 0) GG_LAUNCH(ctx, k_coo_fill, ceil_div(E, 256), 256, 0, st, ei, E, N, rowptr, cnt, src, eid);
+  GG_LAUNCH(ctx, k_coo_sort_rows, ceil_div(N, 256), 256, 0, st, rowptr, N, src, eid);
+  return GG_OK;
+}
+
+}  // namespace gg

@@ -1,0 +1,41 @@
+// Internal interface of resgcn.cu / gemm_tc.cu
+#pragma once
+#include "common.cuh"
+
+namespace gg {
+
+// offsets (in floats) of the small parameter tensors inside NetWeights::blob, by value to kernels
+struct NetOffsets {
+  int D, q, c;
+  unsigned jk_w, bn_scale, bn_shift, w_in, b_in, ln_in_g, ln_in_b;
+  unsigned pb0_w, pb0_b, pb2_w, pb2_b, ee0_w, ee0_b, eg_ln_g, eg_ln_b;
+  unsigned attn_w, attn_b, cmp_w, cmp_b, exp_w, exp_b, head_w, head_b;
+};
+
+// identifiers of the dense per-node / per-edge transforms (select the packed tensor-core operand)
+enum : int { GEMM_ENC2 = 0, GEMM_GATE = 1, GEMM_SAGE_L = 2, GEMM_SAGE_R = 3, GEMM_FUSE = 4, GEMM_GCN0 = 5 };
+
+int load_weights(gg_context* ctx, const gg_resgcn_weights* w);
+size_t resgcn_workspace_bytes(const NetWeights& nw, long long node_cap, long long edge_cap, int n_graphs);
+int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* rowptr,
+                   const int32_t* src, const int32_t* eid, const float* edge_attr,
+                   const int64_t* graph_off, int n_graphs, long long node_cap, long long edge_cap,
+                   float* logits, float* probs, cudaStream_t st);
+int coo_to_csr(gg_context* ctx, Arena& ar, const int64_t* ei, long long E, long long N,
+               int32_t* rowptr, int32_t* src, int32_t* eid, cudaStream_t st);
+
+// C[M,N] (+)= act(A[M,K] W[N,K]^T + bias); M read on the device from *m_ptr (<= m_cap).
+// act: 0 none, 1 GELU(erf), 2 sigmoid.
+int gemm_simt(gg_context* ctx, cudaStream_t st, const float* A, const float* W, const float* bias,
+              float* C, const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate);
+int gemm(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* W,
+         const float* bias, float* C, const int* m_ptr, long long m_cap, int N, int K, int act,
+         int accumulate);
+
+// gemm_tc.cu: tcgen05 path
+int gemm_tc_prepare_weights(gg_context* ctx, const std::vector<float>& blob);
+bool gemm_tc_supported(const gg_context* ctx, int which, int N, int K);
+int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* bias, float* C,
+            const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate);
+
+}  // namespace gg

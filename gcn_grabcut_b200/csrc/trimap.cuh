@@ -1,0 +1,22 @@
+// Internal interface of trimap.cu
+#pragma once
+#include "common.cuh"
+
+namespace gg {
+
+size_t trimap_workspace_bytes(int B, int H, int W, bool need_gray);
+
+// gray_in may be NULL (then the grey plane is derived from bgr inside `ar`).
+int refine_trimap(gg_context* ctx, Arena& ar, const uint8_t* bgr, const uint8_t* gray_in,
+                  const int32_t* labels, const float* probs, const int64_t* node_off, int B, int H,
+                  int W, int radius, float eps, float thr_fg, float thr_bg, uint8_t* trimap,
+                  float* p_bg, float* p_fg, cudaStream_t st);
+
+int guided_filter_plane(gg_context* ctx, Arena& ar, const float* guide, const float* src, int H,
+                        int W, int radius, float eps, float* out, cudaStream_t st);
+
+int project_trimap(gg_context* ctx, const int32_t* labels, const float* probs,
+                   const int64_t* node_off, int B, int H, int W, float thr_fg, float thr_bg,
+                   uint8_t* trimap, cudaStream_t st);
+
+}  // namespace gg

@@ -1,0 +1,164 @@
+"""
+Region -> pixel projection and the batched trimap path -- host-side mirror of the trimap part
+of the reference's ``src/gcn_grabcut/pipeline.py`` (guided_filter :71-100, refine_trimap
+:103-146, and the graph -> network -> trimap section of GCNGrabCutPipeline.segment :296-322).
+
+``guided_filter`` / ``refine_trimap`` keep the reference's signatures and numpy in/out, so the
+reference's ``segment()`` can import them unchanged; ``TrimapPath`` is the batched form that
+the throughput harness uses: B images + label maps in, B OpenCV trimaps out, everything in
+between on the GPU (``gg_trimap_path_host`` / ``gg_trimap_path_device``).  The GrabCut
+refinement downstream (``cv2.grabCut``) is not part of the path and stays as it is.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native as nat
+from .graph_builder import SuperpixelGraphConfig
+from .model import CLASS_BG, CLASS_FG, project_to_pixels  # noqa: F401  (re-exported like the reference)
+
+
+def guided_filter(guide: np.ndarray, src: np.ndarray, radius: int = 8, eps: float = 1e-3,
+                  device=None) -> np.ndarray:
+    """Edge-preserving filter of ``src`` under ``guide`` (float32 (H,W) planes), on the GPU."""
+    import torch
+    dev = nat.device_index(device if device is not None else "cuda")
+    h = nat.handle(dev)
+    tdev = torch.device("cuda", dev)
+    g = torch.from_numpy(np.ascontiguousarray(guide, dtype=np.float32)).to(tdev)
+    s = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)).to(tdev)
+    if g.dim() != 2 or g.shape != s.shape:
+        raise ValueError("guide and src must be (H,W) planes of equal shape")
+    out = torch.empty_like(g)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().gg_guided_filter(h.ptr, nat.ptr(g), nat.ptr(s), int(g.shape[0]), int(g.shape[1]),
+                                             int(radius), float(eps), nat.ptr(out),
+                                             C.c_void_p(nat.current_stream(dev))))
+    return out.cpu().numpy()
+
+
+def refine_trimap(probs: np.ndarray, segments: np.ndarray, image: np.ndarray,
+                  threshold_fg: float = 0.55, threshold_bg: float = 0.55, radius: int = 8,
+                  eps: float = 1e-3, device=None, return_planes: bool = False):
+    """
+    Per-region class probabilities -> pixel-level trimap whose boundaries follow image edges
+    (reference pipeline.py:103-146).  probs (N,3) [BG,UNK,FG]; segments (H,W); image BGR uint8.
+    Returns (H,W) uint8 in cv2.GC_* label space.
+    """
+    import torch
+    dev = nat.device_index(device if device is not None else "cuda")
+    h = nat.handle(dev)
+    tdev = torch.device("cuda", dev)
+    if image.shape[:2] != segments.shape:
+        raise ValueError(f"segments shape {segments.shape} != image shape {image.shape[:2]}")
+    H, W = segments.shape
+    p = torch.from_numpy(np.ascontiguousarray(probs, dtype=np.float32)).to(tdev)
+    seg = torch.from_numpy(np.ascontiguousarray(segments, dtype=np.int32)).to(tdev)
+    img = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(tdev)
+    goff = torch.tensor([0, p.shape[0]], dtype=torch.int64, device=tdev)
+    tri = torch.empty(H, W, dtype=torch.uint8, device=tdev)
+    pb = torch.empty(H, W, dtype=torch.float32, device=tdev) if return_planes else None
+    pf = torch.empty(H, W, dtype=torch.float32, device=tdev) if return_planes else None
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().gg_refine_trimap(h.ptr, nat.ptr(img), nat.ptr(seg), nat.ptr(p), nat.ptr(goff),
+                                             1, H, W, int(radius), float(eps), float(threshold_fg),
+                                             float(threshold_bg), nat.ptr(tri), nat.ptr(pb), nat.ptr(pf),
+                                             C.c_void_p(nat.current_stream(dev))))
+    if return_planes:
+        return tri.cpu().numpy(), pb.cpu().numpy(), pf.cpu().numpy()
+    return tri.cpu().numpy()
+
+
+class TrimapPath:
+    """
+    The whole per-image trimap path, batched:  BGR images + label maps -> OpenCV trimaps.
+
+        path = TrimapPath(state_dict_or_model, SuperpixelGraphConfig(), node_cap=320)
+        trimaps = path(images_uint8_BHW3, labels_int32_BHW)          # host in / host out
+
+    Equivalent, per image, to the reference's
+        graph  = GraphBuilder(image, cfg).build()                    (label map supplied)
+        probs  = model.predict_probs(Data(graph.node_input(), graph.edge_index, graph.edge_attr))
+        trimap = refine_trimap(probs, graph.segments, image, thr_fg, thr_bg, radius)
+    (pipeline.py:298-317), or ``model.predict_trimap`` when ``edge_aware=False``.
+    """
+
+    def __init__(self, model, sp_config: Optional[SuperpixelGraphConfig] = None, node_cap: int = 512,
+                 pair_cap: int = 0, threshold_fg: float = 0.55, threshold_bg: float = 0.55,
+                 filter_radius: int = 8, eps: float = 1e-3, edge_aware: bool = True, chunk: int = 0,
+                 device=None):
+        self.cfg = sp_config or SuperpixelGraphConfig()
+        self.dev = nat.device_index(device if device is not None else "cuda")
+        self.h = nat.handle(self.dev)
+        state = model.state_dict() if hasattr(model, "state_dict") else model
+        nat.load_state_dict(self.h, state)
+        self.h.weights_token = self
+        self.node_cap = int(node_cap)
+        pair_cap = int(pair_cap) if pair_cap else self.node_cap * max(6, 3 + self.cfg.n_nonlocal)
+        self.pc = nat.PathConfig(
+            nat.GraphConfig(int(self.cfg.connectivity), int(self.cfg.n_nonlocal), self.node_cap, pair_cap),
+            int(filter_radius), float(eps), float(threshold_fg), float(threshold_bg), int(bool(edge_aware)),
+            int(chunk))
+
+    def _ensure_weights(self):
+        if self.h.weights_token is not self:
+            raise nat.NativeError(nat.GG_ERR_STATE, "another model was loaded on this device handle; "
+                                                    "create a new TrimapPath")
+
+    def __call__(self, images, labels, out: Optional[np.ndarray] = None,
+                 return_counts: bool = False):
+        """Host buffers (numpy or pinned torch CPU tensors) in, host trimaps out; copies included."""
+        import torch
+        self._ensure_weights()
+        img = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
+        lab = labels if torch.is_tensor(labels) else torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32))
+        if img.is_cuda or lab.is_cuda:
+            raise ValueError("TrimapPath.__call__ takes host buffers; use run_device for CUDA tensors")
+        if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[-1] != 3:
+            raise ValueError("images must be uint8 (B,H,W,3)")
+        if lab.dtype != torch.int32 or tuple(lab.shape) != tuple(img.shape[:3]):
+            raise ValueError("labels must be int32 (B,H,W) matching images")
+        B, H, W = int(img.shape[0]), int(img.shape[1]), int(img.shape[2])
+        tri = out if out is not None else torch.empty((B, H, W), dtype=torch.uint8)
+        tri_t = tri if torch.is_tensor(tri) else torch.from_numpy(tri)
+        nn_ = torch.empty(B, dtype=torch.int32) if return_counts else None
+        ne_ = torch.empty(B, dtype=torch.int32) if return_counts else None
+        with torch.cuda.device(self.dev):
+            nat.check(nat.lib().gg_trimap_path_host(self.h.ptr, nat.ptr(img.contiguous()), nat.ptr(lab.contiguous()),
+                                                    B, H, W, C.byref(self.pc), nat.ptr(tri_t), nat.ptr(nn_),
+                                                    nat.ptr(ne_)))
+        res = tri_t.numpy() if not torch.is_tensor(out) else tri_t
+        if return_counts:
+            return res, nn_.numpy(), ne_.numpy()
+        return res
+
+    def run_device(self, images_t, labels_t, trimap_t=None, probs_t=None, node_off_t=None):
+        """CUDA tensors in, CUDA trimaps out, on the current stream, no host synchronisation."""
+        import torch
+        self._ensure_weights()
+        B, H, W = int(images_t.shape[0]), int(images_t.shape[1]), int(images_t.shape[2])
+        if trimap_t is None:
+            trimap_t = torch.empty((B, H, W), dtype=torch.uint8, device=images_t.device)
+        with torch.cuda.device(self.dev):
+            nat.check(nat.lib().gg_trimap_path_device(
+                self.h.ptr, nat.ptr(images_t, torch.uint8), nat.ptr(labels_t, torch.int32), B, H, W,
+                C.byref(self.pc), nat.ptr(trimap_t), nat.ptr(probs_t), nat.ptr(node_off_t),
+                C.c_void_p(nat.current_stream(self.dev))))
+        return trimap_t
+
+    def shard(self, n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+        """Contiguous block [lo, hi) of a batch of ``n_items`` images owned by ``rank``."""
+        return shard_range(n_items, rank, world_size)
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Images shard across GPUs with no exchange step: rank r owns a contiguous block; blocks
+    differ by at most one image."""
+    if world_size <= 0 or not 0 <= rank < world_size:
+        raise ValueError("bad rank / world_size")
+    base, rem = divmod(int(n_items), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -1,0 +1,237 @@
+/*
+ * gcn_grabcut_b200.h -- C ABI of the B200-native trimap path of GCN-GrabCut
+ *
+ *     label map + BGR image --> attributed region graph --> ResGCNNet posterior --> trimap
+ *
+ * The reference (HanielUlises/GCN-GrabCut v0.3.0) is pure Python and has no FFI of its
+ * own; its boundary for this path is the Python API consumed by
+ * src/gcn_grabcut/pipeline.py:298-321 and inference.py:75-98.  Each entry point below
+ * names the reference interface it replaces.  The Python mirror of that interface
+ * (gcn_grabcut_b200/{graph_builder,model,pipeline}.py) binds these symbols with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, a negative gg_status on
+ *     failure; gg_last_error() returns a thread-local message for the last failure.
+ *   - "dev" pointers are device pointers owned by the caller (e.g. torch data_ptr());
+ *     "host" pointers are host pointers (pinned memory recommended).
+ *   - all device work is enqueued on the caller's stream (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream); device-pointer entry points never
+ *     synchronise the host.  Sizes that are only known on the device (node / edge
+ *     counts) are returned in device arrays; the caller reads them back when needed.
+ *   - images of one call share H and W; H*W < 2^24, H,W >= 2; labels are int32 in
+ *     [0, node_cap) and need not be dense (an absent label is a region of area 0,
+ *     exactly as in the reference: graph_builder.py:158, :194-195).
+ *   - there is no CPU fallback: every entry point fails with GG_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef GCN_GRABCUT_B200_H
+#define GCN_GRABCUT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_ABI_VERSION 1
+
+#define GG_N_IMAGE_FEATS 16 /* graph_builder.py:73 */
+#define GG_N_PRIOR_FEATS 3  /* graph_builder.py:74 */
+#define GG_N_NODE_FEATS 19  /* graph_builder.py:76 */
+#define GG_N_EDGE_FEATS 5   /* graph_builder.py:77 */
+#define GG_N_CLASSES 3      /* model.py:62-64  [BG, UNK, FG] */
+
+typedef enum gg_status {
+  GG_OK = 0,
+  GG_ERR_INVALID = -1,   /* bad argument */
+  GG_ERR_CUDA = -2,      /* CUDA runtime error / no usable device */
+  GG_ERR_CAPACITY = -3,  /* a label >= node_cap, or an edge / pair table overflowed */
+  GG_ERR_STATE = -4      /* e.g. forward before gg_load_weights */
+} gg_status;
+
+typedef struct gg_context* gg_handle;
+
+/* ------------------------------------------------------------------ lifetime / errors */
+int gg_abi_version(void);
+const char* gg_last_error(void);
+int gg_create(gg_handle* out, int device);
+void gg_destroy(gg_handle h);
+
+/* Runtime options.  "gemm_impl": 1 = tcgen05 tensor-core transforms (default),
+ * 0 = SIMT fp32 transforms (validation of the tensor-core path; same device, same API). */
+int gg_set_option(gg_handle h, const char* key, int value);
+
+/* Device-side status word written by the kernels of the last enqueued call:
+ * bit0 label >= node_cap, bit1 adjacency table overflow, bit2 edge capacity overflow.
+ * Synchronises the given stream. */
+int gg_check_device_status(gg_handle h, void* stream, int* status_bits);
+
+/* ------------------------------------------------------------------ graph construction
+ * Replaces GraphBuilder(image, cfg).build() minus SLIC, i.e. graph_builder.py:142-154
+ * (pixel planes), :190-226 (_region_statistics), :228-255 (_assemble_node_features),
+ * :257-350 (_compute_edges, _pair_features, _nonlocal_pairs) and :357-454
+ * (compute_auto_prior), for a batch of B images at once.
+ *
+ * SuperpixelGraphConfig fields honoured (graph_builder.py:64-71): connectivity (4|8),
+ * n_nonlocal (0..32).  n_segments / compactness / sigma / use_lab belong to SLIC, the
+ * input producer.
+ */
+typedef struct gg_graph_config {
+  int32_t connectivity; /* 4 or 8 */
+  int32_t n_nonlocal;   /* k nearest colour neighbours per node, 0 = off */
+  int32_t node_cap;     /* capacity per image: every label must be < node_cap */
+  int32_t pair_cap;     /* capacity per image for undirected pairs (adjacency + non-local);
+                           0 = choose (8 * node_cap) */
+} gg_graph_config;
+
+/* Batched ragged output, all device pointers.  Image b owns nodes
+ * [node_off[b], node_off[b+1]) and directed edges [edge_off[b], edge_off[b+1]).
+ * Rows are laid out exactly as the reference's SuperpixelGraph fields
+ * (graph_builder.py:80-91), so slicing by the offsets yields the per-image arrays.
+ * Capacities: node arrays B*node_cap rows, edge arrays 2*B*pair_cap rows.
+ * Optional pointers may be NULL. */
+typedef struct gg_graph_out {
+  int32_t* n_nodes;     /* [B]      n_nodes = max label + 1      (graph_builder.py:158) */
+  int32_t* n_edges;     /* [B]      directed edge count E        (graph_builder.py:171) */
+  int64_t* node_off;    /* [B+1]    exclusive prefix of n_nodes */
+  int64_t* edge_off;    /* [B+1]    exclusive prefix of n_edges */
+  float* x;             /* [SN,19]  node_input(): 16 image features | 3 prior (…:93-98) */
+  int64_t* edge_index;  /* [2,EC]   row 0 = src, row 1 = dst, image-LOCAL ids, reference COO order
+                                    [adj lo->hi | nl lo->hi | adj hi->lo | nl hi->lo] (…:299-306);
+                                    EC = edge_index_stride = 2*B*pair_cap */
+  float* edge_attr;     /* [SE,5]   (…:309-322) */
+  float* centroids;     /* [SN,2]   node_centroids [y,x] (optional) */
+  float* areas;         /* [SN]     node_areas           (optional) */
+  /* destination-sorted CSR of the same directed edges, GLOBAL node / edge ids, consumed
+   * by gg_resgcn_forward: for node v, entries [csr_rowptr[v], csr_rowptr[v+1]). */
+  int32_t* csr_rowptr;  /* [SN+1] (entries beyond the last node repeat the total) */
+  int32_t* csr_src;     /* [SE]   global source node id */
+  int32_t* csr_eid;     /* [SE]   global edge id (row of edge_attr) */
+  int32_t* n_adj_pairs; /* [B]    undirected adjacency pairs (optional) */
+  int32_t* n_nl_pairs;  /* [B]    undirected non-local pairs (optional) */
+  int32_t* shared_cnt;  /* [B*pair_cap] shared-boundary pixel counts s_ij of the adjacency
+                                    pairs of image b at [b*pair_cap, …) in sorted order (optional) */
+} gg_graph_out;
+
+int gg_build_graphs(gg_handle h, const uint8_t* bgr_dev /*[B,H,W,3]*/,
+                    const int32_t* labels_dev /*[B,H,W]*/, int B, int H, int W,
+                    const gg_graph_config* cfg, const gg_graph_out* out, void* stream);
+
+/* Per-pixel planes of GraphBuilder.__init__ (graph_builder.py:142-154): _lab [B,H,W,3],
+ * _hsv [B,H,W,3], _gray [B,H,W], _grad [B,H,W], all float32; any output may be NULL. */
+int gg_pixel_planes(gg_handle h, const uint8_t* bgr_dev, int B, int H, int W, float* lab_dev,
+                    float* hsv_dev, float* gray_dev, float* grad_dev, void* stream);
+
+/* ------------------------------------------------------------------ trimap network
+ * Replaces ResGCNNet.load_state_dict / forward / predict_probs in eval mode
+ * (model.py:449-546) including the PyG GCNConv / SAGEConv layers it calls.
+ * Weight pointers are HOST float32 arrays in the reference's state-dict layout
+ * (row-major [out,in] for *.weight); names follow the checkpoint keys
+ * (inference.py:76-89).  gcn_* / norm_* are arrays of n_layers pointers.
+ */
+typedef struct gg_resgcn_weights {
+  int32_t hidden;   /* D  = input_proj.0.weight.shape[0] */
+  int32_t n_layers; /* n  = number of gcn_layers.*.bias keys */
+  const float* jk_logits;                       /* [n+2] */
+  const float *in_norm_weight, *in_norm_bias, *in_norm_mean, *in_norm_var; /* [19] */
+  const float *input_proj_0_weight, *input_proj_0_bias;   /* [D,19], [D] */
+  const float *input_proj_1_weight, *input_proj_1_bias;   /* LayerNorm [D] */
+  const float *prior_booster_0_weight, *prior_booster_0_bias; /* [q,3], [q]; q = max(D/4,8) */
+  const float *prior_booster_2_weight, *prior_booster_2_bias; /* [D,q], [D] */
+  const float *edge_enc_0_weight, *edge_enc_0_bias;       /* [c,5], [c];  c = max(D/2,8) */
+  const float *edge_enc_2_weight, *edge_enc_2_bias;       /* [c,c], [c] */
+  const float *edge_gate_0_weight, *edge_gate_0_bias;     /* LayerNorm [c] */
+  const float *edge_gate_1_weight, *edge_gate_1_bias;     /* [D,c], [D] */
+  const float* const* gcn_lin_weight;  /* n x [D,D]  gcn_layers.i.lin.weight */
+  const float* const* gcn_bias;        /* n x [D]    gcn_layers.i.bias */
+  const float* const* norm_weight;     /* n x [D]    norms.i.weight */
+  const float* const* norm_bias;       /* n x [D] */
+  const float *sage_lin_l_weight, *sage_lin_l_bias, *sage_lin_r_weight; /* [D,D],[D],[D,D] */
+  const float *sage_norm_weight, *sage_norm_bias;         /* [D] */
+  const float *ctx_attn_weight, *ctx_attn_bias;           /* [1,D], [1] */
+  const float *ctx_compress_weight, *ctx_compress_bias;   /* [D/2,D], [D/2] */
+  const float *ctx_expand_weight, *ctx_expand_bias;       /* [D,D/2], [D] */
+  const float *fuse_0_weight, *fuse_0_bias;               /* LayerNorm [D] */
+  const float *fuse_1_weight, *fuse_1_bias;               /* [D,D], [D] */
+  const float *head_weight, *head_bias;                   /* [3,D], [3] */
+} gg_resgcn_weights;
+
+int gg_load_weights(gg_handle h, const gg_resgcn_weights* w);
+
+/* COO (2,E) int64 edge list in any order -> destination-sorted CSR (rows sorted by
+ * source id, ties by edge id).  Lets forward() accept what the reference's
+ * forward(data) accepts (model.py:508-514).  edge_index row stride = E. */
+int gg_coo_to_csr(gg_handle h, const int64_t* edge_index_dev, int64_t n_edges, int64_t n_nodes,
+                  int32_t* csr_rowptr_dev /*[n_nodes+1]*/, int32_t* csr_src_dev /*[E]*/,
+                  int32_t* csr_eid_dev /*[E]*/, void* stream);
+
+/* forward over a batch of graphs.  node_cap_total / edge_cap_total bound the row counts
+ * (the true totals are read on the device from graph_off[n_graphs] and
+ * csr_rowptr[total nodes]).  graph_off: int64 [n_graphs+1] node offsets per graph
+ * (= gg_graph_out.node_off; a single graph is {0, N}).
+ * logits_dev / probs_dev: [node_cap_total,3]; either may be NULL. */
+int gg_resgcn_forward(gg_handle h, const float* x_dev, const int32_t* csr_rowptr_dev,
+                      const int32_t* csr_src_dev, const int32_t* csr_eid_dev,
+                      const float* edge_attr_dev, const int64_t* graph_off_dev, int n_graphs,
+                      int64_t node_cap_total, int64_t edge_cap_total, float* logits_dev,
+                      float* probs_dev, void* stream);
+
+/* ------------------------------------------------------------------ region -> pixel projection
+ * gg_refine_trimap replaces refine_trimap (pipeline.py:103-146): guided filter of the BG
+ * and FG posteriors under the grey image (pipeline.py:71-100, cv2.blur numerics: float64
+ * window sums, BORDER_REFLECT_101) and the threshold rule of eq. 27.
+ * gg_project_trimap replaces predict_trimap / _probs_to_trimap (model.py:548-557,
+ * :623-678): node labels gathered through the label map (no filter).
+ * probs_dev: [SN,3] rows indexed by node_off[b] + label; labels with no row
+ * (label >= n_nodes[b]) read as zeros (project_to_pixels padding, model.py:655-661)
+ * resp. GC_PR_BGD (model.py:672-677).  node_off: int64 [B+1].
+ */
+int gg_refine_trimap(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev,
+                     const float* probs_dev, const int64_t* node_off_dev, int B, int H, int W,
+                     int radius, float eps, float thr_fg, float thr_bg,
+                     uint8_t* trimap_dev /*[B,H,W]*/, float* p_bg_dev /*optional [B,H,W]*/,
+                     float* p_fg_dev /*optional*/, void* stream);
+
+int gg_project_trimap(gg_handle h, const int32_t* labels_dev, const float* probs_dev,
+                      const int64_t* node_off_dev, int B, int H, int W, float thr_fg,
+                      float thr_bg, uint8_t* trimap_dev, void* stream);
+
+/* guided_filter(guide, src, radius, eps) on single float32 planes (pipeline.py:71-100). */
+int gg_guided_filter(gg_handle h, const float* guide_dev, const float* src_dev, int H, int W,
+                     int radius, float eps, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------ whole path, host buffers
+ * The call pipeline.segment() makes between cv2.imread and cv2.grabCut
+ * (pipeline.py:298-321), batched: HOST images + label maps in, HOST trimaps out, with the
+ * host<->device copies inside the call (chunked and overlapped with the kernels on
+ * internal streams).  Synchronous.  Optional outputs may be NULL.
+ */
+typedef struct gg_path_config {
+  gg_graph_config graph;
+  int32_t radius;      /* guided-filter radius (pipeline.py:274; default 8) */
+  float eps;           /* pipeline.py:75 (1e-3) */
+  float thr_fg;        /* pipeline.py:268 (0.55) */
+  float thr_bg;
+  int32_t edge_aware;  /* 1: refine_trimap, 0: predict_trimap (pipeline.py:312-321) */
+  int32_t chunk;       /* images per pipelined chunk; 0 = choose */
+} gg_path_config;
+
+int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B,
+                        int H, int W, const gg_path_config* cfg, uint8_t* trimap_host /*[B,H,W]*/,
+                        int32_t* n_nodes_host /*optional [B]*/, int32_t* n_edges_host /*optional [B]*/);
+
+/* Same path with inputs and outputs resident on the device (caller's stream, no host sync). */
+int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, int B,
+                          int H, int W, const gg_path_config* cfg, uint8_t* trimap_dev,
+                          float* probs_dev /*optional [B*node_cap,3]*/,
+                          int64_t* node_off_dev /*optional [B+1]*/, void* stream);
+
+/* Number of kernels of this library launched by this handle so far (bench bookkeeping). */
+int64_t gg_kernel_launch_count(gg_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCN_GRABCUT_B200_H */

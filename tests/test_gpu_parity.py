@@ -1,0 +1,350 @@
+"""
+GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes through the
+C ABI of libgcn_grabcut_b200.so (via the ctypes mirror of the reference API); the oracle
+(oracle/*.py, a CPU restatement pinned against the reference's own outputs) is the checker.
+
+Stated tolerances
+  structure (n_nodes, edge_index, shared-boundary counts, degrees) ........ bit-exact
+  node / edge attributes, prior ........................................... rtol 1e-5, atol 2e-6
+  logits / posteriors ..................................................... atol 1e-4
+  trimap .................................................................. pixel-exact except
+        pixels whose filtered posterior lies within 1e-5 of a decision boundary
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_cases, golden_inputs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+FEAT_RTOL, FEAT_ATOL = 1e-5, 2e-6
+POST_ATOL = 1e-4
+TRI_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def gg():
+    import gcn_grabcut_b200 as g
+    from gcn_grabcut_b200 import _native
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    _native.handle(0)                        # fails loudly if the .so is missing / not sm_100
+    return g
+
+
+def _oracle_graph(img, seg, conn=4, k=4):
+    from oracle import graph_port
+    return graph_port.build_graph(img, seg, conn, k)
+
+
+def _assert_graph_matches(got, ref, ties=0):
+    assert got.n_nodes == ref.n_nodes
+    if ties == 0:
+        assert got.n_edges == ref.n_edges
+        assert np.array_equal(got.edge_index, ref.edge_index), "edge list differs (must be bit-exact)"
+    for name in ("node_features", "prior_features", "node_centroids", "node_areas"):
+        a, b = getattr(got, name), getattr(ref, name)
+        assert a.dtype == np.float32 and a.shape == b.shape, name
+        np.testing.assert_allclose(a, b, rtol=FEAT_RTOL, atol=FEAT_ATOL, err_msg=name)
+    if ties == 0:
+        np.testing.assert_allclose(got.edge_attr, ref.edge_attr, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+
+
+# ----------------------------------------------------------------------------- pixel planes
+def test_pixel_planes_all_colours(gg):
+    """Lab / HSV of ALL 2^24 colours against the float64 restatement (float32-rounded)."""
+    import ctypes as C
+    from gcn_grabcut_b200 import _native as nat
+    from oracle.thirdparty import rgb2hsv, rgb2lab
+    h = nat.handle(0)
+    idx = np.arange(1 << 24, dtype=np.uint32)
+    bgr = np.stack([idx & 255, (idx >> 8) & 255, idx >> 16], -1).astype(np.uint8).reshape(1, 4096, 4096, 3)
+    t = torch.from_numpy(bgr).cuda()
+    lab = torch.empty(1, 4096, 4096, 3, dtype=torch.float32, device="cuda")
+    hsv = torch.empty_like(lab)
+    nat.check(nat.lib().gg_pixel_planes(h.ptr, nat.ptr(t), 1, 4096, 4096, nat.ptr(lab), nat.ptr(hsv),
+                                        C.c_void_p(0), C.c_void_p(0), C.c_void_p(nat.current_stream(0))))
+    lab, hsv = lab.cpu().numpy()[0], hsv.cpu().numpy()[0]
+    bad_lab = bad_hsv = 0
+    worst = 0.0
+    for r0 in range(0, 4096, 256):
+        rgb = bgr[0, r0:r0 + 256, :, ::-1]
+        rl = rgb2lab(rgb).astype(np.float32)
+        rh = rgb2hsv(rgb).astype(np.float32)
+        bad_lab += int(np.sum(rl != lab[r0:r0 + 256]))
+        bad_hsv += int(np.sum(rh != hsv[r0:r0 + 256]))
+        worst = max(worst, float(np.abs(rl - lab[r0:r0 + 256]).max()))
+    print(f"Lab float32 mismatches: {bad_lab} of {3 << 24} (max |d| {worst:.3g}); HSV mismatches: {bad_hsv}")
+    assert bad_hsv == 0                       # exact-rational argument, must hold bit for bit
+    assert bad_lab <= 64 and worst < 1e-4     # 1-ulp float32 events of the fp64 cbrt only
+
+
+def test_gray_and_gradient_planes(gg):
+    import ctypes as C
+    import cv2
+    from gcn_grabcut_b200 import _native as nat
+    h = nat.handle(0)
+    rng = np.random.RandomState(5)
+    img = rng.randint(0, 256, (2, 37, 53, 3), dtype=np.uint8)
+    t = torch.from_numpy(img).cuda()
+    gray = torch.empty(2, 37, 53, dtype=torch.float32, device="cuda")
+    grad = torch.empty_like(gray)
+    nat.check(nat.lib().gg_pixel_planes(h.ptr, nat.ptr(t), 2, 37, 53, C.c_void_p(0), C.c_void_p(0),
+                                        nat.ptr(gray), nat.ptr(grad), C.c_void_p(nat.current_stream(0))))
+    for b in range(2):
+        g = cv2.cvtColor(img[b], cv2.COLOR_BGR2GRAY).astype(np.float32)
+        gx = cv2.Sobel(g, cv2.CV_32F, 1, 0, ksize=3)
+        gy = cv2.Sobel(g, cv2.CV_32F, 0, 1, ksize=3)
+        assert np.array_equal(gray[b].cpu().numpy(), g)
+        assert np.array_equal(grad[b].cpu().numpy(), np.sqrt(gx ** 2 + gy ** 2))
+
+
+# ----------------------------------------------------------------------------- graph construction
+@pytest.mark.parametrize("name", golden_cases())
+def test_graph_builder_vs_golden(gg, name):
+    """GraphBuilder(image, cfg, segments).build() against the reference's own output."""
+    g = load_golden(name)
+    img, seg = golden_inputs(g, name)
+    cfg = gg.SuperpixelGraphConfig(n_segments=int(g["n_segments"]), connectivity=int(g["connectivity"]),
+                                   n_nonlocal=int(g["n_nonlocal"]))
+    got = gg.GraphBuilder(img, cfg, segments=seg).build()
+    assert got.n_nodes == int(g["n_nodes"]) and got.n_edges == int(g["n_edges"])
+    assert got.edge_index.dtype == np.int64 and np.array_equal(got.edge_index, g["edge_index"])
+    assert got.node_input().shape == (got.n_nodes, 19)
+    for key, mine in (("node_features", got.node_features), ("edge_attr", got.edge_attr),
+                      ("prior_features", got.prior_features), ("node_centroids", got.node_centroids),
+                      ("node_areas", got.node_areas)):
+        np.testing.assert_allclose(mine, g[key], rtol=FEAT_RTOL, atol=FEAT_ATOL, err_msg=key)
+        print(f"{name}:{key}: bit-equal {np.mean(mine == g[key]):.5f}, max|d| {np.abs(mine - g[key]).max():.3g}")
+
+
+@pytest.mark.parametrize("conn,k,H,W,nseg", [(4, 4, 320, 480, 300), (8, 4, 200, 264, 120),
+                                             (4, 8, 240, 320, 200), (4, 0, 128, 160, 60),
+                                             (4, 16, 161, 203, 90)])
+def test_graph_batch_vs_oracle(gg, conn, k, H, W, nseg):
+    from gcn_grabcut_b200.synthetic import make_batch
+    B = 6
+    imgs, labs = make_batch(B, H, W, nseg, seed0=100)
+    cfg = gg.SuperpixelGraphConfig(n_segments=nseg, connectivity=conn, n_nonlocal=k)
+    batch = gg.build_graph_batch(imgs, labs, cfg)
+    graphs = batch.to_graphs(labs)
+    shared = batch.shared_cnt.cpu().numpy().reshape(B, batch.pair_cap)
+    n_adj = batch.n_adj_pairs.cpu().numpy()
+    total_ties = 0
+    for b in range(B):
+        ref = _oracle_graph(imgs[b], labs[b], conn, k)
+        ties = int(ref.stages["knn_ties"])
+        total_ties += ties
+        _assert_graph_matches(graphs[b], ref, ties)
+        # adjacency pairs and shared boundary lengths: integer, bit-exact
+        assert n_adj[b] == len(ref.stages["adj_pairs"])
+        assert np.array_equal(shared[b, :n_adj[b]], ref.stages["adj_counts"])
+        assert np.array_equal(graphs[b].edge_index[:, :n_adj[b]].T, ref.stages["adj_pairs"])
+    print(f"conn={conn} k={k}: kNN tie rows over the batch: {total_ties}")
+
+
+def test_graph_edge_cases(gg):
+    rng = np.random.RandomState(3)
+    # (a) ragged label maps: absent labels (area-0 regions), label 0 absent, tiny non-multiple-of-32 image
+    img = rng.randint(0, 256, (2, 19, 45, 3), dtype=np.uint8)
+    seg = np.zeros((2, 19, 45), np.int32)
+    seg[0, :, 20:] = 3
+    seg[0, 10:, :10] = 5
+    seg[1, :9, :] = 1
+    seg[1, 9:, :22] = 2
+    seg[1, 9:, 22:] = 7
+    for k in (0, 2, 4):
+        cfg = gg.SuperpixelGraphConfig(connectivity=8, n_nonlocal=k)
+        graphs = gg.build_graph_batch(img, seg, cfg).to_graphs(seg)
+        for b in range(2):
+            ref = _oracle_graph(img[b], seg[b], 8, k)
+            _assert_graph_matches(graphs[b], ref, int(ref.stages["knn_ties"]))
+    # (b) N <= k+1: no non-local edges (graph_builder.py:291)
+    seg2 = np.zeros((1, 32, 32), np.int32)
+    seg2[0, :, 16:] = 1
+    seg2[0, 16:, :16] = 2
+    img2 = rng.randint(0, 256, (1, 32, 32, 3), dtype=np.uint8)
+    g2 = gg.build_graph_batch(img2, seg2, gg.SuperpixelGraphConfig(n_nonlocal=4)).to_graphs(seg2)[0]
+    ref2 = _oracle_graph(img2[0], seg2[0], 4, 4)
+    _assert_graph_matches(g2, ref2)
+    assert g2.n_edges == 2 * 3 and np.all(g2.edge_attr[:, 4] == 0)
+    # (c) label >= node_cap is reported, not silently dropped
+    from gcn_grabcut_b200._native import NativeError
+    with pytest.raises(NativeError):
+        gg.build_graph_batch(img2, seg2, node_cap=2)
+
+
+def test_graph_invariants_full_size(gg):
+    """Config B (256 x 320x480, ~300 regions): size-independent properties of the result."""
+    from gcn_grabcut_b200.synthetic import make_batch
+    B, H, W = 256, 320, 480
+    imgs, labs = make_batch(8, H, W, 300, seed0=7)
+    reps = B // 8
+    imgs_b, labs_b = np.tile(imgs, (reps, 1, 1, 1)), np.tile(labs, (reps, 1, 1))
+    batch = gg.build_graph_batch(imgs_b, labs_b, gg.SuperpixelGraphConfig())
+    no, eo = batch.node_off.cpu().numpy(), batch.edge_off.cpu().numpy()
+    x = batch.x.cpu().numpy()
+    ei = batch.edge_index.cpu().numpy()
+    for b in range(B):
+        n0, n1, e0, e1 = no[b], no[b + 1], eo[b], eo[b + 1]
+        assert n1 - n0 == labs_b[b].max() + 1
+        np.testing.assert_allclose(x[n0:n1, 11].sum(), 1.0, rtol=1e-5)        # area ratios sum to 1
+        src, dst = ei[0, e0:e1], ei[1, e0:e1]
+        half = (e1 - e0) // 2
+        assert np.array_equal(src[:half], dst[half:]) and np.array_equal(dst[:half], src[half:])
+        assert np.all(src[:half] < dst[:half])
+        assert np.array_equal(np.bincount(src, minlength=n1 - n0), np.bincount(dst, minlength=n1 - n0))
+    # identical images in the batch give identical graphs (replicas 0 and 8, 16, ...)
+    for b in range(8, B, 8):
+        assert np.array_equal(ei[:, eo[b]:eo[b + 1]], ei[:, eo[0]:eo[1]])
+        np.testing.assert_allclose(x[no[b]:no[b + 1]], x[no[0]:no[1]], rtol=1e-6, atol=1e-7)
+    # against the oracle on the 8 distinct images
+    graphs = batch.to_graphs(labs_b)
+    for b in range(8):
+        ref = _oracle_graph(imgs[b], labs[b])
+        _assert_graph_matches(graphs[b], ref, int(ref.stages["knn_ties"]))
+
+
+# ----------------------------------------------------------------------------- network
+def _golden_data(gg, g):
+    x = torch.tensor(np.concatenate([g["node_features"], g["prior_features"]], 1))
+    return gg.Data(x=x, edge_index=torch.tensor(g["edge_index"]), edge_attr=torch.tensor(g["edge_attr"]))
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("name", golden_cases())
+def test_resgcn_vs_golden(gg, name, impl):
+    from gcn_grabcut_b200 import _native as nat
+    from oracle.model_port import random_state_dict
+    g = load_golden(name)
+    D, n = int(g["hidden"]), int(g["n_layers"])
+    net = gg.ResGCNNet(hidden_channels=D, n_layers=n)
+    net.load_state_dict(random_state_dict(D, n, seed=int(g["seed"])))
+    net = net.to("cuda").eval()
+    nat.handle(0).set_option("gemm_impl", 0 if impl == "simt" else 1)
+    try:
+        data = _golden_data(gg, g).to("cuda")
+        logits = net(data).cpu().numpy()
+        probs = net.predict_probs(data)
+    finally:
+        nat.handle(0).set_option("gemm_impl", 1)
+    print(f"{name}[{impl}]: max|dlogit| {np.abs(logits - g['logits']).max():.3g}  "
+          f"max|dprob| {np.abs(probs - g['probs']).max():.3g}")
+    assert probs.dtype == np.float32 and probs.shape == (int(g["n_nodes"]), 3)
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(logits, g["logits"], atol=5e-4, rtol=1e-4)
+    np.testing.assert_allclose(probs, g["probs"], atol=POST_ATOL)
+
+
+def test_resgcn_batched_equals_single(gg):
+    """The reference's invariant (tests/test.py:294-306): a batch == one graph at a time @1e-4,
+    on its own test graphs (path graph, randn features, seeded)."""
+    from oracle import model_port
+    state = model_port.random_state_dict(32, 2, seed=5)
+    net = gg.ResGCNNet(hidden_channels=32, n_layers=2)
+    net.load_state_dict(state)
+    net = net.to("cuda")
+
+    def make(N, seed):
+        gen = torch.Generator().manual_seed(seed)
+        x = torch.randn(N, 19, generator=gen)
+        s, d = torch.arange(N - 1), torch.arange(1, N)
+        ei = torch.stack([torch.cat([s, d]), torch.cat([d, s])])
+        ea = torch.rand(ei.size(1), 5, generator=gen)
+        return x, ei, ea
+    graphs = [make(40, s) for s in (1, 2, 3)]
+    one = torch.cat([net(gg.Data(x=x, edge_index=ei, edge_attr=ea).to("cuda")).cpu() for x, ei, ea in graphs])
+    xb = torch.cat([g[0] for g in graphs])
+    eib = torch.cat([g[1] + 40 * i for i, g in enumerate(graphs)], 1)
+    eab = torch.cat([g[2] for g in graphs])
+    batch = torch.arange(3).repeat_interleave(40)
+    both = net(gg.Data(x=xb, edge_index=eib, edge_attr=eab, batch=batch).to("cuda")).cpu()
+    assert both.shape == (120, 3)
+    assert torch.allclose(one, both, atol=1e-4)
+    ref = model_port.resgcn_forward(state, xb, eib, eab, batch)
+    assert torch.allclose(both, ref, atol=5e-4, rtol=1e-4)
+    # output depends on input (tests/test.py:282-292)
+    assert not torch.allclose(one[:40], one[40:80])
+    # shuffled COO order gives the same result (CSR is rebuilt deterministically)
+    perm = torch.randperm(eib.size(1), generator=torch.Generator().manual_seed(0))
+    shuf = net(gg.Data(x=xb, edge_index=eib[:, perm], edge_attr=eab[perm], batch=batch).to("cuda")).cpu()
+    assert torch.allclose(shuf, both, atol=1e-5)
+
+
+def test_predict_trimap_and_node_labels(gg):
+    from oracle import model_port
+    g = load_golden("geom_160x192_n48")
+    img, seg = golden_inputs(g, "geom_160x192_n48")
+    net = gg.ResGCNNet(hidden_channels=32, n_layers=2)
+    net.load_state_dict(model_port.random_state_dict(32, 2, seed=int(g["seed"])))
+    net = net.to("cuda")
+    tri = net.predict_trimap(_golden_data(gg, g).to("cuda"), seg, 0.55, 0.55)
+    assert tri.shape == seg.shape and tri.dtype == np.uint8
+    assert set(np.unique(tri)).issubset({0, 1, 2, 3})
+    probs = net.predict_probs(_golden_data(gg, g).to("cuda"))
+    assert np.array_equal(tri, model_port.probs_to_trimap(probs, seg, 0.55, 0.55))
+    # padding rule: labels without a probability row become GC_PR_BGD (model.py:672-677)
+    assert np.array_equal(gg._probs_to_trimap(g["probs"][:10], seg, 0.55, 0.55),
+                          model_port.probs_to_trimap(g["probs"][:10], seg, 0.55, 0.55))
+    assert np.array_equal(gg.probs_to_node_trimap(g["probs"]), model_port.probs_to_node_trimap(g["probs"]))
+
+
+# ----------------------------------------------------------------------------- projection
+@pytest.mark.parametrize("name", golden_cases())
+def test_refine_trimap_vs_golden(gg, name):
+    from oracle import trimap_port
+    g = load_golden(name)
+    img, seg = golden_inputs(g, name)
+    for (tf, tb, r, eps, key) in ((0.55, 0.55, 8, 1e-3, "trimap_refined"), (0.4, 0.45, 4, 1e-2, "trimap_r4")):
+        tri, pbg, pfg = gg.refine_trimap(g["probs"], seg, img, tf, tb, radius=r, eps=eps, return_planes=True)
+        _, rbg, rfg = trimap_port.refine_trimap(g["probs"], seg, img, tf, tb, r, eps, return_planes=True)
+        np.testing.assert_allclose(pbg, rbg, atol=2e-6)
+        np.testing.assert_allclose(pfg, rfg, atol=2e-6)
+        near = trimap_port.near_threshold_mask(rbg, rfg, tf, tb, TRI_TOL)
+        bad = (tri != g[key]) & ~near
+        print(f"{name}:{key}: mismatches {int((tri != g[key]).sum())} (near a threshold: {int(near.sum())}), "
+              f"planes bit-equal {np.mean(pfg == rfg):.5f}")
+        assert tri.dtype == np.uint8 and not bad.any()
+
+
+def test_guided_filter_vs_cv2(gg):
+    from oracle import trimap_port
+    rng = np.random.RandomState(0)
+    for (H, W, r) in ((97, 131, 8), (64, 64, 4), (33, 200, 1), (20, 24, 12)):
+        guide = rng.rand(H, W).astype(np.float32)
+        src = (rng.rand(H, W) > 0.5).astype(np.float32) * 0.7 + 0.1
+        out = gg.guided_filter(guide, src, r, 1e-3)
+        ref = trimap_port.guided_filter(guide, src, r, 1e-3)
+        np.testing.assert_allclose(out, ref, atol=3e-6, rtol=1e-5)
+
+
+# ----------------------------------------------------------------------------- whole path
+@pytest.mark.parametrize("edge_aware", [True, False])
+def test_trimap_path_host_vs_oracle(gg, edge_aware):
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import model_port, trimap_port
+    B, H, W = 10, 200, 264
+    imgs, labs = make_batch(B, H, W, 120, seed0=40)
+    state = model_port.random_state_dict(64, 3, seed=1)
+    path = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=int(labs.max()) + 1,
+                         edge_aware=edge_aware, chunk=4)            # 3 chunks: exercises the pipelining
+    tri, nn, ne = path(imgs, labs, return_counts=True)
+    assert tri.shape == (B, H, W) and tri.dtype == np.uint8
+    n_bad = 0
+    for b in range(B):
+        ref = _oracle_graph(imgs[b], labs[b])
+        assert nn[b] == ref.n_nodes and (ne[b] == ref.n_edges or int(ref.stages["knn_ties"]))
+        probs = model_port.predict_probs(state, torch.tensor(ref.node_input()), torch.tensor(ref.edge_index),
+                                         torch.tensor(ref.edge_attr))
+        if edge_aware:
+            rt, rbg, rfg = trimap_port.refine_trimap(probs, labs[b], imgs[b], return_planes=True)
+            near = trimap_port.near_threshold_mask(rbg, rfg, 0.55, 0.55, 2e-4)
+        else:
+            rt = model_port.probs_to_trimap(probs, labs[b], 0.55, 0.55)
+            pn = probs[labs[b]]
+            near = trimap_port.near_threshold_mask(pn[..., 0], pn[..., 2], 0.55, 0.55, 2e-4)
+        n_bad += int(((tri[b] != rt) & ~near).sum())
+    assert n_bad == 0
+    # device-resident entry point gives the same trimaps
+    td = path.run_device(torch.from_numpy(imgs).cuda(), torch.from_numpy(labs).cuda())
+    assert np.array_equal(td.cpu().numpy(), tri)
