@@ -92,7 +92,8 @@ EXPORTED_SYMBOLS = (
     "gg_abi_version", "gg_last_error", "gg_create", "gg_destroy", "gg_set_option",
     "gg_check_device_status", "gg_build_graphs", "gg_pixel_planes", "gg_load_weights",
     "gg_coo_to_csr", "gg_resgcn_forward", "gg_refine_trimap", "gg_project_trimap",
-    "gg_guided_filter", "gg_trimap_path_host", "gg_trimap_path_device", "gg_kernel_launch_count")
+    "gg_guided_filter", "gg_trimap_path_host", "gg_trimap_path_device", "gg_kernel_launch_count",
+    "gg_profile_enable", "gg_profile_report")
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -139,6 +140,8 @@ def lib() -> C.CDLL:
             L.gg_trimap_path_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                 C.c_int, C.POINTER(PathConfig), C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]
+            L.gg_profile_enable.argtypes = [C.c_void_p, C.c_int]
+            L.gg_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
             _lib = L
     return _lib
 
@@ -172,6 +175,19 @@ class Handle:
         bits = C.c_int(0)
         check(lib().gg_check_device_status(self._h, C.c_void_p(stream), C.byref(bits)))
 
+    def profile(self, enable: bool) -> None:
+        check(lib().gg_profile_enable(self._h, int(bool(enable))))
+
+    def profile_report(self):
+        """[(kernel, launches, total_ms)] sorted by total time, from the CUDA-event session."""
+        buf = C.create_string_buffer(1 << 16)
+        check(lib().gg_profile_report(self._h, buf, len(buf)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(",", 2)
+            rows.append((name, int(n), float(ms)))
+        return rows
+
     def close(self):
         if self._h:
             lib().gg_destroy(self._h)
@@ -198,6 +214,8 @@ def device_index(device) -> int:
     d = torch.device(device) if not isinstance(device, torch.device) else device
     if d.type != "cuda":
         raise NativeError(GG_ERR_CUDA, f"device {d}: the trimap path runs on CUDA only (no CPU fallback)")
+    if not torch.cuda.is_available():
+        raise NativeError(GG_ERR_CUDA, "no CUDA device visible; gcn_grabcut_b200 has no CPU fallback")
     return torch.cuda.current_device() if d.index is None else d.index
 
 

@@ -42,6 +42,21 @@ void Arena::release() {
   cap = off = 0;
 }
 
+static cudaEvent_t prof_event(gg_context* ctx) {
+  if (ctx->prof_pool_used == ctx->prof_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->prof_pool.push_back(e);
+  }
+  return ctx->prof_pool[ctx->prof_pool_used++];
+}
+void prof_begin(gg_context* ctx, const char* name, cudaStream_t st) {
+  gg_context::ProfRec r{name, prof_event(ctx), prof_event(ctx)};
+  cudaEventRecord(r.e0, st);
+  ctx->prof.push_back(r);
+}
+void prof_end(gg_context* ctx, cudaStream_t st) { cudaEventRecord(ctx->prof.back().e1, st); }
+
 __global__ void k_status_or(const int* __restrict__ word, int* __restrict__ sticky) {
   if (*word) atomicOr(sticky, *word);
 }
@@ -184,6 +199,7 @@ void gg_destroy(gg_handle h) {
   if (h->d_status) cudaFree(h->d_status);
   if (h->d_lin) cudaFree(h->d_lin);
   for (auto& ev : h->ev) cudaEventDestroy(ev);
+  for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_run) cudaStreamDestroy(h->s_run);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -361,5 +377,41 @@ int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* lab
 }
 
 int64_t gg_kernel_launch_count(gg_handle h) { return h ? h->launches : 0; }
+
+int gg_profile_enable(gg_handle h, int enable) {
+  GG_REQUIRE(h, "gg_profile_enable: null");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_CUDA_OK(cudaDeviceSynchronize());
+  h->prof_on = enable != 0;
+  h->prof.clear();
+  h->prof_pool_used = 0;
+  return GG_OK;
+}
+
+// Text report "kernel,launches,total_ms\n" per kernel, sorted by total time (descending).
+int gg_profile_report(gg_handle h, char* buf, size_t cap) {
+  GG_REQUIRE(h && buf && cap > 0, "gg_profile_report: null");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_CUDA_OK(cudaDeviceSynchronize());
+  struct Acc { const char* name; long n; double ms; };
+  std::vector<Acc> acc;
+  for (auto& r : h->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    bool found = false;
+    for (auto& a : acc)
+      if (!strcmp(a.name, r.name)) { a.n++; a.ms += ms; found = true; break; }
+    if (!found) acc.push_back({r.name, 1, (double)ms});
+  }
+  std::sort(acc.begin(), acc.end(), [](const Acc& a, const Acc& b) { return a.ms > b.ms; });
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& a : acc) {
+    int w = snprintf(buf + off, cap - off, "%s,%ld,%.6f\n", a.name, a.n, a.ms);
+    if (w < 0 || (size_t)w >= cap - off) break;
+    off += (size_t)w;
+  }
+  return GG_OK;
+}
 
 }  // extern "C"

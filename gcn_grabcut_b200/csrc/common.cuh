@@ -85,8 +85,7 @@ struct NetWeights {
   // tcgen05 operand images (bf16 split, canonical K-major SWIZZLE_128B), see gemm_tc.cuh
   void* tc_blob = nullptr;
   size_t tc_bytes = 0;
-  std::vector<size_t> tc_gcn;  // byte offsets per layer
-  size_t tc_sage = 0, tc_fuse = 0, tc_gate = 0, tc_enc2 = 0;
+  std::vector<size_t> tc_off;  // byte offset of each GEMM's operand image (by GEMM id), -1 = none
 };
 
 }  // namespace gg
@@ -104,11 +103,24 @@ struct gg_context {
   int gemm_impl = 1;      // 0 = SIMT fp32 (validation), 1 = tcgen05 bf16x3
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev;
+  // per-kernel CUDA-event timing (gg_profile_enable / gg_profile_report)
+  bool prof_on = false;
+  struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_pool;
+  size_t prof_pool_used = 0;
 };
+
+namespace gg {
+void prof_begin(gg_context* ctx, const char* name, cudaStream_t st);
+void prof_end(gg_context* ctx, cudaStream_t st);
+}
 
 #define GG_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)        \
   do {                                                                \
+    if ((ctx)->prof_on) gg::prof_begin((ctx), #kernel, (stream));     \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);       \
+    if ((ctx)->prof_on) gg::prof_end((ctx), (stream));                \
     (ctx)->launches++;                                                \
     GG_CUDA_OK(cudaGetLastError());                                   \
   } while (0)

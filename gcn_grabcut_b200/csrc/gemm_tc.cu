@@ -1,13 +1,322 @@
-// tcgen05 tensor-core path for the dense node / edge transforms (placeholder until validated).
+// tcgen05 tensor-core path for the dense per-node / per-edge transforms of ResGCNNet.
+//
+//   C[M,N] (+)= act(A[M,K] W[N,K]^T + bias)        M ~ 10^4..10^5 rows, N,K in {64,128}
+//
+// fp32 semantics on bf16 tensor cores: every fp32 operand is split into three bf16 terms
+// (x = x1 + x2 + x3, residuals exact in fp32) and the six products with i+j <= 4
+// (x1w1, x1w2, x2w1, x2w2, x1w3, x3w1) are accumulated in fp32 in TMEM -- the dropped terms
+// are O(2^-24) relative, i.e. fp32-class accuracy, at 6 MMA passes.
+//
+// Kernel structure (one persistent CTA per SM, 256 threads):
+//   * the weight operand W is pre-split and pre-swizzled ON THE HOST at gg_load_weights
+//     time into the exact shared-memory image (canonical K-major SWIZZLE_128B atoms); each CTA
+//     pulls it in once with a single 1-D bulk TMA copy (cp.async.bulk + mbarrier tx-count);
+//   * per 128-row tile: all warps load the fp32 A rows (coalesced float4), split them and
+//     store the three bf16 images with the 128B swizzle applied by hand; fence.proxy.async;
+//   * one thread issues the 6 x K/16 tcgen05.mma (M=128, N, K=16; accumulator in TMEM) and
+//     commits to an mbarrier;
+//   * all warps read the accumulator back with tcgen05.ld (32 lanes x 32 columns per
+//     instruction), apply bias / activation / accumulate and store fp32 rows.
+// SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UBLKCP (bulk TMA).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "resgcn.cuh"
 
 namespace gg {
-int gemm_tc_prepare_weights(gg_context*, const std::vector<float>&) { return GG_OK; }
-bool gemm_tc_supported(const gg_context*, int, int, int) { return false; }
-int gemm_tc(gg_context*, cudaStream_t, int, const float*, const float*, float*, const int*, long long,
-            int, int, int, int) {
-  set_error("gemm_tc: not built");
-  return GG_ERR_STATE;
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 256;
+
+// ----------------------------------------------------------------------------- PTX wrappers
+GG_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+GG_D void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+GG_D void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+GG_D void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+GG_D void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+GG_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+GG_D void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+GG_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+GG_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+GG_D void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+GG_D void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+GG_D void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+GG_D void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+GG_D void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+GG_D void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows
+// x 128 B = 1024) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+GG_D uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
+// both K-major, N>>3 at [17,23), M>>4 at [24,29)
+GG_HD uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+GG_D float gelu_erf_tc(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// byte offset of element (row r, k) inside one split image made of K/64 atoms of [rows x 128 B]
+GG_HD uint32_t sw128_offset(int r, int k, int rows) {
+  const int a = k >> 6, c = (k & 63) >> 3, j = k & 7;
+  return (uint32_t)(a * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4) + j * 2);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const float* __restrict__ bias,
+          float* __restrict__ C, const int* __restrict__ m_ptr, int N, int K, int accumulate) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  const int M = *m_ptr;
+  const int n_tiles = (M + TC_BM - 1) / TC_BM;
+  if ((int)blockIdx.x >= n_tiles) return;
+
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* smem = tc_smem_raw + (base - raw);
+  const int n_atoms = K >> 6;
+  const uint32_t a_split = (uint32_t)n_atoms * TC_BM * 128;       // bytes of one A split image
+  const uint32_t b_split = (uint32_t)n_atoms * N * 128;
+  const uint32_t sA = base, sB = base + 3 * a_split;
+  unsigned char* pA = smem;
+  const uint32_t ctrl = sB + 3 * b_split;                         // barriers + tmem pointer
+  const uint32_t bar_b = ctrl, bar_mma = ctrl + 8, tmem_slot = ctrl + 16;
+  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem + 3 * a_split + 3 * b_split + 16);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tmem_cols = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+
+  if (tid == 0) {
+    mbar_init(bar_b, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+  if (tid == 0) {
+    mbar_expect_tx(bar_b, 3 * b_split);
+    bulk_g2s(sB, Bimg, 3 * b_split, bar_b);
+  }
+  const uint32_t idesc = umma_idesc_bf16(TC_BM, N);
+  const int k4 = K >> 2;                                           // float4 per row
+
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int row0 = tile * TC_BM;
+    // ---- A tile: fp32 rows -> three swizzled bf16 images
+    for (int r = warp; r < TC_BM; r += TC_THREADS / 32) {
+      const int row = row0 + r;
+      for (int q = lane; q < k4; q += 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < M) v = *reinterpret_cast<const float4*>(A + (size_t)row * K + 4 * q);
+        const float x[4] = {v.x, v.y, v.z, v.w};
+        uint32_t w[3][2];
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+          unsigned short hb[3][2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float rres = x[e + u];
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const __nv_bfloat16 b = __float2bfloat16_rn(rres);
+              hb[s][u] = __bfloat16_as_ushort(b);
+              rres -= __bfloat162float(b);
+            }
+          }
+#pragma unroll
+          for (int s = 0; s < 3; ++s) w[s][e >> 1] = (uint32_t)hb[s][0] | ((uint32_t)hb[s][1] << 16);
+        }
+        const uint32_t off = sw128_offset(r, 4 * q, TC_BM);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+          *reinterpret_cast<uint2*>(pA + s * a_split + off) = make_uint2(w[s][0], w[s][1]);
+      }
+    }
+    fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core
+    __syncthreads();
+
+    // ---- MMA: one thread issues 6 x (K/16) tcgen05.mma, accumulator in TMEM
+    if (tid == 0) {
+      if (it == 0) mbar_wait(bar_b, 0);
+      tc_fence_after();
+      const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+      uint32_t acc = 0;
+#pragma unroll
+      for (int t = 5; t >= 0; --t) {     // small terms first
+        for (int a = 0; a < n_atoms; ++a) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = umma_desc(sA + pa[t] * a_split + a * (TC_BM * 128) + kk * 32);
+            const uint64_t bd = umma_desc(sB + pb[t] * b_split + a * (N * 128) + kk * 32);
+            umma_bf16(tmem_base, ad, bd, idesc, acc);
+            acc = 1;
+          }
+        }
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, it & 1);
+    tc_fence_after();
+
+    // ---- epilogue: TMEM -> registers -> bias / activation / accumulate -> global
+    {
+      const int q = warp & 3, hh = warp >> 2;
+      const int row = row0 + 32 * q + lane;
+      const int ncol_w = N >> 1;                        // columns per warp
+      for (int c0 = 0; c0 < ncol_w; c0 += 32) {
+        const int col0 = hh * ncol_w + c0;
+        uint32_t rr[32];
+        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, rr);
+        tmem_ld_wait();
+        if (row < M) {
+          float* crow = C + (size_t)row * N + col0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 o;
+            float* op = reinterpret_cast<float*>(&o);
+            float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (accumulate) prev = *reinterpret_cast<const float4*>(crow + i);
+            const float* pp = reinterpret_cast<const float*>(&prev);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float v = __uint_as_float(rr[i + u]) + (bias ? bias[col0 + i + u] : 0.0f) + pp[u];
+              if (ACT == 1) v = gelu_erf_tc(v);
+              if (ACT == 2) v = 1.0f / (1.0f + expf(-v));
+              op[u] = v;
+            }
+            *reinterpret_cast<float4*>(crow + i) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                      // TMEM and the A images may be overwritten
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ----------------------------------------------------------------------------- host side
+static size_t tc_image_bytes(int N, int K) { return (size_t)3 * (K / 64) * N * 128; }
+
+static void pack_weight(const float* W, int N, int K, uint8_t* img) {
+  const size_t split = (size_t)(K / 64) * N * 128;
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      float r = W[(size_t)n * K + k];
+      const uint32_t off = sw128_offset(n, k, N);
+      for (int s = 0; s < 3; ++s) {
+        const __nv_bfloat16 b = __float2bfloat16_rn(r);
+        const unsigned short bits = __bfloat16_as_ushort(b);
+        memcpy(img + s * split + off, &bits, 2);
+        r -= __bfloat162float(b);
+      }
+    }
+}
+
+static bool tc_shape_ok(int N, int K) {
+  return (K == 64 || K == 128) && (N == 64 || N == 128);
+}
+
+int gemm_tc_prepare_weights(gg_context* ctx, const std::vector<float>& blob) {
+  NetWeights& nw = ctx->net;
+  if (nw.tc_blob) { cudaFree(nw.tc_blob); nw.tc_blob = nullptr; }
+  nw.tc_bytes = 0;
+  nw.tc_off.assign(GEMM_GCN0 + nw.n_layers, (size_t)-1);
+  const int D = nw.D, c = nw.c;
+  struct Item { int which; size_t w_off; int N, K; };
+  std::vector<Item> items = {{GEMM_ENC2, nw.ee2_w, c, c}, {GEMM_GATE, nw.eg_w, D, c},
+                             {GEMM_SAGE_L, nw.sage_wl, D, D}, {GEMM_SAGE_R, nw.sage_wr, D, D},
+                             {GEMM_FUSE, nw.fuse_w, D, D}};
+  for (int l = 0; l < nw.n_layers; ++l) items.push_back({GEMM_GCN0 + l, nw.gcn_w[l], D, D});
+  size_t total = 0;
+  for (auto& it : items)
+    if (tc_shape_ok(it.N, it.K)) { nw.tc_off[it.which] = total; total += (tc_image_bytes(it.N, it.K) + 1023) & ~size_t(1023); }
+  if (total == 0) return GG_OK;
+  std::vector<uint8_t> host(total, 0);
+  for (auto& it : items)
+    if (tc_shape_ok(it.N, it.K)) pack_weight(blob.data() + it.w_off, it.N, it.K, host.data() + nw.tc_off[it.which]);
+  GG_CUDA_OK(cudaMalloc(&nw.tc_blob, total));
+  GG_CUDA_OK(cudaMemcpy(nw.tc_blob, host.data(), total, cudaMemcpyHostToDevice));
+  nw.tc_bytes = total;
+  return GG_OK;
+}
+
+bool gemm_tc_supported(const gg_context* ctx, int which, int N, int K) {
+  const NetWeights& nw = ctx->net;
+  return nw.tc_blob != nullptr && which >= 0 && which < (int)nw.tc_off.size() &&
+         nw.tc_off[which] != (size_t)-1 && tc_shape_ok(N, K);
+}
+
+int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* bias, float* C,
+            const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate) {
+  const NetWeights& nw = ctx->net;
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(nw.tc_blob) + nw.tc_off[which];
+  const size_t smem = (size_t)3 * (K / 64) * TC_BM * 128 + tc_image_bytes(N, K) + 64 + 1024;
+  const int tiles_cap = ceil_div(m_cap, TC_BM);
+  const int grid = tiles_cap < ctx->sm_count ? tiles_cap : ctx->sm_count;
+  if (act == 0) {
+    GG_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GG_LAUNCH(ctx, k_tc_gemm<0>, grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, K, accumulate);
+  } else if (act == 1) {
+    GG_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GG_LAUNCH(ctx, k_tc_gemm<1>, grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, K, accumulate);
+  } else {
+    GG_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GG_LAUNCH(ctx, k_tc_gemm<2>, grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, K, accumulate);
+  }
+  return GG_OK;
+}
+
 }  // namespace gg

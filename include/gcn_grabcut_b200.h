@@ -231,6 +231,13 @@ int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* la
 /* Number of kernels of this library launched by this handle so far (bench bookkeeping). */
 int64_t gg_kernel_launch_count(gg_handle h);
 
+/* Per-kernel timing with CUDA events recorded on the launching stream around every kernel
+ * of this library.  enable=1 starts a fresh session, enable=0 stops recording.
+ * gg_profile_report synchronises the device and writes one line per kernel,
+ * "name,launches,total_ms", sorted by total time, into buf (NUL-terminated). */
+int gg_profile_enable(gg_handle h, int enable);
+int gg_profile_report(gg_handle h, char* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif
