@@ -9,15 +9,16 @@
 // sliding sums (vertical pass, then horizontal pass, through shared memory), the algebra
 // uses round-to-nearest intrinsics that are never contracted into FMAs.
 //
-// Two tiled kernels: (1) means of {g, g^2, s_c, g s_c} -> a_c, b_c planes;
-//                    (2) means of {a_c, b_c} -> q_c = mean(a_c) g + mean(b_c) -> clip -> labels.
+// Two column-walker kernels: (1) means of {g, g^2, s_c, g s_c} -> a_c, b_c planes;
+//                            (2) means of {a_c, b_c} -> q_c = mean(a_c) g + mean(b_c) -> clip -> labels.
 #include "common.cuh"
 #include "pixel_math.cuh"
 #include "trimap.cuh"
 
 namespace gg {
 
-constexpr int GF_TY = 16, GF_TX = 64, GF_SEGX = 16, GF_THREADS = 256;
+constexpr int GF_NT = 128;          // threads per block = halo columns per block
+constexpr int GF_SY = 64;           // output rows per block (strip height)
 constexpr int GF_MAX_RADIUS = 24;
 
 struct GuidedParams {
@@ -47,179 +48,192 @@ struct GfTraits {
   static constexpr int NPLANE2 = 2 * NSRC;       // a_c, b_c
 };
 
-size_t guided_smem_bytes(int radius, bool trimap) {
-  const int tyh = GF_TY + 2 * radius, txh = GF_TX + 2 * radius;
-  const int ld = txh | 1;
-  const int nsrc = trimap ? 2 : 1;
-  const int np1 = 2 + 2 * nsrc, np2 = 2 * nsrc;
-  const size_t in1 = (size_t)(1 + nsrc) * tyh * txh * 4, in2 = (size_t)np2 * tyh * txh * 4;
-  const size_t means1 = (size_t)np1 * GF_TY * GF_TX * 4, means2 = (size_t)np2 * GF_TY * GF_TX * 4;
-  const size_t a1 = in1 > means1 ? in1 : means1, a2 = in2 > means2 ? in2 : means2;
-  const size_t v1 = (size_t)np1 * GF_TY * ld * 8, v2 = (size_t)np2 * GF_TY * ld * 8;
-  const size_t s1 = ((a1 + 15) & ~size_t(15)) + v1, s2 = ((a2 + 15) & ~size_t(15)) + v2;
-  return (s1 > s2 ? s1 : s2) + 16;
-}
+// Column walker.  Thread t owns halo column x0 - r + t of a strip and walks down its rows with
+// float64 vertical running sums of all NP planes in registers (add row y+r, subtract row
+// y-r-1; old rows are re-read through L1/L2).  Per row the sums go to a small shared row
+// buffer and (plane, segment) tasks slide the horizontal window over it; segment lengths are
+// odd so that the 64-bit reads of a warp hit distinct banks.  Means = float32(sum * 1/k^2),
+// exactly cv2.blur's float32 path.
+template <int NP>
+struct HorizontalPlan {
+  int seglen, nseg, tx;
+  __device__ HorizontalPlan(int radius) {
+    tx = GF_NT - 2 * radius;
+    const int per = GF_NT / NP;
+    seglen = ((tx + per - 1) / per) | 1;
+    nseg = (tx + seglen - 1) / seglen;
+  }
+};
 
-// Vertical sliding window sums: for plane p and halo column c, V[p][y][c] =
-// sum_{dy=0..2r} in_p[y+dy][c], y = 0..TY-1 (float64).  `value(p, row, col)` yields the
-// float32 plane value.  Then horizontal sliding sums and scaling by 1/k^2.
-template <int NP, typename ValueFn>
-GG_D void box_means(ValueFn value, double* sV, float* sM, int radius, int txh, int ld) {
-  const int k = 2 * radius + 1;
-  const double scale = 1.0 / ((double)k * (double)k);
-  // ---- vertical pass
-  for (int t = threadIdx.x; t < NP * txh; t += blockDim.x) {
-    const int p = t / txh, c = t - p * txh;
+template <int NP>
+GG_D void horizontal_means(const double* sV, float* sM, const HorizontalPlan<NP>& hp, int radius,
+                           double scale) {
+  const int t = threadIdx.x;
+  if (t < NP * hp.nseg) {
+    const int pl = t / hp.nseg, seg = t - pl * hp.nseg;
+    const int o0 = seg * hp.seglen;
+    const int len = min(hp.seglen, hp.tx - o0);
+    const double* in = sV + pl * GF_NT + o0;
+    float* out = sM + pl * GF_NT + o0;
+    const int k = 2 * radius + 1;
     double s = 0.0;
-    for (int dy = 0; dy < k; ++dy) s += (double)value(p, dy, c);
-    double* out = sV + (size_t)p * GF_TY * ld + c;
-    out[0] = s;
-    for (int y = 1; y < GF_TY; ++y) {
-      s += (double)value(p, y + k - 1, c);
-      s -= (double)value(p, y - 1, c);
-      out[(size_t)y * ld] = s;
-    }
-  }
-  __syncthreads();
-  // ---- horizontal pass (lane -> row fastest: conflict-free 64-bit reads, ld odd)
-  constexpr int NSEG = GF_TX / GF_SEGX;
-  for (int t = threadIdx.x; t < NP * GF_TY * NSEG; t += blockDim.x) {
-    const int y = t % GF_TY, seg = (t / GF_TY) % NSEG, p = t / (GF_TY * NSEG);
-    const double* in = sV + (size_t)p * GF_TY * ld + (size_t)y * ld + seg * GF_SEGX;
-    float* out = sM + ((size_t)p * GF_TY + y) * GF_TX + seg * GF_SEGX;
-    double s = 0.0;
-    for (int dx = 0; dx < k; ++dx) s += in[dx];
+    for (int d = 0; d < k; ++d) s += in[d];
     out[0] = (float)(s * scale);
-    for (int x = 1; x < GF_SEGX; ++x) {
-      s += in[x + k - 1];
-      s -= in[x - 1];
-      out[x] = (float)(s * scale);
+    for (int i = 1; i < len; ++i) {
+      s += in[i + k - 1];
+      s -= in[i - 1];
+      out[i] = (float)(s * scale);
     }
   }
-  __syncthreads();
 }
 
 template <bool kTrimap>
-__global__ void __launch_bounds__(GF_THREADS)
+__global__ void __launch_bounds__(GF_NT)
 k_guided_ab(const GuidedParams p) {
   using T = GfTraits<kTrimap>;
-  extern __shared__ __align__(16) unsigned char gf_smem[];
-  const int r = p.radius, tyh = GF_TY + 2 * r, txh = GF_TX + 2 * r, ld = txh | 1;
-  const int H = p.H, W = p.W, b = blockIdx.z;
-  const int y0 = blockIdx.y * GF_TY, x0 = blockIdx.x * GF_TX;
-  float* sIn = reinterpret_cast<float*>(gf_smem);                     // [(1+NSRC)][tyh][txh]
-  float* sM = sIn;                                                    // aliases (inputs dead by then)
-  const size_t in_bytes = (size_t)(1 + T::NSRC) * tyh * txh * 4;
-  const size_t m_bytes = (size_t)T::NPLANE1 * GF_TY * GF_TX * 4;
-  const size_t a_bytes = ((in_bytes > m_bytes ? in_bytes : m_bytes) + 15) & ~size_t(15);
-  double* sV = reinterpret_cast<double*>(gf_smem + a_bytes);
-  const int plane = tyh * txh;
-
-  // ---- load tile + halo (BORDER_REFLECT_101)
+  constexpr int NP = T::NPLANE1;
+  __shared__ double sV[NP * GF_NT];
+  __shared__ float sM[NP * GF_NT];
+  __shared__ float sLut[256];
+  const int r = p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
+  const HorizontalPlan<NP> hp(r);
+  const int x0 = blockIdx.x * hp.tx;
+  const int y_begin = blockIdx.y * GF_SY, y_end = min(H, y_begin + GF_SY);
+  const int xs = reflect101(x0 - r + t, W);
   const size_t img_off = (size_t)b * H * W;
+  const double scale = 1.0 / ((double)(2 * r + 1) * (double)(2 * r + 1));
   int64_t no = 0;
   int nn = 0;
-  if (kTrimap) { no = p.node_off[b]; nn = (int)(p.node_off[b + 1] - no); }
-  for (int i = threadIdx.x; i < plane; i += blockDim.x) {
-    const int ty = i / txh, tx = i - ty * txh;
-    const int y = reflect101(y0 + ty - r, H), x = reflect101(x0 + tx - r, W);
-    const size_t o = img_off + (size_t)y * W + x;
-    if (kTrimap) {
-      sIn[i] = __fdiv_rn((float)p.gray[o], 255.0f);
-      const int l = p.labels[o];
-      float pb = 0.0f, pf = 0.0f;                      // project_to_pixels zero padding
-      if (l >= 0 && l < nn) { const float* row = p.probs + (size_t)(no + l) * 3; pb = row[0]; pf = row[2]; }
-      sIn[plane + i] = pb;
-      sIn[2 * plane + i] = pf;
-    } else {
-      sIn[i] = p.guide[o];
-      sIn[plane + i] = p.src[o];
-    }
+  if (kTrimap) {
+    no = p.node_off[b];
+    nn = (int)(p.node_off[b + 1] - no);
+    for (int i = t; i < 256; i += GF_NT) sLut[i] = __fdiv_rn((float)i, 255.0f);   // guide = gray/255
+    __syncthreads();
   }
-  __syncthreads();
-  auto value = [&](int pl, int row, int col) -> float {
-    const int i = row * txh + col;
-    const float g = sIn[i];
-    if (pl == 0) return g;
-    if (pl == 1) return __fmul_rn(g, g);
-    const int c = (pl - 2) >> 1;
-    const float s = sIn[(1 + c) * plane + i];
-    return ((pl - 2) & 1) ? __fmul_rn(g, s) : s;
+  // base planes of one pixel of this thread's column: g and the NSRC source planes
+  auto fetch = [&](int yy, float& g, float (&sv)[T::NSRC]) {
+    const size_t o = img_off + (size_t)reflect101(yy, H) * W + xs;
+    if (kTrimap) {
+      g = sLut[p.gray[o]];
+      const int l = p.labels[o];
+      sv[0] = 0.0f;
+      sv[T::NSRC - 1] = 0.0f;                       // project_to_pixels zero padding
+      if (l >= 0 && l < nn) {
+        const float* row = p.probs + (size_t)(no + l) * 3;
+        sv[0] = row[0];
+        sv[T::NSRC - 1] = row[2];
+      }
+    } else {
+      g = p.guide[o];
+      sv[0] = p.src[o];
+    }
   };
-  // means are written over the input area: every thread must be done reading inputs, which
-  // box_means guarantees (its first barrier separates the vertical pass from the writes)
-  box_means<T::NPLANE1>(value, sV, sM, r, txh, ld);
-
-  // ---- a_c = cov/(var+eps), b_c = mean_s - a_c mean_g
-  for (int i = threadIdx.x; i < GF_TY * GF_TX; i += blockDim.x) {
-    const int ty = i / GF_TX, tx = i - ty * GF_TX;
-    const int y = y0 + ty, x = x0 + tx;
-    if (y >= H || x >= W) continue;
-    const float mg = sM[i], mgg = sM[GF_TY * GF_TX + i];
-    const float var = __fsub_rn(mgg, __fmul_rn(mg, mg));
-    const float den = __fadd_rn(var, p.eps);
-    const size_t o = img_off + (size_t)y * W + x;
+  double vs[NP];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) vs[q] = 0.0;
+  auto accumulate = [&](float g, const float (&sv)[T::NSRC], double sign) {
+    vs[0] += sign * (double)g;
+    vs[1] += sign * (double)__fmul_rn(g, g);
 #pragma unroll
     for (int c = 0; c < T::NSRC; ++c) {
-      const float ms = sM[(2 + 2 * c) * GF_TY * GF_TX + i], mgs = sM[(3 + 2 * c) * GF_TY * GF_TX + i];
-      const float cov = __fsub_rn(mgs, __fmul_rn(mg, ms));
-      const float a = __fdiv_rn(cov, den);
-      const float bb = __fsub_rn(ms, __fmul_rn(a, mg));
-      p.ab[(size_t)(2 * c) * p.plane_stride + o] = a;
-      p.ab[(size_t)(2 * c + 1) * p.plane_stride + o] = bb;
+      vs[2 + 2 * c] += sign * (double)sv[c];
+      vs[3 + 2 * c] += sign * (double)__fmul_rn(g, sv[c]);
+    }
+  };
+  for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
+    float g, sv[T::NSRC];
+    fetch(yy, g, sv);
+    accumulate(g, sv, 1.0);
+  }
+  for (int y = y_begin; y < y_end; ++y) {
+    {
+      float g, sv[T::NSRC];
+      fetch(y + r, g, sv);
+      accumulate(g, sv, 1.0);
+      if (y > y_begin) {
+        float g2, sv2[T::NSRC];
+        fetch(y - r - 1, g2, sv2);
+        accumulate(g2, sv2, -1.0);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) sV[q * GF_NT + t] = vs[q];
+    __syncthreads();
+    horizontal_means<NP>(sV, sM, hp, r, scale);
+    __syncthreads();
+    const int o = t - r, x = x0 + o;
+    if (o >= 0 && o < hp.tx && x < W) {
+      const float mg = sM[o], mgg = sM[GF_NT + o];
+      const float var = __fsub_rn(mgg, __fmul_rn(mg, mg));
+      const float den = __fadd_rn(var, p.eps);
+      const size_t op = img_off + (size_t)y * W + x;
+#pragma unroll
+      for (int c = 0; c < T::NSRC; ++c) {
+        const float ms = sM[(2 + 2 * c) * GF_NT + o], mgs = sM[(3 + 2 * c) * GF_NT + o];
+        const float cov = __fsub_rn(mgs, __fmul_rn(mg, ms));
+        const float a = __fdiv_rn(cov, den);
+        const float bb = __fsub_rn(ms, __fmul_rn(a, mg));
+        p.ab[(size_t)(2 * c) * p.plane_stride + op] = a;
+        p.ab[(size_t)(2 * c + 1) * p.plane_stride + op] = bb;
+      }
     }
   }
 }
 
 template <bool kTrimap>
-__global__ void __launch_bounds__(GF_THREADS)
+__global__ void __launch_bounds__(GF_NT)
 k_guided_out(const GuidedParams p) {
   using T = GfTraits<kTrimap>;
-  extern __shared__ __align__(16) unsigned char gf_smem[];
-  const int r = p.radius, tyh = GF_TY + 2 * r, txh = GF_TX + 2 * r, ld = txh | 1;
-  const int H = p.H, W = p.W, b = blockIdx.z;
-  const int y0 = blockIdx.y * GF_TY, x0 = blockIdx.x * GF_TX;
-  float* sIn = reinterpret_cast<float*>(gf_smem);                     // [NPLANE2][tyh][txh]
-  float* sM = sIn;
-  const size_t in_bytes = (size_t)T::NPLANE2 * tyh * txh * 4;
-  const size_t m_bytes = (size_t)T::NPLANE2 * GF_TY * GF_TX * 4;
-  const size_t a_bytes = ((in_bytes > m_bytes ? in_bytes : m_bytes) + 15) & ~size_t(15);
-  double* sV = reinterpret_cast<double*>(gf_smem + a_bytes);
-  const int plane = tyh * txh;
+  constexpr int NP = T::NPLANE2;
+  __shared__ double sV[NP * GF_NT];
+  __shared__ float sM[NP * GF_NT];
+  const int r = p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
+  const HorizontalPlan<NP> hp(r);
+  const int x0 = blockIdx.x * hp.tx;
+  const int y_begin = blockIdx.y * GF_SY, y_end = min(H, y_begin + GF_SY);
+  const int xs = reflect101(x0 - r + t, W);
   const size_t img_off = (size_t)b * H * W;
-
-  for (int i = threadIdx.x; i < plane; i += blockDim.x) {
-    const int ty = i / txh, tx = i - ty * txh;
-    const int y = reflect101(y0 + ty - r, H), x = reflect101(x0 + tx - r, W);
-    const size_t o = img_off + (size_t)y * W + x;
+  const double scale = 1.0 / ((double)(2 * r + 1) * (double)(2 * r + 1));
+  double vs[NP];
 #pragma unroll
-    for (int q = 0; q < T::NPLANE2; ++q) sIn[q * plane + i] = p.ab[(size_t)q * p.plane_stride + o];
-  }
-  __syncthreads();
-  auto value = [&](int pl, int row, int col) -> float { return sIn[pl * plane + row * txh + col]; };
-  box_means<T::NPLANE2>(value, sV, sM, r, txh, ld);
-
-  for (int i = threadIdx.x; i < GF_TY * GF_TX; i += blockDim.x) {
-    const int ty = i / GF_TX, tx = i - ty * GF_TX;
-    const int y = y0 + ty, x = x0 + tx;
-    if (y >= H || x >= W) continue;
-    const size_t o = img_off + (size_t)y * W + x;
-    const float g = kTrimap ? __fdiv_rn((float)p.gray[o], 255.0f) : p.guide[o];
-    float q[T::NSRC];
+  for (int q = 0; q < NP; ++q) vs[q] = 0.0;
+  auto add_row = [&](int yy, double sign) {
+    const size_t o = img_off + (size_t)reflect101(yy, H) * W + xs;
+    float v[NP];
 #pragma unroll
-    for (int c = 0; c < T::NSRC; ++c)
-      q[c] = __fadd_rn(__fmul_rn(sM[(2 * c) * GF_TY * GF_TX + i], g), sM[(2 * c + 1) * GF_TY * GF_TX + i]);
-    if (kTrimap) {
-      const float pbg = fminf(fmaxf(q[0], 0.0f), 1.0f);          // np.clip(., 0, 1)
-      const float pfg = fminf(fmaxf(q[T::NSRC - 1], 0.0f), 1.0f);
-      uint8_t t = (pfg > pbg) ? 3 : 2;                           // pipeline.py:143-145
-      if (pbg >= p.thr_bg) t = 0;
-      if (pfg >= p.thr_fg) t = 1;
-      p.trimap[o] = t;
-      if (p.q0) p.q0[o] = pbg;
-      if (p.q1) p.q1[o] = pfg;
-    } else {
-      p.q0[o] = q[0];
+    for (int q = 0; q < NP; ++q) v[q] = p.ab[(size_t)q * p.plane_stride + o];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) vs[q] += sign * (double)v[q];
+  };
+  for (int yy = y_begin - r; yy < y_begin + r; ++yy) add_row(yy, 1.0);
+  for (int y = y_begin; y < y_end; ++y) {
+    add_row(y + r, 1.0);
+    if (y > y_begin) add_row(y - r - 1, -1.0);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) sV[q * GF_NT + t] = vs[q];
+    __syncthreads();
+    horizontal_means<NP>(sV, sM, hp, r, scale);
+    __syncthreads();
+    const int o = t - r, x = x0 + o;
+    if (o >= 0 && o < hp.tx && x < W) {
+      const size_t op = img_off + (size_t)y * W + x;
+      const float g = kTrimap ? __fdiv_rn((float)p.gray[op], 255.0f) : p.guide[op];
+      float q[T::NSRC];
+#pragma unroll
+      for (int c = 0; c < T::NSRC; ++c)
+        q[c] = __fadd_rn(__fmul_rn(sM[(2 * c) * GF_NT + o], g), sM[(2 * c + 1) * GF_NT + o]);
+      if (kTrimap) {
+        const float pbg = fminf(fmaxf(q[0], 0.0f), 1.0f);          // np.clip(., 0, 1)
+        const float pfg = fminf(fmaxf(q[T::NSRC - 1], 0.0f), 1.0f);
+        uint8_t tv = (pfg > pbg) ? 3 : 2;                          // pipeline.py:143-145
+        if (pbg >= p.thr_bg) tv = 0;
+        if (pfg >= p.thr_fg) tv = 1;
+        p.trimap[op] = tv;
+        if (p.q0) p.q0[op] = pbg;
+        if (p.q1) p.q1[op] = pfg;
+      } else {
+        p.q0[op] = q[0];
+      }
     }
   }
 }
@@ -279,12 +293,9 @@ int refine_trimap(gg_context* ctx, Arena& ar, const uint8_t* bgr, const uint8_t*
   p.gray = gray; p.labels = labels; p.probs = probs; p.node_off = node_off;
   p.ab = ab; p.plane_stride = npx; p.trimap = trimap; p.q0 = p_bg; p.q1 = p_fg;
   p.H = H; p.W = W; p.radius = radius; p.eps = eps; p.thr_fg = thr_fg; p.thr_bg = thr_bg;
-  const size_t smem = guided_smem_bytes(radius, true);
-  GG_CUDA_OK(cudaFuncSetAttribute(k_guided_ab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  GG_CUDA_OK(cudaFuncSetAttribute(k_guided_out<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(W, GF_TX), ceil_div(H, GF_TY), B);
-  GG_LAUNCH(ctx, k_guided_ab<true>, grid, GF_THREADS, smem, st, p);
-  GG_LAUNCH(ctx, k_guided_out<true>, grid, GF_THREADS, smem, st, p);
+  dim3 grid(ceil_div(W, GF_NT - 2 * radius), ceil_div(H, GF_SY), B);
+  GG_LAUNCH(ctx, k_guided_ab<true>, grid, GF_NT, 0, st, p);
+  GG_LAUNCH(ctx, k_guided_out<true>, grid, GF_NT, 0, st, p);
   return GG_OK;
 }
 
@@ -298,12 +309,9 @@ int guided_filter_plane(gg_context* ctx, Arena& ar, const float* guide, const fl
   GuidedParams p{};
   p.guide = guide; p.src = src; p.ab = ab; p.plane_stride = npx; p.q0 = out;
   p.H = H; p.W = W; p.radius = radius; p.eps = eps;
-  const size_t smem = guided_smem_bytes(radius, false);
-  GG_CUDA_OK(cudaFuncSetAttribute(k_guided_ab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  GG_CUDA_OK(cudaFuncSetAttribute(k_guided_out<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(W, GF_TX), ceil_div(H, GF_TY), 1);
-  GG_LAUNCH(ctx, k_guided_ab<false>, grid, GF_THREADS, smem, st, p);
-  GG_LAUNCH(ctx, k_guided_out<false>, grid, GF_THREADS, smem, st, p);
+  dim3 grid(ceil_div(W, GF_NT - 2 * radius), ceil_div(H, GF_SY), 1);
+  GG_LAUNCH(ctx, k_guided_ab<false>, grid, GF_NT, 0, st, p);
+  GG_LAUNCH(ctx, k_guided_out<false>, grid, GF_NT, 0, st, p);
   return GG_OK;
 }
 
