@@ -51,6 +51,7 @@ static cudaEvent_t prof_event(gg_context* ctx) {
   return ctx->prof_pool[ctx->prof_pool_used++];
 }
 void prof_begin(gg_context* ctx, const char* name, cudaStream_t st) {
+  if (*name == '(') ++name;          // GG_LAUNCH((k<a, b>), ...) stringifies with the parenthesis
   gg_context::ProfRec r{name, prof_event(ctx), prof_event(ctx)};
   cudaEventRecord(r.e0, st);
   ctx->prof.push_back(r);
@@ -315,8 +316,9 @@ int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* la
 }
 
 // Host buffers in, host trimaps out.  The batch is cut into chunks; chunk i+1 is copied in
-// (stream s_in) and chunk i-1 copied out (s_out) while chunk i runs (s_run).  Two chunk
-// slots (inputs + workspace + trimaps) alternate.
+// (stream s_in) and chunk i-1 copied out (s_out) while chunk i runs (s_run).  Up to three
+// chunk slots (inputs + workspace + trimaps) rotate, so the copy-in stream never waits for
+// the compute of the chunk it is about to overwrite.
 int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H, int W,
                         const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
                         int32_t* n_edges_host) {
@@ -325,18 +327,18 @@ int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* lab
   GG_CUDA_OK(cudaSetDevice(h->device));
   if (!h->net.loaded) { set_error("gg_trimap_path_host: call gg_load_weights first"); return GG_ERR_STATE; }
   const size_t npx = (size_t)H * W;
-  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)((48u << 20) / (npx * 7) + 1)));
+  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)((32u << 20) / (npx * 7) + 1)));
   chunk = std::min(chunk, B);
   const int n_chunks = (B + chunk - 1) / chunk;
-  const int n_slots = n_chunks > 1 ? 2 : 1;
+  const int n_slots = std::min(n_chunks, 3);
   const size_t in_bytes = Arena::padded((size_t)chunk * npx * 3, 1) + Arena::padded((size_t)chunk * npx, 4) +
                           Arena::padded((size_t)chunk * npx, 1);
   const size_t slot_bytes = in_bytes + path_workspace_bytes(h, chunk, H, W, *cfg) + 4096;
   GG_TRY(h->host_arena.reserve(slot_bytes * n_slots));
   char* base = h->host_arena.base;
-  cudaEvent_t* ev_in = &h->ev[0];     // [2] input of slot s landed
-  cudaEvent_t* ev_run = &h->ev[2];    // [2] compute of slot s done
-  cudaEvent_t* ev_out = &h->ev[4];    // [2] output of slot s copied out
+  cudaEvent_t* ev_in = &h->ev[0];     // [3] input of slot s landed
+  cudaEvent_t* ev_run = &h->ev[3];    // [3] compute of slot s done
+  cudaEvent_t* ev_out = &h->ev[6];    // [3] output of slot s copied out
   GG_CUDA_OK(cudaMemsetAsync(h->d_status + 1, 0, sizeof(int), h->s_run));
   for (int ci = 0; ci < n_chunks; ++ci) {
     const int s = ci % n_slots;

@@ -100,6 +100,7 @@ struct gg_context {
   int* d_status = nullptr;
   double* d_lin = nullptr;   // sRGB linearisation table (256 doubles), built in gg_create
   int64_t launches = 0;
+  uint64_t attr_done = 0;   // one bit per kernel whose max-dynamic-smem attribute is already set
   int gemm_impl = 1;      // 0 = SIMT fp32 (validation), 1 = tcgen05 bf16x3
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev;
@@ -110,6 +111,16 @@ struct gg_context {
   std::vector<cudaEvent_t> prof_pool;
   size_t prof_pool_used = 0;
 };
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per context and kernel (bit id)
+#define GG_SMEM_ATTR_ONCE(ctx, bit, kernel, bytes)                                              \
+  do {                                                                                          \
+    if (!((ctx)->attr_done >> (bit) & 1ull)) {                                                  \
+      GG_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                      (int)(bytes)));                                           \
+      (ctx)->attr_done |= 1ull << (bit);                                                        \
+    }                                                                                           \
+  } while (0)
 
 namespace gg {
 void prof_begin(gg_context* ctx, const char* name, cudaStream_t st);

@@ -154,34 +154,44 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int row0 = tile * TC_BM;
-    // ---- A tile: fp32 rows -> three swizzled bf16 images
-    for (int r = warp; r < TC_BM; r += TC_THREADS / 32) {
-      const int row = row0 + r;
-      for (int q = lane; q < k4; q += 32) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < M) v = *reinterpret_cast<const float4*>(A + (size_t)row * K + 4 * q);
-        const float x[4] = {v.x, v.y, v.z, v.w};
-        uint32_t w[3][2];
+    // ---- A tile: fp32 rows -> three swizzled bf16 images.  Each warp owns 16 rows; all the
+    // global loads of the warp are issued before the first conversion (one latency, not 16).
+    {
+      constexpr int RPW = TC_BM / (TC_THREADS / 32);
+      float4 v[RPW];
 #pragma unroll
-        for (int e = 0; e < 4; e += 2) {
-          unsigned short hb[3][2];
+      for (int i = 0; i < RPW; ++i) {
+        const int row = row0 + warp + i * (TC_THREADS / 32);
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < M && lane < k4) v[i] = __ldg(reinterpret_cast<const float4*>(A + (size_t)row * K) + lane);
+      }
+      if (lane < k4) {
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            float rres = x[e + u];
+        for (int i = 0; i < RPW; ++i) {
+          const int r = warp + i * (TC_THREADS / 32);
+          const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+          uint32_t w[3][2];
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              const __nv_bfloat16 b = __float2bfloat16_rn(rres);
-              hb[s][u] = __bfloat16_as_ushort(b);
-              rres -= __bfloat162float(b);
+          for (int e = 0; e < 4; e += 2) {
+            unsigned short hb[3][2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              float rres = x[e + u];
+#pragma unroll
+              for (int sp = 0; sp < 3; ++sp) {
+                const __nv_bfloat16 bq = __float2bfloat16_rn(rres);
+                hb[sp][u] = __bfloat16_as_ushort(bq);
+                rres -= __bfloat162float(bq);
+              }
             }
+#pragma unroll
+            for (int sp = 0; sp < 3; ++sp) w[sp][e >> 1] = (uint32_t)hb[sp][0] | ((uint32_t)hb[sp][1] << 16);
           }
+          const uint32_t off = sw128_offset(r, 4 * lane, TC_BM);
 #pragma unroll
-          for (int s = 0; s < 3; ++s) w[s][e >> 1] = (uint32_t)hb[s][0] | ((uint32_t)hb[s][1] << 16);
+          for (int sp = 0; sp < 3; ++sp)
+            *reinterpret_cast<uint2*>(pA + sp * a_split + off) = make_uint2(w[sp][0], w[sp][1]);
         }
-        const uint32_t off = sw128_offset(r, 4 * q, TC_BM);
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-          *reinterpret_cast<uint2*>(pA + s * a_split + off) = make_uint2(w[s][0], w[s][1]);
       }
     }
     fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core
@@ -222,21 +232,26 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
         tmem_ld_wait();
         if (row < M) {
           float* crow = C + (size_t)row * N + col0;
+          float4 prev[8];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < 8; ++i) prev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (accumulate) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) prev[i] = *reinterpret_cast<const float4*>(crow + 4 * i);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
             float4 o;
             float* op = reinterpret_cast<float*>(&o);
-            float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (accumulate) prev = *reinterpret_cast<const float4*>(crow + i);
-            const float* pp = reinterpret_cast<const float*>(&prev);
+            const float* pp = reinterpret_cast<const float*>(&prev[i]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float v = __uint_as_float(rr[i + u]) + (bias ? bias[col0 + i + u] : 0.0f) + pp[u];
-              if (ACT == 1) v = gelu_erf_tc(v);
-              if (ACT == 2) v = 1.0f / (1.0f + expf(-v));
-              op[u] = v;
+              float vv = __uint_as_float(rr[4 * i + u]) + (bias ? __ldg(bias + col0 + 4 * i + u) : 0.0f) + pp[u];
+              if (ACT == 1) vv = gelu_erf_tc(vv);
+              if (ACT == 2) vv = 1.0f / (1.0f + expf(-vv));
+              op[u] = vv;
             }
-            *reinterpret_cast<float4*>(crow + i) = o;
+            *reinterpret_cast<float4*>(crow + 4 * i) = o;
           }
         }
       }
@@ -304,16 +319,17 @@ int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const f
   const NetWeights& nw = ctx->net;
   const uint8_t* img = reinterpret_cast<const uint8_t*>(nw.tc_blob) + nw.tc_off[which];
   const size_t smem = (size_t)3 * (K / 64) * TC_BM * 128 + tc_image_bytes(N, K) + 64 + 1024;
+  const size_t smem_max = (size_t)3 * 2 * TC_BM * 128 + tc_image_bytes(128, 128) + 64 + 1024;   // K = N = 128
   const int tiles_cap = ceil_div(m_cap, TC_BM);
   const int grid = tiles_cap < ctx->sm_count ? tiles_cap : ctx->sm_count;
   if (act == 0) {
-    GG_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GG_SMEM_ATTR_ONCE(ctx, 16, k_tc_gemm<0>, smem_max);
     GG_LAUNCH(ctx, k_tc_gemm<0>, grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, K, accumulate);
   } else if (act == 1) {
-    GG_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GG_SMEM_ATTR_ONCE(ctx, 17, k_tc_gemm<1>, smem_max);
     GG_LAUNCH(ctx, k_tc_gemm<1>, grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, K, accumulate);
   } else {
-    GG_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GG_SMEM_ATTR_ONCE(ctx, 18, k_tc_gemm<2>, smem_max);
     GG_LAUNCH(ctx, k_tc_gemm<2>, grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, K, accumulate);
   }
   return GG_OK;

@@ -78,13 +78,19 @@ __global__ void k_coord_tables(double* __restrict__ tab, int H, int W) {
 // them to a per-warp shared-memory table when the label changes (plain read-modify-write,
 // no atomics: 64-bit shared atomics are CAS loops on sm_100).  Table slots go to the global
 // per-region accumulators with one RED.F64 per field when evicted / at the end of the strip.
+//
+// Per-region fields (RS_NF doubles): 0-2 sum Lab, 3-5 sum Lab^2, 6-8 sum HSV, 9 sum y/H (f32
+// coords), 10 sum x/W (f32 coords), 11 sum |grad|, 12 sum |grad|/(max+1e-6), 13 sum y/H
+// (f64 coords), 14 sum x/W (f64 coords), 15 pixel count, 16 boundary pixels, 17 frame pixels
+// (the three counters are integers, exact in float64).
 constexpr int RS_ROWS = 64;
 constexpr int RS_WARPS = 8;
 constexpr int RS_SLOTS = 16;
-constexpr int RS_STAGE_LD = 17;  // doubles per lane in the staging area (padded)
+constexpr int RS_NF = 18;
+constexpr int RS_STAGE_LD = 19;  // doubles per lane in the staging area (odd: conflict-free)
 constexpr size_t RS_SMEM_BYTES =
-    (256 + RS_WARPS * RS_SLOTS * 16 + RS_WARPS * 32 * RS_STAGE_LD) * sizeof(double) +
-    RS_WARPS * RS_SLOTS * sizeof(int);
+    (256 + RS_WARPS * RS_SLOTS * RS_NF + RS_WARPS * 32 * RS_STAGE_LD) * sizeof(double) +
+    (256 + RS_WARPS * RS_SLOTS) * sizeof(int);
 
 struct RegionStatsParams {
   const uint8_t* bgr;
@@ -93,7 +99,7 @@ struct RegionStatsParams {
   const int* gradmax_sq;   // [B]
   const double* coord;     // k_coord_tables
   const double* lin_lut;   // [256]
-  double* acc;             // [B][node_cap][16]
+  double* acc;             // [B][node_cap][RS_NF]
   int* label_max;          // [B]
   unsigned long long* pair_keys;  // [B][table_cap]
   int* pair_cnts;                 // [B][table_cap]
@@ -110,8 +116,8 @@ GG_D uint32_t pair_hash(uint32_t lo, uint32_t hi) {
 }
 
 // Insert / increment an undirected pair in the per-image open-addressing table.
-GG_D void pair_emit(unsigned long long* keys, int* cnts, int cap, int a, int b, int count,
-                    int* status) {
+__device__ __noinline__ void pair_emit(unsigned long long* keys, int* cnts, int cap, int a, int b,
+                                       int count, int* status) {
   const uint32_t lo = (uint32_t)min(a, b), hi = (uint32_t)max(a, b);
   const unsigned long long key = ((unsigned long long)lo << 32) | hi;
   const unsigned long long EMPTY = ~0ull;
@@ -128,20 +134,35 @@ GG_D void pair_emit(unsigned long long* keys, int* cnts, int cap, int a, int b, 
   atomicOr(status, ST_PAIR_TABLE);
 }
 
+// float32 division that never takes the slow (subnormal / zero) path of __fdiv_rn: callers
+// pass num >= 0, den > 0, both normal; a zero numerator is substituted and selected away.
+GG_D float fdiv_pos(float num, float den) {
+  const float q = __fdiv_rn(num == 0.0f ? 1.0f : num, den);
+  return num == 0.0f ? 0.0f : q;
+}
+
+GG_D int reflect_row1(int y, int n) {       // BORDER_REFLECT_101 for y in [-1, n]
+  return y < 0 ? (n > 1 ? 1 : 0) : (y >= n ? (n > 1 ? n - 2 : 0) : y);
+}
+
 __global__ void __launch_bounds__(RS_WARPS * 32, 2)
 k_region_stats(const RegionStatsParams p) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   double* s_lin = reinterpret_cast<double*>(rs_smem);                       // [256]
-  double* s_vals_all = s_lin + 256;                                         // [W][SLOTS][16]
-  double* s_stage_all = s_vals_all + RS_WARPS * RS_SLOTS * 16;              // [W][32*LD]
-  int* s_tags_all = reinterpret_cast<int*>(s_stage_all + RS_WARPS * 32 * RS_STAGE_LD);
+  double* s_vals_all = s_lin + 256;                                         // [W][SLOTS][NF]
+  double* s_stage_all = s_vals_all + RS_WARPS * RS_SLOTS * RS_NF;           // [W][32*LD]
+  float* s_vlut = reinterpret_cast<float*>(s_stage_all + RS_WARPS * 32 * RS_STAGE_LD);  // [256]
+  int* s_tags_all = reinterpret_cast<int*>(s_vlut + 256);
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* vals = s_vals_all + wid * RS_SLOTS * 16;
+  double* vals = s_vals_all + wid * RS_SLOTS * RS_NF;
   double* stage = s_stage_all + wid * 32 * RS_STAGE_LD;
   int* tags = s_tags_all + wid * RS_SLOTS;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lin[i] = p.lin_lut[i];
-  for (int i = lane; i < RS_SLOTS * 16; i += 32) vals[i] = 0.0;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_lin[i] = p.lin_lut[i];
+    s_vlut[i] = __fdiv_rn((float)i, 255.0f);          // HSV value channel: max/255
+  }
+  for (int i = lane; i < RS_SLOTS * RS_NF; i += 32) vals[i] = 0.0;
   if (lane < RS_SLOTS) tags[lane] = -1;
   __syncthreads();
 
@@ -160,7 +181,7 @@ k_region_stats(const RegionStatsParams p) {
   const uint8_t* img = p.bgr + (size_t)b * H * W * 3;
   const uint8_t* gry = p.gray + (size_t)b * H * W;
   const int32_t* lab = p.labels + (size_t)b * H * W;
-  double* acc_g = p.acc + (size_t)b * p.node_cap * 16;
+  double* acc_g = p.acc + (size_t)b * p.node_cap * RS_NF;
   unsigned long long* keys = p.pair_keys + (size_t)b * p.table_cap;
   int* cnts = p.pair_cnts + (size_t)b * p.table_cap;
 
@@ -168,23 +189,24 @@ k_region_stats(const RegionStatsParams p) {
   const double xtf = p.coord[2 * H + xc], xtd = p.coord[2 * H + W + xc];
   const int gm = p.gradmax_sq[b];
   const float gden = __fadd_rn(__fsqrt_rn((float)gm), 1e-6f);  // grad.max() + 1e-6 (float32)
+  const int frame_x = (x == 0) + (x == W - 1);
+  const bool has_l = valid && x > 0, has_r = valid && x + 1 < W;
 
   // horizontal Sobel partials of a grey row: hs = g[x-1]+2g[x]+g[x+1], hd = g[x+1]-g[x-1]
   auto row_partials = [&](int yy, int& hs, int& hd) {
-    const uint8_t* r = gry + (size_t)reflect101(yy, H) * W;
+    const uint8_t* r = gry + (size_t)reflect_row1(yy, H) * W;
     const int gl = r[xl], gc = r[xc], gr = r[xr];
     hs = gl + 2 * gc + gr;
     hd = gr - gl;
-  };
-  auto load_label = [&](int yy, int xx) -> int {
-    return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? lab[(size_t)yy * W + xx] : -1;
   };
 
   int hs_m, hd_m, hs_c, hd_c, hs_p, hd_p;
   row_partials(y_begin - 1, hs_m, hd_m);
   row_partials(y_begin, hs_c, hd_c);
-  int lab_up = valid ? load_label(y_begin - 1, x) : -1;
-  int lab_c = valid ? load_label(y_begin, x) : -1;
+  const int32_t* lrow = lab + (size_t)y_begin * W + xc;      // label row pointer at (y, x)
+  const uint8_t* prow = img + ((size_t)y_begin * W + xc) * 3;
+  int lab_up = (valid && y_begin > 0) ? lrow[-W] : -1;
+  int lab_c = valid ? lrow[0] : -1;
 
   // per-lane run accumulators
   int cur = -1, cnt = 0, bnd = 0, brd = 0;
@@ -196,16 +218,10 @@ k_region_stats(const RegionStatsParams p) {
 
   auto evict_slot = [&](int slot) {  // warp-uniform
     const int tag = tags[slot];
-    if (tag >= 0 && lane < 16) {
-      double* g = acc_g + (size_t)tag * 16 + lane;
-      if (lane < 15) {
-        const double v = vals[slot * 16 + lane];
-        if (v != 0.0) atomicAdd(g, v);
-      } else {
-        const unsigned long long v = ((unsigned long long*)vals)[slot * 16 + 15];
-        if (v) atomicAdd((unsigned long long*)g, v);
-      }
-      vals[slot * 16 + lane] = 0.0;
+    if (tag >= 0 && lane < RS_NF) {
+      const double v = vals[slot * RS_NF + lane];
+      if (v != 0.0) atomicAdd(acc_g + (size_t)tag * RS_NF + lane, v);
+      vals[slot * RS_NF + lane] = 0.0;
     }
   };
 
@@ -215,57 +231,51 @@ k_region_stats(const RegionStatsParams p) {
       st[0] = aL; st[1] = aA; st[2] = aB; st[3] = aL2; st[4] = aA2; st[5] = aB2;
       st[6] = aH; st[7] = aS; st[8] = aV; st[9] = aYf; st[10] = (double)cnt * xtf;
       st[11] = aG; st[12] = aGs; st[13] = aYd; st[14] = (double)cnt * xtd;
-      ((unsigned long long*)st)[15] = (unsigned long long)cnt | ((unsigned long long)bnd << 24) |
-                                      ((unsigned long long)brd << 48);
+      st[15] = (double)cnt; st[16] = (double)bnd; st[17] = (double)brd;
       cnt = bnd = brd = 0;
       aL = aA = aB = aL2 = aA2 = aB2 = aH = aS = aV = aYf = aG = aGs = aYd = 0.0;
     }
+    const int myslot = (int)(((uint32_t)cur * 0x9E3779B1u) >> 28) & (RS_SLOTS - 1);
     __syncwarp();
     unsigned m = mask;
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
       const int L = __shfl_sync(0xffffffffu, cur, src);
-      const int slot = (int)(((uint32_t)L * 0x9E3779B1u) >> 28) & (RS_SLOTS - 1);
+      const int slot = __shfl_sync(0xffffffffu, myslot, src);
       if (tags[slot] != L) {
         evict_slot(slot);
         __syncwarp();
         if (lane == 0) tags[slot] = L;
         __syncwarp();
       }
-      if (lane < 15) {
-        vals[slot * 16 + lane] += stage[src * RS_STAGE_LD + lane];
-      } else if (lane == 15) {
-        ((unsigned long long*)vals)[slot * 16 + 15] +=
-            ((unsigned long long*)stage)[src * RS_STAGE_LD + 15];
-      }
-      __syncwarp();
+      // field f is always handled by lane f: no cross-lane hazard between iterations
+      if (lane < RS_NF) vals[slot * RS_NF + lane] += stage[src * RS_STAGE_LD + lane];
     }
+    __syncwarp();
   };
 
   // BGR of the first row
-  uint8_t pb = 0, pg = 0, pr = 0;
-  if (valid) {
-    const uint8_t* px = img + ((size_t)y_begin * W + x) * 3;
-    pb = px[0]; pg = px[1]; pr = px[2];
-  }
+  int pb = 0, pg = 0, pr = 0;
+  if (valid) { pb = prow[0]; pg = prow[1]; pr = prow[2]; }
 
   for (int y = y_begin; y < y_end; ++y) {
     // ---- look ahead: next grey row partials, next label row, next BGR
     row_partials(y + 1, hs_p, hd_p);
-    const int lab_dn = valid ? load_label(y + 1, x) : -1;
-    uint8_t nb_ = 0, ng_ = 0, nr_ = 0;
+    const bool has_dn = valid && (y + 1 < H);
+    const int lab_dn = has_dn ? lrow[W] : -1;
+    int nb_ = 0, ng_ = 0, nr_ = 0;
     if (valid && y + 1 < y_end) {
-      const uint8_t* px = img + ((size_t)(y + 1) * W + x) * 3;
+      const uint8_t* px = prow + (size_t)W * 3;
       nb_ = px[0]; ng_ = px[1]; nr_ = px[2];
     }
     // ---- horizontal neighbours of the label row
     int lab_r = __shfl_down_sync(0xffffffffu, lab_c, 1);
     int lab_l = __shfl_up_sync(0xffffffffu, lab_c, 1);
-    if (lane == 31) lab_r = valid ? load_label(y, x + 1) : -1;
-    if (lane == 0) lab_l = valid ? load_label(y, x - 1) : -1;
+    if (lane == 31) lab_r = has_r ? lrow[1] : -1;
+    if (lane == 0) lab_l = has_l ? lrow[-1] : -1;
 
-    bool in_range = valid && lab_c >= 0 && lab_c < p.node_cap;
+    const bool in_range = valid && lab_c >= 0 && lab_c < p.node_cap;
     if (valid && !in_range) atomicOr(p.status, ST_LABEL_RANGE);
 
     // ---- run bookkeeping: hand finished runs to the warp table
@@ -276,13 +286,23 @@ k_region_stats(const RegionStatsParams p) {
       cur = lab_c;
       lmax = max(lmax, lab_c);
       // ---- per-pixel quantities
-      float L, A, Bv, hh, ss, vv;
+      float L, A, Bv;
       bgr_to_lab(s_lin, p.lab.m, pb, pg, pr, L, A, Bv);
-      bgr_to_hsv(pb, pg, pr, hh, ss, vv);
+      // HSV (see pixel_math.cuh bgr_to_hsv; divisions guarded against the slow path)
+      const int mx = max(pr, max(pg, pb)), mn = min(pr, min(pg, pb));
+      const int d = mx - mn;
+      const float vv = s_vlut[mx];
+      int hp_;
+      if (pb == mx) hp_ = 4 * d + (pr - pg);
+      else if (pg == mx) hp_ = 2 * d + (pb - pr);
+      else { hp_ = pg - pb; if (hp_ < 0) hp_ += 6 * d; }
+      const float dsafe = d > 0 ? (float)d : 1.0f;
+      const float ss = d > 0 ? __fdiv_rn(dsafe, (float)max(mx, 1)) : 0.0f;
+      const float hh = d > 0 ? fdiv_pos((float)hp_, 6.0f * dsafe) : 0.0f;
       const int gx = hd_m + 2 * hd_c + hd_p;
       const int gy = hs_p - hs_m;
       const float g = __fsqrt_rn((float)(gx * gx + gy * gy));
-      const float gs = __fdiv_rn(g, gden);
+      const float gs = fdiv_pos(g, gden);
       aL += (double)L; aA += (double)A; aB += (double)Bv;
       aL2 += (double)__fmul_rn(L, L); aA2 += (double)__fmul_rn(A, A); aB2 += (double)__fmul_rn(Bv, Bv);
       aH += (double)hh; aS += (double)ss; aV += (double)vv;
@@ -293,7 +313,7 @@ k_region_stats(const RegionStatsParams p) {
       const bool diff = (lab_up >= 0 && lab_up != lab_c) || (lab_dn >= 0 && lab_dn != lab_c) ||
                         (lab_l >= 0 && lab_l != lab_c) || (lab_r >= 0 && lab_r != lab_c);
       bnd += (diff && lab_c != 0) ? 1 : 0;
-      brd += (y == 0) + (y == H - 1) + (x == 0) + (x == W - 1);   // corners count twice
+      brd += (y == 0) + (y == H - 1) + frame_x;   // corners count twice
     }
 
     // ---- adjacency transitions (graph_builder.py:267-281)
@@ -321,11 +341,11 @@ k_region_stats(const RegionStatsParams p) {
     if (p.connectivity == 8) {
       int dn_r = __shfl_down_sync(0xffffffffu, lab_dn, 1);
       int dn_l = __shfl_up_sync(0xffffffffu, lab_dn, 1);
-      if (lane == 31) dn_r = valid ? load_label(y + 1, x + 1) : -1;
-      if (lane == 0) dn_l = valid ? load_label(y + 1, x - 1) : -1;
+      if (lane == 31) dn_r = (has_r && has_dn) ? lrow[W + 1] : -1;
+      if (lane == 0) dn_l = (has_l && has_dn) ? lrow[W - 1] : -1;
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int o = s ? dn_l : dn_r;
+      for (int sdir = 0; sdir < 2; ++sdir) {
+        const int o = sdir ? dn_l : dn_r;
         const bool t = in_range && o >= 0 && o != lab_c && o < p.node_cap;
         const unsigned tm = __ballot_sync(0xffffffffu, t);
         if (t) {
@@ -342,6 +362,8 @@ k_region_stats(const RegionStatsParams p) {
     hs_m = hs_c; hd_m = hd_c; hs_c = hs_p; hd_c = hd_p;
     lab_up = lab_c; lab_c = lab_dn;
     pb = nb_; pg = ng_; pr = nr_;
+    lrow += W;
+    prow += (size_t)W * 3;
   }
 
   // ---- end of strip: flush runs, pairs, table, label max
@@ -362,11 +384,10 @@ __global__ void k_finalize_regions(const double* __restrict__ acc, const int* __
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = label_max[b] + 1;
   if (i >= n || i >= node_cap) return;
-  const double* a = acc + ((size_t)b * node_cap + i) * 16;
-  const unsigned long long pk = ((const unsigned long long*)a)[15];
-  const float counts = (float)(int)(pk & 0xFFFFFFull);
-  const float bnd = (float)(int)((pk >> 24) & 0xFFFFFFull);
-  const float brd = (float)(int)(pk >> 48);
+  const double* a = acc + ((size_t)b * node_cap + i) * RS_NF;
+  const float counts = (float)a[15];
+  const float bnd = (float)a[16];
+  const float brd = (float)a[17];
   const float safe = fmaxf(counts, 1.0f);
   float* s = st + (size_t)b * ST_FIELDS * node_cap + i;
   auto put = [&](int f, float v) { s[(size_t)f * node_cap] = v; };
@@ -1039,7 +1060,7 @@ size_t graph_workspace_bytes(int B, int H, int W, const gg_graph_config& cfg) {
   size_t s = 0;
   s += Arena::padded((size_t)B * H * W, 1);                 // gray
   s += Arena::padded(2 * (size_t)(H + W), 8);               // coord tables
-  s += Arena::padded((size_t)B * nc * 16, 8);               // acc
+  s += Arena::padded((size_t)B * nc * RS_NF, 8);            // acc
   s += Arena::padded((size_t)B * tc, 8);                    // pair keys
   s += Arena::padded((size_t)B * tc, 4);                    // pair counts
   s += Arena::padded((size_t)B * 4, 4) * 6;                 // per-image ints
@@ -1083,7 +1104,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
   uint8_t* gray = ar.take<uint8_t>((size_t)B * H * W);
   double* coord = ar.take<double>(2 * (size_t)(H + W));
   const double* lin = ctx->d_lin;
-  double* acc = ar.take<double>((size_t)B * nc * 16);
+  double* acc = ar.take<double>((size_t)B * nc * RS_NF);
   unsigned long long* pkeys = ar.take<unsigned long long>((size_t)B * tc);
   int* pcnts = ar.take<int>((size_t)B * tc);
   int* gradmax = ar.take<int>((size_t)B * 4);
@@ -1103,7 +1124,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
   float* tmp2 = ar.take<float>((size_t)B * nc * 2);
   if (gray_out) *gray_out = gray;
 
-  GG_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)B * nc * 16 * sizeof(double), st));
+  GG_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)B * nc * RS_NF * sizeof(double), st));
   GG_CUDA_OK(cudaMemsetAsync(pkeys, 0xFF, (size_t)B * tc * sizeof(unsigned long long), st));
   GG_CUDA_OK(cudaMemsetAsync(pcnts, 0, (size_t)B * tc * sizeof(int), st));
   GG_CUDA_OK(cudaMemsetAsync(gradmax, 0, (size_t)B * 4 * sizeof(int), st));
@@ -1124,8 +1145,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     p.n_sx = ceil_div(W, 32); p.n_sy = ceil_div(H, RS_ROWS);
     p.lab = make_lab_matrix();
     const long long tasks = (long long)B * p.n_sx * p.n_sy;
-    GG_CUDA_OK(cudaFuncSetAttribute(k_region_stats, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)RS_SMEM_BYTES));
+    GG_SMEM_ATTR_ONCE(ctx, 0, k_region_stats, RS_SMEM_BYTES);
     GG_LAUNCH(ctx, k_region_stats, ceil_div(tasks, RS_WARPS), RS_WARPS * 32, RS_SMEM_BYTES, st, p);
   }
   {

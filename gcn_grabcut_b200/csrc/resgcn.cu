@@ -612,7 +612,7 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
     const size_t smem = ((size_t)D * 19 + (size_t)nw.q * 3 + (size_t)D * nw.q) * sizeof(float);
     const int blocks = min(warp_blocks, ctx->sm_count * 8);
     GG_CPL_SWITCH(D, {
-      GG_CUDA_OK(cudaFuncSetAttribute(k_input_stage<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GG_SMEM_ATTR_ONCE(ctx, 1 + CPL, k_input_stage<CPL>, smem);
       GG_LAUNCH(ctx, k_input_stage<CPL>, blocks, 256, smem, st, x, wb, o, sizes, h, z);
     });
   }

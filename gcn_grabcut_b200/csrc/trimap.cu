@@ -53,7 +53,8 @@ struct GfTraits {
 // y-r-1; old rows are re-read through L1/L2).  Per row the sums go to a small shared row
 // buffer and (plane, segment) tasks slide the horizontal window over it; segment lengths are
 // odd so that the 64-bit reads of a warp hit distinct banks.  Means = float32(sum * 1/k^2),
-// exactly cv2.blur's float32 path.
+// exactly cv2.blur's float32 path.  RT > 0: radius known at compile time (loops unrolled);
+// RT == 0: runtime radius.
 template <int NP>
 struct HorizontalPlan {
   int seglen, nseg, tx;
@@ -65,7 +66,7 @@ struct HorizontalPlan {
   }
 };
 
-template <int NP>
+template <int NP, int RT>
 GG_D void horizontal_means(const double* sV, float* sM, const HorizontalPlan<NP>& hp, int radius,
                            double scale) {
   const int t = threadIdx.x;
@@ -75,19 +76,44 @@ GG_D void horizontal_means(const double* sV, float* sM, const HorizontalPlan<NP>
     const int len = min(hp.seglen, hp.tx - o0);
     const double* in = sV + pl * GF_NT + o0;
     float* out = sM + pl * GF_NT + o0;
-    const int k = 2 * radius + 1;
-    double s = 0.0;
-    for (int d = 0; d < k; ++d) s += in[d];
-    out[0] = (float)(s * scale);
-    for (int i = 1; i < len; ++i) {
-      s += in[i + k - 1];
-      s -= in[i - 1];
-      out[i] = (float)(s * scale);
+    if (RT > 0) {
+      constexpr int K = 2 * RT + 1;
+      constexpr int PER = GF_NT / NP;
+      constexpr int SEG = (((GF_NT - 2 * RT) + PER - 1) / PER) | 1;      // == hp.seglen
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < K; ++d) s += in[d];
+      out[0] = (float)(s * scale);
+#pragma unroll
+      for (int i = 1; i < SEG; ++i) {
+        if (i < len) {
+          s += in[i + K - 1];
+          s -= in[i - 1];
+          out[i] = (float)(s * scale);
+        }
+      }
+    } else {
+      const int k = 2 * radius + 1;
+      double s = 0.0;
+      for (int d = 0; d < k; ++d) s += in[d];
+      out[0] = (float)(s * scale);
+      for (int i = 1; i < len; ++i) {
+        s += in[i + k - 1];
+        s -= in[i - 1];
+        out[i] = (float)(s * scale);
+      }
     }
   }
 }
 
-template <bool kTrimap>
+// row index of BORDER_REFLECT_101 for |overshoot| < n (one fold), else the general loop
+GG_D int reflect_row(int y, int n) {
+  if (y < 0) y = -y;
+  if (y >= n) y = 2 * n - 2 - y;
+  return (y < 0 || y >= n) ? reflect101(y, n) : y;
+}
+
+template <bool kTrimap, int RT>
 __global__ void __launch_bounds__(GF_NT)
 k_guided_ab(const GuidedParams p) {
   using T = GfTraits<kTrimap>;
@@ -95,71 +121,89 @@ k_guided_ab(const GuidedParams p) {
   __shared__ double sV[NP * GF_NT];
   __shared__ float sM[NP * GF_NT];
   __shared__ float sLut[256];
-  const int r = p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
+  const int r = RT > 0 ? RT : p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
   const HorizontalPlan<NP> hp(r);
   const int x0 = blockIdx.x * hp.tx;
   const int y_begin = blockIdx.y * GF_SY, y_end = min(H, y_begin + GF_SY);
   const int xs = reflect101(x0 - r + t, W);
-  const size_t img_off = (size_t)b * H * W;
   const double scale = 1.0 / ((double)(2 * r + 1) * (double)(2 * r + 1));
-  int64_t no = 0;
+  const size_t img_off = (size_t)b * H * W;
+  // column base pointers (element (y, xs) lives at col[y * W])
+  const uint8_t* gcol = kTrimap ? p.gray + img_off + xs : nullptr;
+  const int32_t* lcol = kTrimap ? p.labels + img_off + xs : nullptr;
+  const float* ucol = kTrimap ? nullptr : p.guide + img_off + xs;
+  const float* scol = kTrimap ? nullptr : p.src + img_off + xs;
+  const float* prob0 = nullptr;
   int nn = 0;
   if (kTrimap) {
-    no = p.node_off[b];
+    const int64_t no = p.node_off[b];
     nn = (int)(p.node_off[b + 1] - no);
+    prob0 = p.probs + (size_t)no * 3;
     for (int i = t; i < 256; i += GF_NT) sLut[i] = __fdiv_rn((float)i, 255.0f);   // guide = gray/255
     __syncthreads();
   }
   // base planes of one pixel of this thread's column: g and the NSRC source planes
   auto fetch = [&](int yy, float& g, float (&sv)[T::NSRC]) {
-    const size_t o = img_off + (size_t)reflect101(yy, H) * W + xs;
+    const size_t ro = (size_t)reflect_row(yy, H) * W;
     if (kTrimap) {
-      g = sLut[p.gray[o]];
-      const int l = p.labels[o];
+      const int gr = gcol[ro];
+      const int l = lcol[ro];
+      g = sLut[gr];
       sv[0] = 0.0f;
       sv[T::NSRC - 1] = 0.0f;                       // project_to_pixels zero padding
       if (l >= 0 && l < nn) {
-        const float* row = p.probs + (size_t)(no + l) * 3;
+        const float* row = prob0 + (size_t)l * 3;
         sv[0] = row[0];
         sv[T::NSRC - 1] = row[2];
       }
     } else {
-      g = p.guide[o];
-      sv[0] = p.src[o];
+      g = ucol[ro];
+      sv[0] = scol[ro];
     }
   };
   double vs[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) vs[q] = 0.0;
-  auto accumulate = [&](float g, const float (&sv)[T::NSRC], double sign) {
-    vs[0] += sign * (double)g;
-    vs[1] += sign * (double)__fmul_rn(g, g);
+  auto add = [&](float g, const float (&sv)[T::NSRC]) {
+    vs[0] += (double)g;
+    vs[1] += (double)__fmul_rn(g, g);
 #pragma unroll
     for (int c = 0; c < T::NSRC; ++c) {
-      vs[2 + 2 * c] += sign * (double)sv[c];
-      vs[3 + 2 * c] += sign * (double)__fmul_rn(g, sv[c]);
+      vs[2 + 2 * c] += (double)sv[c];
+      vs[3 + 2 * c] += (double)__fmul_rn(g, sv[c]);
+    }
+  };
+  auto sub = [&](float g, const float (&sv)[T::NSRC]) {
+    vs[0] -= (double)g;
+    vs[1] -= (double)__fmul_rn(g, g);
+#pragma unroll
+    for (int c = 0; c < T::NSRC; ++c) {
+      vs[2 + 2 * c] -= (double)sv[c];
+      vs[3 + 2 * c] -= (double)__fmul_rn(g, sv[c]);
     }
   };
   for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
     float g, sv[T::NSRC];
     fetch(yy, g, sv);
-    accumulate(g, sv, 1.0);
+    add(g, sv);
   }
+  // software pipeline: the rows entering / leaving the window of row y+1 are fetched while
+  // row y is being reduced
+  float gn, svn[T::NSRC], go = 0.f, svo[T::NSRC];
+#pragma unroll
+  for (int c = 0; c < T::NSRC; ++c) svo[c] = 0.f;
+  fetch(y_begin + r, gn, svn);
   for (int y = y_begin; y < y_end; ++y) {
-    {
-      float g, sv[T::NSRC];
-      fetch(y + r, g, sv);
-      accumulate(g, sv, 1.0);
-      if (y > y_begin) {
-        float g2, sv2[T::NSRC];
-        fetch(y - r - 1, g2, sv2);
-        accumulate(g2, sv2, -1.0);
-      }
+    add(gn, svn);
+    if (y > y_begin) sub(go, svo);
+    if (y + 1 < y_end) {
+      fetch(y + 1 + r, gn, svn);
+      fetch(y - r, go, svo);
     }
 #pragma unroll
     for (int q = 0; q < NP; ++q) sV[q * GF_NT + t] = vs[q];
     __syncthreads();
-    horizontal_means<NP>(sV, sM, hp, r, scale);
+    horizontal_means<NP, RT>(sV, sM, hp, r, scale);
     __syncthreads();
     const int o = t - r, x = x0 + o;
     if (o >= 0 && o < hp.tx && x < W) {
@@ -180,39 +224,54 @@ k_guided_ab(const GuidedParams p) {
   }
 }
 
-template <bool kTrimap>
+template <bool kTrimap, int RT>
 __global__ void __launch_bounds__(GF_NT)
 k_guided_out(const GuidedParams p) {
   using T = GfTraits<kTrimap>;
   constexpr int NP = T::NPLANE2;
   __shared__ double sV[NP * GF_NT];
   __shared__ float sM[NP * GF_NT];
-  const int r = p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
+  const int r = RT > 0 ? RT : p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
   const HorizontalPlan<NP> hp(r);
   const int x0 = blockIdx.x * hp.tx;
   const int y_begin = blockIdx.y * GF_SY, y_end = min(H, y_begin + GF_SY);
   const int xs = reflect101(x0 - r + t, W);
   const size_t img_off = (size_t)b * H * W;
   const double scale = 1.0 / ((double)(2 * r + 1) * (double)(2 * r + 1));
+  const float* col = p.ab + img_off + xs;
   double vs[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) vs[q] = 0.0;
-  auto add_row = [&](int yy, double sign) {
-    const size_t o = img_off + (size_t)reflect101(yy, H) * W + xs;
-    float v[NP];
+  auto load_row = [&](int yy, float (&v)[NP]) {
+    const size_t ro = (size_t)reflect_row(yy, H) * W;
 #pragma unroll
-    for (int q = 0; q < NP; ++q) v[q] = p.ab[(size_t)q * p.plane_stride + o];
-#pragma unroll
-    for (int q = 0; q < NP; ++q) vs[q] += sign * (double)v[q];
+    for (int q = 0; q < NP; ++q) v[q] = col[(size_t)q * p.plane_stride + ro];
   };
-  for (int yy = y_begin - r; yy < y_begin + r; ++yy) add_row(yy, 1.0);
+  for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
+    float v[NP];
+    load_row(yy, v);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) vs[q] += (double)v[q];
+  }
+  float vn[NP], vo[NP];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) vo[q] = 0.f;
+  load_row(y_begin + r, vn);
   for (int y = y_begin; y < y_end; ++y) {
-    add_row(y + r, 1.0);
-    if (y > y_begin) add_row(y - r - 1, -1.0);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) vs[q] += (double)vn[q];
+    if (y > y_begin) {
+#pragma unroll
+      for (int q = 0; q < NP; ++q) vs[q] -= (double)vo[q];
+    }
+    if (y + 1 < y_end) {
+      load_row(y + 1 + r, vn);
+      load_row(y - r, vo);
+    }
 #pragma unroll
     for (int q = 0; q < NP; ++q) sV[q * GF_NT + t] = vs[q];
     __syncthreads();
-    horizontal_means<NP>(sV, sM, hp, r, scale);
+    horizontal_means<NP, RT>(sV, sM, hp, r, scale);
     __syncthreads();
     const int o = t - r, x = x0 + o;
     if (o >= 0 && o < hp.tx && x < W) {
@@ -236,6 +295,21 @@ k_guided_out(const GuidedParams p) {
       }
     }
   }
+}
+
+template <bool kTrimap>
+static int launch_guided(gg_context* ctx, const GuidedParams& p, dim3 grid, cudaStream_t st) {
+  if (p.radius == 8) {
+    GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 8>), grid, GF_NT, 0, st, p);
+    GG_LAUNCH(ctx, (k_guided_out<kTrimap, 8>), grid, GF_NT, 0, st, p);
+  } else if (p.radius == 4) {
+    GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 4>), grid, GF_NT, 0, st, p);
+    GG_LAUNCH(ctx, (k_guided_out<kTrimap, 4>), grid, GF_NT, 0, st, p);
+  } else {
+    GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 0>), grid, GF_NT, 0, st, p);
+    GG_LAUNCH(ctx, (k_guided_out<kTrimap, 0>), grid, GF_NT, 0, st, p);
+  }
+  return GG_OK;
 }
 
 // predict_trimap / _probs_to_trimap (model.py:623-678): node rule gathered through the map.
@@ -294,8 +368,7 @@ int refine_trimap(gg_context* ctx, Arena& ar, const uint8_t* bgr, const uint8_t*
   p.ab = ab; p.plane_stride = npx; p.trimap = trimap; p.q0 = p_bg; p.q1 = p_fg;
   p.H = H; p.W = W; p.radius = radius; p.eps = eps; p.thr_fg = thr_fg; p.thr_bg = thr_bg;
   dim3 grid(ceil_div(W, GF_NT - 2 * radius), ceil_div(H, GF_SY), B);
-  GG_LAUNCH(ctx, k_guided_ab<true>, grid, GF_NT, 0, st, p);
-  GG_LAUNCH(ctx, k_guided_out<true>, grid, GF_NT, 0, st, p);
+  GG_TRY(launch_guided<true>(ctx, p, grid, st));
   return GG_OK;
 }
 
@@ -310,8 +383,7 @@ int guided_filter_plane(gg_context* ctx, Arena& ar, const float* guide, const fl
   p.guide = guide; p.src = src; p.ab = ab; p.plane_stride = npx; p.q0 = out;
   p.H = H; p.W = W; p.radius = radius; p.eps = eps;
   dim3 grid(ceil_div(W, GF_NT - 2 * radius), ceil_div(H, GF_SY), 1);
-  GG_LAUNCH(ctx, k_guided_ab<false>, grid, GF_NT, 0, st, p);
-  GG_LAUNCH(ctx, k_guided_out<false>, grid, GF_NT, 0, st, p);
+  GG_TRY(launch_guided<false>(ctx, p, grid, st));
   return GG_OK;
 }
 
