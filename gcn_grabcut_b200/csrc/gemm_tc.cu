@@ -2,8 +2,8 @@
 //
 //   C[M,N] (+)= act(A[M,K] W[N,K]^T + bias)        M ~ 10^4..10^5 rows, N,K in {64,128}
 //
-// fp32 semantics on bf16 tensor cores: every fp32 operand is split into three bf16 terms
-// (x = x1 + x2 + x3, residuals exact in fp32) and the six products with i+j <= 4
+// fp32 semantics on bf16 tensor cores: every fp32 operand is split EXACTLY into three bf16
+// terms by truncation (x = x1 + x2 + x3, 8 mantissa bits each) and the six products with i+j <= 4
 // (x1w1, x1w2, x2w1, x2w2, x1w3, x3w1) are accumulated in fp32 in TMEM -- the dropped terms
 // are O(2^-24) relative, i.e. fp32-class accuracy, at 6 MMA passes.
 //
@@ -110,10 +110,15 @@ GG_HD uint32_t sw128_offset(int r, int k, int rows) {
   return (uint32_t)(a * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4) + j * 2);
 }
 
-template <int ACT>
+// PRO: how the A operand is produced.  0: rows of A as they are.  1: LayerNorm over the row
+// (eps 1e-5, affine ln_g/ln_b), optionally after scaling the row by gvec[node_graph[row]]
+// (K must be 128).  2: first edge-encoder layer, A[row][k] = GELU(w0[k,:5] . attr[row,:5] + b0[k])
+// computed on the fly from the 5-d edge attributes (model.py:124-126).
+template <int ACT, int PRO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const float* __restrict__ bias,
-          float* __restrict__ C, const int* __restrict__ m_ptr, int N, int K, int accumulate) {
+          float* __restrict__ C, const int* __restrict__ m_ptr, int N, int K, int accumulate,
+          const TcPrologue pro) {
   extern __shared__ unsigned char tc_smem_raw[];
   const int M = *m_ptr;
   const int n_tiles = (M + TC_BM - 1) / TC_BM;
@@ -157,40 +162,102 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
     // ---- A tile: fp32 rows -> three swizzled bf16 images.  Each warp owns 16 rows; all the
     // global loads of the warp are issued before the first conversion (one latency, not 16).
     {
-      constexpr int RPW = TC_BM / (TC_THREADS / 32);
+      // Work items are (row, float4 chunk): a warp covers 32/k4 rows per pass (1 for K = 128,
+      // 2 for K = 64), so that all lanes are busy for both widths.
+      constexpr int RPW = TC_BM / (TC_THREADS / 32);          // rows per warp
+      const int rpp = 32 / k4;                                 // rows per pass
+      const int sub = lane / k4, ch = lane - sub * k4;        // row within the pass, chunk within the row
+      const int n_pass = RPW / rpp;
       float4 v[RPW];
+      if (PRO == 2) {
+        // edge attributes (5 floats per row) -> 4 hidden units per lane
+        float w0[4][5], b0[4];
 #pragma unroll
-      for (int i = 0; i < RPW; ++i) {
-        const int row = row0 + warp + i * (TC_THREADS / 32);
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < M && lane < k4) v[i] = __ldg(reinterpret_cast<const float4*>(A + (size_t)row * K) + lane);
-      }
-      if (lane < k4) {
+        for (int u = 0; u < 4; ++u) {
+          const int kk = 4 * ch + u;
+          b0[u] = __ldg(pro.b0 + kk);
+#pragma unroll
+          for (int j = 0; j < 5; ++j) w0[u][j] = __ldg(pro.w0 + kk * 5 + j);
+        }
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
-          const int r = warp + i * (TC_THREADS / 32);
-          const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-          uint32_t w[3][2];
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < n_pass) {
+            const int row = row0 + warp * RPW + i * rpp + sub;
+            if (row < M) {
+              float a5[5];
 #pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            unsigned short hb[3][2];
+              for (int j = 0; j < 5; ++j) a5[j] = __ldg(A + (size_t)row * 5 + j);
+              float o[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              float rres = x[e + u];
+              for (int u = 0; u < 4; ++u) {
+                float sacc = b0[u];
 #pragma unroll
-              for (int sp = 0; sp < 3; ++sp) {
-                const __nv_bfloat16 bq = __float2bfloat16_rn(rres);
-                hb[sp][u] = __bfloat16_as_ushort(bq);
-                rres -= __bfloat162float(bq);
+                for (int j = 0; j < 5; ++j) sacc = fmaf(w0[u][j], a5[j], sacc);
+                o[u] = gelu_erf_tc(sacc);
               }
+              v[i] = make_float4(o[0], o[1], o[2], o[3]);
             }
-#pragma unroll
-            for (int sp = 0; sp < 3; ++sp) w[sp][e >> 1] = (uint32_t)hb[sp][0] | ((uint32_t)hb[sp][1] << 16);
           }
-          const uint32_t off = sw128_offset(r, 4 * lane, TC_BM);
+        }
+      } else {
 #pragma unroll
-          for (int sp = 0; sp < 3; ++sp)
-            *reinterpret_cast<uint2*>(pA + sp * a_split + off) = make_uint2(w[sp][0], w[sp][1]);
+        for (int i = 0; i < RPW; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < n_pass) {
+            const int row = row0 + warp * RPW + i * rpp + sub;
+            if (row < M) v[i] = __ldg(reinterpret_cast<const float4*>(A + (size_t)row * K) + ch);
+          }
+        }
+        if (PRO == 1) {
+          // fused LayerNorm (K == 128: one float4 per lane covers the row, rpp == 1)
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(pro.ln_g) + lane);
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(pro.ln_b) + lane);
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) {
+            const int row = row0 + warp * RPW + i;
+            float4 x4 = v[i];
+            if (pro.gvec != nullptr && row < M) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(pro.gvec + (size_t)pro.node_graph[row] * K) + lane);
+              x4.x *= s4.x; x4.y *= s4.y; x4.z *= s4.z; x4.w *= s4.w;
+            }
+            float sum = (x4.x + x4.y) + (x4.z + x4.w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum / (float)K;
+            const float dx = x4.x - mean, dy = x4.y - mean, dz = x4.z - mean, dw = x4.w - mean;
+            float sq = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const float rstd = 1.0f / sqrtf(sq / (float)K + 1e-5f);
+            v[i] = make_float4(dx * rstd * g4.x + b4.x, dy * rstd * g4.y + b4.y,
+                               dz * rstd * g4.z + b4.z, dw * rstd * g4.w + b4.w);
+          }
+        }
+      }
+      // exact 3-way split by truncation: x = x1 + x2 + x3 with x1 = top 8 mantissa bits of x,
+      // x2 = top 8 bits of the (exact) remainder, x3 = what is left (<= 8 bits): ALU-only.
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        if (i < n_pass) {
+          const int r = warp * RPW + i * rpp + sub;
+          const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+          uint32_t hb[3][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t b1 = __float_as_uint(x[e]) & 0xFFFF0000u;
+            const float r1 = x[e] - __uint_as_float(b1);
+            const uint32_t b2 = __float_as_uint(r1) & 0xFFFF0000u;
+            const float r2 = r1 - __uint_as_float(b2);
+            hb[0][e] = b1; hb[1][e] = b2; hb[2][e] = __float_as_uint(r2);
+          }
+          const uint32_t off = sw128_offset(r, 4 * ch, TC_BM);
+#pragma unroll
+          for (int sp = 0; sp < 3; ++sp) {
+            const uint32_t lo = __byte_perm(hb[sp][0], hb[sp][1], 0x7632);   // {hi16(e0), hi16(e1)}
+            const uint32_t hi = __byte_perm(hb[sp][2], hb[sp][3], 0x7632);
+            *reinterpret_cast<uint2*>(pA + sp * a_split + off) = make_uint2(lo, hi);
+          }
         }
       }
     }
@@ -272,10 +339,14 @@ static void pack_weight(const float* W, int N, int K, uint8_t* img) {
       float r = W[(size_t)n * K + k];
       const uint32_t off = sw128_offset(n, k, N);
       for (int s = 0; s < 3; ++s) {
-        const __nv_bfloat16 b = __float2bfloat16_rn(r);
-        const unsigned short bits = __bfloat16_as_ushort(b);
+        uint32_t u;
+        memcpy(&u, &r, 4);
+        u &= 0xFFFF0000u;                       // truncation split: exact, 3 x 8 mantissa bits
+        const unsigned short bits = (unsigned short)(u >> 16);
         memcpy(img + s * split + off, &bits, 2);
-        r -= __bfloat162float(b);
+        float part;
+        memcpy(&part, &u, 4);
+        r -= part;
       }
     }
 }
@@ -315,24 +386,30 @@ bool gemm_tc_supported(const gg_context* ctx, int which, int N, int K) {
 }
 
 int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* bias, float* C,
-            const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate) {
+            const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate,
+            const TcPrologue* prologue) {
   const NetWeights& nw = ctx->net;
   const uint8_t* img = reinterpret_cast<const uint8_t*>(nw.tc_blob) + nw.tc_off[which];
   const size_t smem = (size_t)3 * (K / 64) * TC_BM * 128 + tc_image_bytes(N, K) + 64 + 1024;
   const size_t smem_max = (size_t)3 * 2 * TC_BM * 128 + tc_image_bytes(128, 128) + 64 + 1024;   // K = N = 128
   const int tiles_cap = ceil_div(m_cap, TC_BM);
   const int grid = tiles_cap < ctx->sm_count ? tiles_cap : ctx->sm_count;
-  if (act == 0) {
-    GG_SMEM_ATTR_ONCE(ctx, 16, k_tc_gemm<0>, smem_max);
-    GG_LAUNCH(ctx, k_tc_gemm<0>, grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, K, accumulate);
-  } else if (act == 1) {
-    GG_SMEM_ATTR_ONCE(ctx, 17, k_tc_gemm<1>, smem_max);
-    GG_LAUNCH(ctx, k_tc_gemm<1>, grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, K, accumulate);
-  } else {
-    GG_SMEM_ATTR_ONCE(ctx, 18, k_tc_gemm<2>, smem_max);
-    GG_LAUNCH(ctx, k_tc_gemm<2>, grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, K, accumulate);
+  TcPrologue pro{};
+  if (prologue) pro = *prologue;
+  GG_REQUIRE(pro.mode == 0 || (pro.mode == 1 && K == 128) || (pro.mode == 2 && K == 64),
+             "gemm_tc: unsupported prologue for K=%d", K);
+#define GG_TC_CASE(ACT_, PRO_, BIT_)                                                               \
+  if (act == ACT_ && pro.mode == PRO_) {                                                          \
+    GG_SMEM_ATTR_ONCE(ctx, BIT_, (k_tc_gemm<ACT_, PRO_>), smem_max);                              \
+    GG_LAUNCH(ctx, (k_tc_gemm<ACT_, PRO_>), grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, \
+              K, accumulate, pro);                                                                \
+    return GG_OK;                                                                                 \
   }
-  return GG_OK;
+  GG_TC_CASE(0, 0, 16) GG_TC_CASE(1, 0, 17) GG_TC_CASE(2, 0, 18)
+  GG_TC_CASE(0, 1, 19) GG_TC_CASE(1, 1, 20) GG_TC_CASE(0, 2, 21)
+#undef GG_TC_CASE
+  set_error("gemm_tc: unsupported act/prologue combination %d/%d", act, pro.mode);
+  return GG_ERR_INVALID;
 }
 
 }  // namespace gg

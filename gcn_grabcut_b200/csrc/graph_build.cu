@@ -12,6 +12,8 @@
 //
 // Float32 epilogues use explicit round-to-nearest intrinsics (never contracted to FMA) so
 // that, given identical region sums, every feature is bit-identical to numpy's.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "pixel_math.cuh"
 #include "graph_build.cuh"
@@ -89,8 +91,8 @@ constexpr int RS_SLOTS = 16;
 constexpr int RS_NF = 18;
 constexpr int RS_STAGE_LD = 19;  // doubles per lane in the staging area (odd: conflict-free)
 constexpr size_t RS_SMEM_BYTES =
-    (256 + RS_WARPS * RS_SLOTS * RS_NF + RS_WARPS * 32 * RS_STAGE_LD) * sizeof(double) +
-    (256 + RS_WARPS * RS_SLOTS) * sizeof(int);
+    (256 + RS_WARPS * RS_SLOTS * RS_NF + RS_WARPS * 32 * RS_STAGE_LD + RS_WARPS * 32) * sizeof(double) +
+    (256 + RS_WARPS * RS_SLOTS + RS_WARPS * 32) * sizeof(int);
 
 struct RegionStatsParams {
   const uint8_t* bgr;
@@ -145,19 +147,27 @@ GG_D int reflect_row1(int y, int n) {       // BORDER_REFLECT_101 for y in [-1, 
   return y < 0 ? (n > 1 ? 1 : 0) : (y >= n ? (n > 1 ? n - 2 : 0) : y);
 }
 
-__global__ void __launch_bounds__(RS_WARPS * 32, 2)
+template <int MINB>
+__global__ void __launch_bounds__(RS_WARPS * 32, MINB)
 k_region_stats(const RegionStatsParams p) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   double* s_lin = reinterpret_cast<double*>(rs_smem);                       // [256]
   double* s_vals_all = s_lin + 256;                                         // [W][SLOTS][NF]
   double* s_stage_all = s_vals_all + RS_WARPS * RS_SLOTS * RS_NF;           // [W][32*LD]
-  float* s_vlut = reinterpret_cast<float*>(s_stage_all + RS_WARPS * 32 * RS_STAGE_LD);  // [256]
-  int* s_tags_all = reinterpret_cast<int*>(s_vlut + 256);
+  unsigned long long* s_pkey_all =
+      reinterpret_cast<unsigned long long*>(s_stage_all + RS_WARPS * 32 * RS_STAGE_LD);  // [W][32]
+  float* s_vlut = reinterpret_cast<float*>(s_pkey_all + RS_WARPS * 32);                  // [256]
+  int* s_tags_all = reinterpret_cast<int*>(s_vlut + 256);                                // [W][SLOTS]
+  int* s_pcnt_all = s_tags_all + RS_WARPS * RS_SLOTS;                                    // [W][32]
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* vals = s_vals_all + wid * RS_SLOTS * RS_NF;
   double* stage = s_stage_all + wid * 32 * RS_STAGE_LD;
   int* tags = s_tags_all + wid * RS_SLOTS;
+  unsigned long long* pkey = s_pkey_all + wid * 32;   // per-warp cache of label pairs (lane = slot)
+  int* pcnt = s_pcnt_all + wid * 32;
+  pkey[lane] = ~0ull;
+  pcnt[lane] = 0;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     s_lin[i] = p.lin_lut[i];
     s_vlut[i] = __fdiv_rn((float)i, 255.0f);          // HSV value channel: max/255
@@ -255,6 +265,38 @@ k_region_stats(const RegionStatsParams p) {
     __syncwarp();
   };
 
+  // Label pairs go through a per-warp shared-memory cache (lane = slot, looked up with one
+  // ballot) so that the global hash table sees one atomic per distinct pair and strip
+  // instead of one per boundary segment.  want: this lane has (a, b, n) to record.
+  int victim = 0;
+  auto pair_add = [&](bool want, int a, int bq, int n) {
+    unsigned em = __ballot_sync(0xffffffffu, want);
+    const unsigned long long mykey =
+        ((unsigned long long)(uint32_t)min(a, bq) << 32) | (uint32_t)max(a, bq);
+    while (em) {
+      const int src = __ffs(em) - 1;
+      em &= em - 1;
+      const unsigned long long key = __shfl_sync(0xffffffffu, mykey, src);
+      const int n_add = __shfl_sync(0xffffffffu, n, src);
+      const unsigned long long mine = pkey[lane];
+      const unsigned hit = __ballot_sync(0xffffffffu, mine == key);
+      if (hit) {
+        if (lane == __ffs(hit) - 1) pcnt[lane] += n_add;
+      } else {
+        const unsigned empty = __ballot_sync(0xffffffffu, mine == ~0ull);
+        const int slot = empty ? __ffs(empty) - 1 : victim;
+        if (!empty) victim = (victim + 1) & 31;
+        if (lane == slot) {
+          if (mine != ~0ull)
+            pair_emit(keys, cnts, p.table_cap, (int)(mine >> 32), (int)(mine & 0xFFFFFFFFull), pcnt[lane], p.status);
+          pkey[lane] = key;
+          pcnt[lane] = n_add;
+        }
+      }
+      __syncwarp();
+    }
+  };
+
   // BGR of the first row
   int pb = 0, pg = 0, pr = 0;
   if (valid) { pb = prow[0]; pg = prow[1]; pr = prow[2]; }
@@ -318,24 +360,29 @@ k_region_stats(const RegionStatsParams p) {
 
     // ---- adjacency transitions (graph_builder.py:267-281)
     // right neighbour: aggregated down the column in registers
-    if (in_range && lab_r >= 0 && lab_r != lab_c && lab_r < p.node_cap) {
-      if (lab_c == rp_a && lab_r == rp_b) {
-        rp_cnt += 1;
-      } else {
-        if (rp_cnt > 0) pair_emit(keys, cnts, p.table_cap, rp_a, rp_b, rp_cnt, p.status);
-        rp_a = lab_c; rp_b = lab_r; rp_cnt = 1;
-      }
+    {
+      const bool tr = in_range && lab_r >= 0 && lab_r != lab_c && lab_r < p.node_cap;
+      const bool same = tr && lab_c == rp_a && lab_r == rp_b;
+      const bool emit = tr && !same && rp_cnt > 0;
+      if (__any_sync(0xffffffffu, emit)) pair_add(emit, rp_a, rp_b, rp_cnt);
+      if (same) rp_cnt += 1;
+      else if (tr) { rp_a = lab_c; rp_b = lab_r; rp_cnt = 1; }
     }
     // down neighbour (and the two diagonals for connectivity 8): aggregated across lanes
     {
       const bool t = in_range && lab_dn >= 0 && lab_dn != lab_c && lab_dn < p.node_cap;
       const unsigned tm = __ballot_sync(0xffffffffu, t);
-      if (t) {
-        const unsigned long long key =
-            ((unsigned long long)(uint32_t)min(lab_c, lab_dn) << 32) | (uint32_t)max(lab_c, lab_dn);
-        const unsigned grp = __match_any_sync(tm, key);
-        if ((__ffs(grp) - 1) == lane)
-          pair_emit(keys, cnts, p.table_cap, lab_c, lab_dn, __popc(grp), p.status);
+      if (tm) {
+        bool lead = false;
+        int n = 0;
+        if (t) {
+          const unsigned long long key =
+              ((unsigned long long)(uint32_t)min(lab_c, lab_dn) << 32) | (uint32_t)max(lab_c, lab_dn);
+          const unsigned grp = __match_any_sync(tm, key);
+          lead = (__ffs(grp) - 1) == lane;
+          n = __popc(grp);
+        }
+        pair_add(lead, lab_c, lab_dn, n);
       }
     }
     if (p.connectivity == 8) {
@@ -348,12 +395,17 @@ k_region_stats(const RegionStatsParams p) {
         const int o = sdir ? dn_l : dn_r;
         const bool t = in_range && o >= 0 && o != lab_c && o < p.node_cap;
         const unsigned tm = __ballot_sync(0xffffffffu, t);
-        if (t) {
-          const unsigned long long key =
-              ((unsigned long long)(uint32_t)min(lab_c, o) << 32) | (uint32_t)max(lab_c, o);
-          const unsigned grp = __match_any_sync(tm, key);
-          if ((__ffs(grp) - 1) == lane)
-            pair_emit(keys, cnts, p.table_cap, lab_c, o, __popc(grp), p.status);
+        if (tm) {
+          bool lead = false;
+          int n = 0;
+          if (t) {
+            const unsigned long long key =
+                ((unsigned long long)(uint32_t)min(lab_c, o) << 32) | (uint32_t)max(lab_c, o);
+            const unsigned grp = __match_any_sync(tm, key);
+            lead = (__ffs(grp) - 1) == lane;
+            n = __popc(grp);
+          }
+          pair_add(lead, lab_c, o, n);
         }
       }
     }
@@ -369,8 +421,10 @@ k_region_stats(const RegionStatsParams p) {
   // ---- end of strip: flush runs, pairs, table, label max
   const unsigned fm = __ballot_sync(0xffffffffu, cnt > 0);
   if (fm) flush_lanes(fm);
-  if (rp_cnt > 0) pair_emit(keys, cnts, p.table_cap, rp_a, rp_b, rp_cnt, p.status);
+  pair_add(rp_cnt > 0, rp_a, rp_b, rp_cnt);
   __syncwarp();
+  if (pkey[lane] != ~0ull)
+    pair_emit(keys, cnts, p.table_cap, (int)(pkey[lane] >> 32), (int)(pkey[lane] & 0xFFFFFFFFull), pcnt[lane], p.status);
   for (int s = 0; s < RS_SLOTS; ++s) evict_slot(s);
   lmax = warp_max_i(lmax);
   if (lane == 0 && lmax >= 0) atomicMax(&p.label_max[b], lmax);
@@ -1145,8 +1199,14 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     p.n_sx = ceil_div(W, 32); p.n_sy = ceil_div(H, RS_ROWS);
     p.lab = make_lab_matrix();
     const long long tasks = (long long)B * p.n_sx * p.n_sy;
-    GG_SMEM_ATTR_ONCE(ctx, 0, k_region_stats, RS_SMEM_BYTES);
-    GG_LAUNCH(ctx, k_region_stats, ceil_div(tasks, RS_WARPS), RS_WARPS * 32, RS_SMEM_BYTES, st, p);
+    static const int occ = getenv("GG_RS_OCC") ? atoi(getenv("GG_RS_OCC")) : 2;
+    if (occ == 3) {
+      GG_SMEM_ATTR_ONCE(ctx, 0, k_region_stats<3>, RS_SMEM_BYTES);
+      GG_LAUNCH(ctx, k_region_stats<3>, ceil_div(tasks, RS_WARPS), RS_WARPS * 32, RS_SMEM_BYTES, st, p);
+    } else {
+      GG_SMEM_ATTR_ONCE(ctx, 30, k_region_stats<2>, RS_SMEM_BYTES);
+      GG_LAUNCH(ctx, k_region_stats<2>, ceil_div(tasks, RS_WARPS), RS_WARPS * 32, RS_SMEM_BYTES, st, p);
+    }
   }
   {
     dim3 grid(ceil_div(nc, 256), B);

@@ -207,6 +207,30 @@ k_layernorm(const float* __restrict__ in, const float* __restrict__ g, const flo
 // ------------------------------------------------------------------ GCN aggregation
 // u_v = sum_{j in N(v), j != v} dinv_v dinv_j xw_j + dinv_v^2 xw_v + bias
 // h_v += GELU(u_v * gate_v);  z_v += w_l h_v          (model.py:523-528; GCNConv defaults)
+// Warp per node; a lane owns CPL consecutive channels (one 128-bit load per neighbour row for
+// D = 128); neighbour rows are fetched four at a time so that four gathers are in flight.
+template <int CPL>
+struct ChanVec {
+  float v[CPL];
+  GG_D void load(const float* row, int lane) {
+    if (CPL == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(row + 4 * lane);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) v[j] = row[CPL * lane + j];
+    }
+  }
+  GG_D void store(float* row, int lane) const {
+    if (CPL == 4) {
+      *reinterpret_cast<float4*>(row + 4 * lane) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) row[CPL * lane + j] = v[j];
+    }
+  }
+};
+
 template <int CPL>
 __global__ void __launch_bounds__(256)
 k_gcn_aggregate(const float* __restrict__ xw, const int32_t* __restrict__ rowptr,
@@ -218,25 +242,41 @@ k_gcn_aggregate(const float* __restrict__ xw, const int32_t* __restrict__ rowptr
   const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (v >= sizes[0]) return;
   const float dv = dinv[v];
-  float acc[CPL];
+  ChanVec<CPL> acc, self;
+  self.load(xw + (size_t)v * D, lane);
 #pragma unroll
-  for (int j = 0; j < CPL; ++j) acc[j] = dv * dv * xw[(size_t)v * D + lane + 32 * j];
-  for (int e = rowptr[v]; e < rowptr[v + 1]; ++e) {
-    const int s = src[e];
-    if (s == v) continue;
-    const float w = dv * dinv[s];
-    const float* row = xw + (size_t)s * D;
+  for (int j = 0; j < CPL; ++j) acc.v[j] = dv * dv * self.v[j];
+  const int e0 = rowptr[v], e1 = rowptr[v + 1];
+  for (int e = e0; e < e1; e += 4) {
+    int s4[4];
+    float w4[4];
+    ChanVec<CPL> r4[4];
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) acc[j] = fmaf(w, row[lane + 32 * j], acc[j]);
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = e + u < e1;
+      s4[u] = ok ? src[e + u] : v;
+      w4[u] = (ok && s4[u] != v) ? dv * dinv[s4[u]] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r4[u].load(xw + (size_t)s4[u] * D, lane);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc.v[j] = fmaf(w4[u], r4[u].v[j], acc.v[j]);
   }
+  ChanVec<CPL> hv, zv, gv, bv;
+  hv.load(h + (size_t)v * D, lane);
+  zv.load(z + (size_t)v * D, lane);
+  gv.load(gate + (size_t)v * D, lane);
+  bv.load(bias, lane);
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
-    const size_t idx = (size_t)v * D + lane + 32 * j;
-    const float u = acc[j] + bias[lane + 32 * j];
-    const float hv = h[idx] + gelu_erf(u * gate[idx]);
-    h[idx] = hv;
-    z[idx] += jkw * hv;
+    const float u = acc.v[j] + bv.v[j];
+    hv.v[j] += gelu_erf(u * gv.v[j]);
+    zv.v[j] += jkw * hv.v[j];
   }
+  hv.store(h + (size_t)v * D, lane);
+  zv.store(z + (size_t)v * D, lane);
 }
 
 // SAGE mean aggregation: m_v = mean_{j -> v} h_j (self loops kept, empty -> 0)
@@ -249,17 +289,27 @@ k_sage_mean(const float* __restrict__ h, const int32_t* __restrict__ rowptr,
   const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (v >= sizes[0]) return;
   const int e0 = rowptr[v], e1 = rowptr[v + 1];
-  float acc[CPL];
+  ChanVec<CPL> acc;
 #pragma unroll
-  for (int j = 0; j < CPL; ++j) acc[j] = 0.0f;
-  for (int e = e0; e < e1; ++e) {
-    const float* row = h + (size_t)src[e] * D;
+  for (int j = 0; j < CPL; ++j) acc.v[j] = 0.0f;
+  for (int e = e0; e < e1; e += 4) {
+    ChanVec<CPL> r4[4];
+    float w4[4];
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) acc[j] += row[lane + 32 * j];
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = e + u < e1;
+      w4[u] = ok ? 1.0f : 0.0f;
+      r4[u].load(h + (size_t)(ok ? src[e + u] : v) * D, lane);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc.v[j] = fmaf(w4[u], r4[u].v[j], acc.v[j]);
   }
   const float inv = 1.0f / (float)max(e1 - e0, 1);
 #pragma unroll
-  for (int j = 0; j < CPL; ++j) m[(size_t)v * D + lane + 32 * j] = acc[j] * inv;
+  for (int j = 0; j < CPL; ++j) acc.v[j] *= inv;
+  acc.store(m + (size_t)v * D, lane);
 }
 
 // s = GELU(LN(t)); z += w s      (model.py:530-533)
@@ -617,20 +667,33 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
     });
   }
   // ---- edge context -> gate
+  const bool use_tc = ctx->gemm_impl == 1;
   if (edge_cap > 0) {
-    GG_LAUNCH(ctx, k_edge_enc1, ceil_div(edge_cap * c, 256), 256, 0, st, edge_attr, wb, o, sizes, e1);
-    GG_TRY(gemm(ctx, st, GEMM_ENC2, e1, wb + nw.ee2_w, wb + nw.ee2_b, enc, n_edges_p, edge_cap, c, c, 0, 0));
+    if (use_tc && gemm_tc_supported(ctx, GEMM_ENC2, c, c) && c == 64) {
+      TcPrologue pro;                                   // first encoder layer fused into the A producer
+      pro.mode = 2; pro.w0 = wb + nw.ee0_w; pro.b0 = wb + nw.ee0_b;
+      GG_TRY(gemm_tc(ctx, st, GEMM_ENC2, edge_attr, wb + nw.ee2_b, enc, n_edges_p, edge_cap, c, c, 0, 0, &pro));
+    } else {
+      GG_LAUNCH(ctx, k_edge_enc1, ceil_div(edge_cap * c, 256), 256, 0, st, edge_attr, wb, o, sizes, e1);
+      GG_TRY(gemm(ctx, st, GEMM_ENC2, e1, wb + nw.ee2_w, wb + nw.ee2_b, enc, n_edges_p, edge_cap, c, c, 0, 0));
+    }
   }
   GG_LAUNCH(ctx, k_edge_ctx, warp_blocks, 256, 0, st, enc, rowptr, eid, wb, o, sizes, ctxv);
   GG_TRY(gemm(ctx, st, GEMM_GATE, ctxv, wb + nw.eg_w, wb + nw.eg_b, gate, n_nodes_p, node_cap, D, c, 2, 0));
 
   // ---- residual GCN blocks
   for (int l = 0; l < n; ++l) {
-    GG_CPL_SWITCH(D, {
-      GG_LAUNCH(ctx, k_layernorm<CPL>, warp_blocks, 256, 0, st, h, wb + nw.norm_g[l], wb + nw.norm_b[l],
-                (const float*)nullptr, (const int*)nullptr, sizes, t0);
-    });
-    GG_TRY(gemm(ctx, st, GEMM_GCN0 + l, t0, wb + nw.gcn_w[l], nullptr, t1, n_nodes_p, node_cap, D, D, 0, 0));
+    if (use_tc && gemm_tc_supported(ctx, GEMM_GCN0 + l, D, D) && D == 128) {
+      TcPrologue pro;                                   // LayerNorm fused into the A producer
+      pro.mode = 1; pro.ln_g = wb + nw.norm_g[l]; pro.ln_b = wb + nw.norm_b[l];
+      GG_TRY(gemm_tc(ctx, st, GEMM_GCN0 + l, h, nullptr, t1, n_nodes_p, node_cap, D, D, 0, 0, &pro));
+    } else {
+      GG_CPL_SWITCH(D, {
+        GG_LAUNCH(ctx, k_layernorm<CPL>, warp_blocks, 256, 0, st, h, wb + nw.norm_g[l], wb + nw.norm_b[l],
+                  (const float*)nullptr, (const int*)nullptr, sizes, t0);
+      });
+      GG_TRY(gemm(ctx, st, GEMM_GCN0 + l, t0, wb + nw.gcn_w[l], nullptr, t1, n_nodes_p, node_cap, D, D, 0, 0));
+    }
     GG_CPL_SWITCH(D, {
       GG_LAUNCH(ctx, k_gcn_aggregate<CPL>, warp_blocks, 256, 0, st, t1, rowptr, src, dinv,
                 wb + nw.gcn_b[l], gate, nw.h_jk[l + 1], sizes, h, z);
@@ -649,11 +712,18 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
     const size_t smem = (size_t)(D + D / 2) * sizeof(float);
     GG_LAUNCH(ctx, k_graph_context, n_graphs, 256, smem, st, z, graph_off, wb, o, n_graphs, score, gvec);
   }
-  GG_CPL_SWITCH(D, {
-    GG_LAUNCH(ctx, k_layernorm<CPL>, warp_blocks, 256, 0, st, z, wb + nw.fuse_ln_g, wb + nw.fuse_ln_b,
-              (const float*)gvec, (const int*)node_graph, sizes, t0);
-  });
-  GG_TRY(gemm(ctx, st, GEMM_FUSE, t0, wb + nw.fuse_w, wb + nw.fuse_b, t1, n_nodes_p, node_cap, D, D, 1, 0));
+  if (use_tc && gemm_tc_supported(ctx, GEMM_FUSE, D, D) && D == 128) {
+    TcPrologue pro;                                     // z * gvec[graph] -> LayerNorm fused into the A producer
+    pro.mode = 1; pro.ln_g = wb + nw.fuse_ln_g; pro.ln_b = wb + nw.fuse_ln_b;
+    pro.gvec = gvec; pro.node_graph = node_graph;
+    GG_TRY(gemm_tc(ctx, st, GEMM_FUSE, z, wb + nw.fuse_b, t1, n_nodes_p, node_cap, D, D, 1, 0, &pro));
+  } else {
+    GG_CPL_SWITCH(D, {
+      GG_LAUNCH(ctx, k_layernorm<CPL>, warp_blocks, 256, 0, st, z, wb + nw.fuse_ln_g, wb + nw.fuse_ln_b,
+                (const float*)gvec, (const int*)node_graph, sizes, t0);
+    });
+    GG_TRY(gemm(ctx, st, GEMM_FUSE, t0, wb + nw.fuse_w, wb + nw.fuse_b, t1, n_nodes_p, node_cap, D, D, 1, 0));
+  }
   GG_LAUNCH(ctx, k_head, warp_blocks, 256, 0, st, t1, wb, o, sizes, logits, probs);
   return GG_OK;
 }

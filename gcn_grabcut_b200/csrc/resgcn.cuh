@@ -32,10 +32,22 @@ int gemm(gg_context* ctx, cudaStream_t st, int which, const float* A, const floa
          const float* bias, float* C, const int* m_ptr, long long m_cap, int N, int K, int act,
          int accumulate);
 
+// How gemm_tc produces its A operand (fused prologues), see k_tc_gemm.
+struct TcPrologue {
+  int mode = 0;                      // 0 plain, 1 LayerNorm(row [* gvec[node_graph]]), 2 edge-encoder layer 1
+  const float* ln_g = nullptr;
+  const float* ln_b = nullptr;
+  const float* gvec = nullptr;       // [n_graphs, K] optional per-graph row scale (mode 1)
+  const int* node_graph = nullptr;   // [M]
+  const float* w0 = nullptr;         // [K,5]  (mode 2)
+  const float* b0 = nullptr;         // [K]
+};
+
 // gemm_tc.cu: tcgen05 path
 int gemm_tc_prepare_weights(gg_context* ctx, const std::vector<float>& blob);
 bool gemm_tc_supported(const gg_context* ctx, int which, int N, int K);
 int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* bias, float* C,
-            const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate);
+            const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate,
+            const TcPrologue* prologue = nullptr);
 
 }  // namespace gg

@@ -20,6 +20,7 @@ namespace gg {
 constexpr int GF_NT = 128;          // threads per block = halo columns per block
 constexpr int GF_SY = 64;           // output rows per block (strip height)
 constexpr int GF_MAX_RADIUS = 24;
+constexpr int GF_PROB_TABLE = 1024;  // labels whose (p_bg, p_fg) are staged in shared memory
 
 struct GuidedParams {
   // trimap mode
@@ -58,49 +59,67 @@ struct GfTraits {
 template <int NP>
 struct HorizontalPlan {
   int seglen, nseg, tx;
+  int off, len;          // this thread's task: elements [off, off+len) of plane-major row buffers
   __device__ HorizontalPlan(int radius) {
     tx = GF_NT - 2 * radius;
     const int per = GF_NT / NP;
     seglen = ((tx + per - 1) / per) | 1;
     nseg = (tx + seglen - 1) / seglen;
+    const int t = threadIdx.x;
+    const int pl = t / nseg, seg = t - pl * nseg;
+    const int o0 = seg * seglen;
+    off = pl * GF_NT + o0;
+    len = (t < NP * nseg) ? min(seglen, tx - o0) : 0;
   }
 };
+
+constexpr int GF_RB = 1;   // rows reduced per barrier interval (2 costs occupancy: measured slower on B200)
 
 template <int NP, int RT>
 GG_D void horizontal_means(const double* sV, float* sM, const HorizontalPlan<NP>& hp, int radius,
                            double scale) {
-  const int t = threadIdx.x;
-  if (t < NP * hp.nseg) {
-    const int pl = t / hp.nseg, seg = t - pl * hp.nseg;
-    const int o0 = seg * hp.seglen;
-    const int len = min(hp.seglen, hp.tx - o0);
-    const double* in = sV + pl * GF_NT + o0;
-    float* out = sM + pl * GF_NT + o0;
+  // sV / sM: [GF_RB][NP][GF_NT]; one task = one (plane, segment) for all GF_RB rows
+  if (hp.len > 0) {
+    const int len = hp.len;
+    const double* in = sV + hp.off;
+    float* out = sM + hp.off;
+    constexpr int RS = NP * GF_NT;       // row stride
     if (RT > 0) {
       constexpr int K = 2 * RT + 1;
       constexpr int PER = GF_NT / NP;
       constexpr int SEG = (((GF_NT - 2 * RT) + PER - 1) / PER) | 1;      // == hp.seglen
-      double s = 0.0;
+      double s[GF_RB];
 #pragma unroll
-      for (int d = 0; d < K; ++d) s += in[d];
-      out[0] = (float)(s * scale);
+      for (int j = 0; j < GF_RB; ++j) s[j] = 0.0;
+#pragma unroll
+      for (int d = 0; d < K; ++d)
+#pragma unroll
+        for (int j = 0; j < GF_RB; ++j) s[j] += in[j * RS + d];
+#pragma unroll
+      for (int j = 0; j < GF_RB; ++j) out[j * RS] = (float)(s[j] * scale);
 #pragma unroll
       for (int i = 1; i < SEG; ++i) {
         if (i < len) {
-          s += in[i + K - 1];
-          s -= in[i - 1];
-          out[i] = (float)(s * scale);
+#pragma unroll
+          for (int j = 0; j < GF_RB; ++j) {
+            s[j] += in[j * RS + i + K - 1];
+            s[j] -= in[j * RS + i - 1];
+            out[j * RS + i] = (float)(s[j] * scale);
+          }
         }
       }
     } else {
       const int k = 2 * radius + 1;
-      double s = 0.0;
-      for (int d = 0; d < k; ++d) s += in[d];
-      out[0] = (float)(s * scale);
-      for (int i = 1; i < len; ++i) {
-        s += in[i + k - 1];
-        s -= in[i - 1];
-        out[i] = (float)(s * scale);
+#pragma unroll
+      for (int j = 0; j < GF_RB; ++j) {
+        double s = 0.0;
+        for (int d = 0; d < k; ++d) s += in[j * RS + d];
+        out[j * RS] = (float)(s * scale);
+        for (int i = 1; i < len; ++i) {
+          s += in[j * RS + i + k - 1];
+          s -= in[j * RS + i - 1];
+          out[j * RS + i] = (float)(s * scale);
+        }
       }
     }
   }
@@ -118,9 +137,11 @@ __global__ void __launch_bounds__(GF_NT)
 k_guided_ab(const GuidedParams p) {
   using T = GfTraits<kTrimap>;
   constexpr int NP = T::NPLANE1;
-  __shared__ double sV[NP * GF_NT];
-  __shared__ float sM[NP * GF_NT];
+  constexpr int NS = T::NSRC;
+  __shared__ double sV[GF_RB * NP * GF_NT];
+  __shared__ float sM[GF_RB * NP * GF_NT];
   __shared__ float sLut[256];
+  __shared__ float2 sProb[kTrimap ? GF_PROB_TABLE : 1];     // (p_bg, p_fg) per label, if it fits
   const int r = RT > 0 ? RT : p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
   const HorizontalPlan<NP> hp(r);
   const int x0 = blockIdx.x * hp.tx;
@@ -140,21 +161,30 @@ k_guided_ab(const GuidedParams p) {
     nn = (int)(p.node_off[b + 1] - no);
     prob0 = p.probs + (size_t)no * 3;
     for (int i = t; i < 256; i += GF_NT) sLut[i] = __fdiv_rn((float)i, 255.0f);   // guide = gray/255
+    if (nn <= GF_PROB_TABLE)
+      for (int i = t; i < nn; i += GF_NT) sProb[i] = make_float2(prob0[(size_t)i * 3], prob0[(size_t)i * 3 + 2]);
     __syncthreads();
   }
+  const bool prob_in_smem = kTrimap && nn <= GF_PROB_TABLE;
   // base planes of one pixel of this thread's column: g and the NSRC source planes
-  auto fetch = [&](int yy, float& g, float (&sv)[T::NSRC]) {
+  auto fetch = [&](int yy, float& g, float (&sv)[NS]) {
     const size_t ro = (size_t)reflect_row(yy, H) * W;
     if (kTrimap) {
       const int gr = gcol[ro];
       const int l = lcol[ro];
       g = sLut[gr];
       sv[0] = 0.0f;
-      sv[T::NSRC - 1] = 0.0f;                       // project_to_pixels zero padding
+      sv[NS - 1] = 0.0f;                            // project_to_pixels zero padding
       if (l >= 0 && l < nn) {
-        const float* row = prob0 + (size_t)l * 3;
-        sv[0] = row[0];
-        sv[T::NSRC - 1] = row[2];
+        if (prob_in_smem) {
+          const float2 pr = sProb[l];
+          sv[0] = pr.x;
+          sv[NS - 1] = pr.y;
+        } else {
+          const float* row = prob0 + (size_t)l * 3;
+          sv[0] = row[0];
+          sv[NS - 1] = row[2];
+        }
       }
     } else {
       g = ucol[ro];
@@ -164,63 +194,83 @@ k_guided_ab(const GuidedParams p) {
   double vs[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) vs[q] = 0.0;
-  auto add = [&](float g, const float (&sv)[T::NSRC]) {
+  auto add = [&](float g, const float (&sv)[NS]) {
     vs[0] += (double)g;
     vs[1] += (double)__fmul_rn(g, g);
 #pragma unroll
-    for (int c = 0; c < T::NSRC; ++c) {
+    for (int c = 0; c < NS; ++c) {
       vs[2 + 2 * c] += (double)sv[c];
       vs[3 + 2 * c] += (double)__fmul_rn(g, sv[c]);
     }
   };
-  auto sub = [&](float g, const float (&sv)[T::NSRC]) {
+  auto sub = [&](float g, const float (&sv)[NS]) {
     vs[0] -= (double)g;
     vs[1] -= (double)__fmul_rn(g, g);
 #pragma unroll
-    for (int c = 0; c < T::NSRC; ++c) {
+    for (int c = 0; c < NS; ++c) {
       vs[2 + 2 * c] -= (double)sv[c];
       vs[3 + 2 * c] -= (double)__fmul_rn(g, sv[c]);
     }
   };
   for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
-    float g, sv[T::NSRC];
+    float g, sv[NS];
     fetch(yy, g, sv);
     add(g, sv);
   }
-  // software pipeline: the rows entering / leaving the window of row y+1 are fetched while
-  // row y is being reduced
-  float gn, svn[T::NSRC], go = 0.f, svo[T::NSRC];
+  // software pipeline: the rows entering / leaving the windows of the NEXT batch of GF_RB rows
+  // are in flight while the current batch is reduced
+  struct Batch { float gn[GF_RB], go[GF_RB], svn[GF_RB][NS], svo[GF_RB][NS]; };
+  auto load_batch = [&](int y0, Batch& bt) {
 #pragma unroll
-  for (int c = 0; c < T::NSRC; ++c) svo[c] = 0.f;
-  fetch(y_begin + r, gn, svn);
-  for (int y = y_begin; y < y_end; ++y) {
-    add(gn, svn);
-    if (y > y_begin) sub(go, svo);
-    if (y + 1 < y_end) {
-      fetch(y + 1 + r, gn, svn);
-      fetch(y - r, go, svo);
+    for (int j = 0; j < GF_RB; ++j) {
+      bt.gn[j] = bt.go[j] = 0.f;
+#pragma unroll
+      for (int c = 0; c < NS; ++c) bt.svn[j][c] = bt.svo[j][c] = 0.f;
+      if (y0 + j < y_end) {
+        fetch(y0 + j + r, bt.gn[j], bt.svn[j]);
+        if (y0 + j > y_begin) fetch(y0 + j - r - 1, bt.go[j], bt.svo[j]);
+      }
     }
+  };
+  Batch cur, nxt;
+  load_batch(y_begin, cur);
+  for (int y = y_begin; y < y_end; y += GF_RB) {
+    if (y + GF_RB < y_end) load_batch(y + GF_RB, nxt);
 #pragma unroll
-    for (int q = 0; q < NP; ++q) sV[q * GF_NT + t] = vs[q];
+    for (int j = 0; j < GF_RB; ++j) {
+      if (y + j < y_end) {
+        add(cur.gn[j], cur.svn[j]);
+        if (y + j > y_begin) sub(cur.go[j], cur.svo[j]);
+      }
+#pragma unroll
+      for (int q = 0; q < NP; ++q) sV[(j * NP + q) * GF_NT + t] = vs[q];
+    }
     __syncthreads();
     horizontal_means<NP, RT>(sV, sM, hp, r, scale);
     __syncthreads();
     const int o = t - r, x = x0 + o;
     if (o >= 0 && o < hp.tx && x < W) {
-      const float mg = sM[o], mgg = sM[GF_NT + o];
-      const float var = __fsub_rn(mgg, __fmul_rn(mg, mg));
-      const float den = __fadd_rn(var, p.eps);
-      const size_t op = img_off + (size_t)y * W + x;
 #pragma unroll
-      for (int c = 0; c < T::NSRC; ++c) {
-        const float ms = sM[(2 + 2 * c) * GF_NT + o], mgs = sM[(3 + 2 * c) * GF_NT + o];
-        const float cov = __fsub_rn(mgs, __fmul_rn(mg, ms));
-        const float a = __fdiv_rn(cov, den);
-        const float bb = __fsub_rn(ms, __fmul_rn(a, mg));
-        p.ab[(size_t)(2 * c) * p.plane_stride + op] = a;
-        p.ab[(size_t)(2 * c + 1) * p.plane_stride + op] = bb;
+      for (int j = 0; j < GF_RB; ++j) {
+        if (y + j < y_end) {
+          const float* m = sM + j * NP * GF_NT + o;
+          const float mg = m[0], mgg = m[GF_NT];
+          const float var = __fsub_rn(mgg, __fmul_rn(mg, mg));
+          const float den = __fadd_rn(var, p.eps);
+          const size_t op = img_off + (size_t)(y + j) * W + x;
+#pragma unroll
+          for (int c = 0; c < NS; ++c) {
+            const float ms = m[(2 + 2 * c) * GF_NT], mgs = m[(3 + 2 * c) * GF_NT];
+            const float cov = __fsub_rn(mgs, __fmul_rn(mg, ms));
+            const float a = __fdiv_rn(cov, den);
+            const float bb = __fsub_rn(ms, __fmul_rn(a, mg));
+            p.ab[(size_t)(2 * c) * p.plane_stride + op] = a;
+            p.ab[(size_t)(2 * c + 1) * p.plane_stride + op] = bb;
+          }
+        }
       }
     }
+    cur = nxt;
   }
 }
 
@@ -229,8 +279,8 @@ __global__ void __launch_bounds__(GF_NT)
 k_guided_out(const GuidedParams p) {
   using T = GfTraits<kTrimap>;
   constexpr int NP = T::NPLANE2;
-  __shared__ double sV[NP * GF_NT];
-  __shared__ float sM[NP * GF_NT];
+  __shared__ double sV[GF_RB * NP * GF_NT];
+  __shared__ float sM[GF_RB * NP * GF_NT];
   const int r = RT > 0 ? RT : p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
   const HorizontalPlan<NP> hp(r);
   const int x0 = blockIdx.x * hp.tx;
@@ -245,7 +295,7 @@ k_guided_out(const GuidedParams p) {
   auto load_row = [&](int yy, float (&v)[NP]) {
     const size_t ro = (size_t)reflect_row(yy, H) * W;
 #pragma unroll
-    for (int q = 0; q < NP; ++q) v[q] = col[(size_t)q * p.plane_stride + ro];
+    for (int q = 0; q < NP; ++q) v[q] = __ldg(col + (size_t)q * p.plane_stride + ro);
   };
   for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
     float v[NP];
@@ -253,47 +303,66 @@ k_guided_out(const GuidedParams p) {
 #pragma unroll
     for (int q = 0; q < NP; ++q) vs[q] += (double)v[q];
   }
-  float vn[NP], vo[NP];
+  struct Batch { float vn[GF_RB][NP], vo[GF_RB][NP]; };
+  auto load_batch = [&](int y0, Batch& bt) {
 #pragma unroll
-  for (int q = 0; q < NP; ++q) vo[q] = 0.f;
-  load_row(y_begin + r, vn);
-  for (int y = y_begin; y < y_end; ++y) {
+    for (int j = 0; j < GF_RB; ++j) {
 #pragma unroll
-    for (int q = 0; q < NP; ++q) vs[q] += (double)vn[q];
-    if (y > y_begin) {
-#pragma unroll
-      for (int q = 0; q < NP; ++q) vs[q] -= (double)vo[q];
+      for (int q = 0; q < NP; ++q) bt.vn[j][q] = bt.vo[j][q] = 0.f;
+      if (y0 + j < y_end) {
+        load_row(y0 + j + r, bt.vn[j]);
+        if (y0 + j > y_begin) load_row(y0 + j - r - 1, bt.vo[j]);
+      }
     }
-    if (y + 1 < y_end) {
-      load_row(y + 1 + r, vn);
-      load_row(y - r, vo);
-    }
+  };
+  Batch cur, nxt;
+  load_batch(y_begin, cur);
+  for (int y = y_begin; y < y_end; y += GF_RB) {
+    if (y + GF_RB < y_end) load_batch(y + GF_RB, nxt);
 #pragma unroll
-    for (int q = 0; q < NP; ++q) sV[q * GF_NT + t] = vs[q];
+    for (int j = 0; j < GF_RB; ++j) {
+      if (y + j < y_end) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) vs[q] += (double)cur.vn[j][q];
+        if (y + j > y_begin) {
+#pragma unroll
+          for (int q = 0; q < NP; ++q) vs[q] -= (double)cur.vo[j][q];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NP; ++q) sV[(j * NP + q) * GF_NT + t] = vs[q];
+    }
     __syncthreads();
     horizontal_means<NP, RT>(sV, sM, hp, r, scale);
     __syncthreads();
     const int o = t - r, x = x0 + o;
     if (o >= 0 && o < hp.tx && x < W) {
-      const size_t op = img_off + (size_t)y * W + x;
-      const float g = kTrimap ? __fdiv_rn((float)p.gray[op], 255.0f) : p.guide[op];
-      float q[T::NSRC];
 #pragma unroll
-      for (int c = 0; c < T::NSRC; ++c)
-        q[c] = __fadd_rn(__fmul_rn(sM[(2 * c) * GF_NT + o], g), sM[(2 * c + 1) * GF_NT + o]);
-      if (kTrimap) {
-        const float pbg = fminf(fmaxf(q[0], 0.0f), 1.0f);          // np.clip(., 0, 1)
-        const float pfg = fminf(fmaxf(q[T::NSRC - 1], 0.0f), 1.0f);
-        uint8_t tv = (pfg > pbg) ? 3 : 2;                          // pipeline.py:143-145
-        if (pbg >= p.thr_bg) tv = 0;
-        if (pfg >= p.thr_fg) tv = 1;
-        p.trimap[op] = tv;
-        if (p.q0) p.q0[op] = pbg;
-        if (p.q1) p.q1[op] = pfg;
-      } else {
-        p.q0[op] = q[0];
+      for (int j = 0; j < GF_RB; ++j) {
+        if (y + j < y_end) {
+          const float* m = sM + j * NP * GF_NT + o;
+          const size_t op = img_off + (size_t)(y + j) * W + x;
+          const float g = kTrimap ? __fdiv_rn((float)p.gray[op], 255.0f) : p.guide[op];
+          float q[T::NSRC];
+#pragma unroll
+          for (int c = 0; c < T::NSRC; ++c)
+            q[c] = __fadd_rn(__fmul_rn(m[(2 * c) * GF_NT], g), m[(2 * c + 1) * GF_NT]);
+          if (kTrimap) {
+            const float pbg = fminf(fmaxf(q[0], 0.0f), 1.0f);          // np.clip(., 0, 1)
+            const float pfg = fminf(fmaxf(q[T::NSRC - 1], 0.0f), 1.0f);
+            uint8_t tv = (pfg > pbg) ? 3 : 2;                          // pipeline.py:143-145
+            if (pbg >= p.thr_bg) tv = 0;
+            if (pfg >= p.thr_fg) tv = 1;
+            p.trimap[op] = tv;
+            if (p.q0) p.q0[op] = pbg;
+            if (p.q1) p.q1[op] = pfg;
+          } else {
+            p.q0[op] = q[0];
+          }
+        }
       }
     }
+    cur = nxt;
   }
 }
 
