@@ -109,16 +109,32 @@ static size_t path_workspace_bytes(gg_context* ctx, int B, int H, int W, const g
          resgcn_workspace_bytes(ctx->net, SN, SE, B) + trimap_workspace_bytes(B, H, W, false);
 }
 
+static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* labels, int B,
+                    int H, int W, const gg_path_config& pc, uint8_t* trimap, float* probs_out,
+                    int64_t* node_off_out, int32_t* n_nodes_out, int32_t* n_edges_out,
+                    cudaStream_t st, cudaEvent_t graph_done = nullptr);
+
+// The same path with the batch cut into ctx->n_sub contiguous sub-batches that run
+// concurrently on internal streams (forked from / joined into the caller's stream).  The
+// kernels of the path are latency-bound at one batch per GPU; two independent sub-batches in
+// flight fill the idle issue slots.  Outputs that are prefix-summed over the whole batch
+// (probs / node_off) force a single batch.
+static int run_path_multi(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* labels, int B,
+                          int H, int W, const gg_path_config& pc, uint8_t* trimap, float* probs_out,
+                          int64_t* node_off_out, int32_t* n_nodes_out, int32_t* n_edges_out,
+                          cudaStream_t st, int first_sub_stream = 0);
+
 // graph build -> network -> trimap for B images whose inputs are on the device.
 static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* labels, int B,
                     int H, int W, const gg_path_config& pc, uint8_t* trimap, float* probs_out,
                     int64_t* node_off_out, int32_t* n_nodes_out, int32_t* n_edges_out,
-                    cudaStream_t st) {
+                    cudaStream_t st, cudaEvent_t graph_done) {
   const gg_graph_config cfg = norm_cfg(pc.graph);
   const long long SN = (long long)B * cfg.node_cap, SE = 2ll * B * cfg.pair_cap;
   PathBuffers pb = take_path_buffers(ar, B, cfg);
   const uint8_t* gray = nullptr;
   GG_TRY(build_graphs(ctx, ar, bgr, labels, B, H, W, cfg, pb.g, st, &gray));
+  if (graph_done) GG_CUDA_OK(cudaEventRecord(graph_done, st));
   GG_TRY(resgcn_forward(ctx, ar, pb.g.x, pb.g.csr_rowptr, pb.g.csr_src, pb.g.csr_eid, pb.g.edge_attr,
                         pb.g.node_off, B, SN, SE, nullptr, pb.probs, st));
   if (pc.edge_aware) {
@@ -136,6 +152,56 @@ static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_
   if (n_edges_out)
     GG_CUDA_OK(cudaMemcpyAsync(n_edges_out, pb.g.n_edges, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   return GG_OK;
+}
+
+static int run_path_multi(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* labels, int B,
+                          int H, int W, const gg_path_config& pc, uint8_t* trimap, float* probs_out,
+                          int64_t* node_off_out, int32_t* n_nodes_out, int32_t* n_edges_out,
+                          cudaStream_t st, int first_sub_stream) {
+  int S = std::min(ctx->n_sub, B);
+  if (probs_out || node_off_out || B < 16) S = 1;
+  if (S <= 1) {
+    ctx->status_word = ctx->d_status;
+    return run_path(ctx, ar, bgr, labels, B, H, W, pc, trimap, probs_out, node_off_out, n_nodes_out,
+                    n_edges_out, st);
+  }
+  const size_t npx = (size_t)H * W;
+  const int per = (B + S - 1) / S;
+  const size_t slice = path_workspace_bytes(ctx, per, H, W, pc);
+  cudaEvent_t ev_fork = ctx->ev[12];
+  GG_CUDA_OK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));
+  GG_CUDA_OK(cudaEventRecord(ev_fork, st));
+  int rc = GG_OK;
+  for (int s = 0; s < S && rc == GG_OK; ++s) {
+    const int b0 = s * per, nb = std::min(per, B - b0);
+    if (nb <= 0) break;
+    cudaStream_t ss = ctx->s_sub[(first_sub_stream + s) & 3];
+    GG_CUDA_OK(cudaStreamWaitEvent(ss, ev_fork, 0));
+    // stagger: sub-batch s starts its (issue-bound) pixel kernels when sub-batch s-1 has finished
+    // its own and moved on to the (latency-bound, low-occupancy) network stage
+    if (s > 0 && ctx->stagger) GG_CUDA_OK(cudaStreamWaitEvent(ss, ctx->ev[17 + s - 1], 0));
+    Arena sub;
+    sub.base = ar.base + ar.off + (size_t)s * slice;
+    sub.cap = slice;
+    ctx->status_word = ctx->d_status + 8 + s;
+    rc = run_path(ctx, sub, bgr + (size_t)b0 * npx * 3, labels + (size_t)b0 * npx, nb, H, W, pc,
+                  trimap + (size_t)b0 * npx, nullptr, nullptr, n_nodes_out ? n_nodes_out + b0 : nullptr,
+                  n_edges_out ? n_edges_out + b0 : nullptr, ss, ctx->ev[17 + s]);
+    if (rc == GG_OK) {
+      GG_LAUNCH(ctx, k_status_or, 1, 1, 0, ss, ctx->d_status + 8 + s, ctx->d_status);
+      GG_CUDA_OK(cudaEventRecord(ctx->ev[13 + s], ss));
+      GG_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev[13 + s], 0));
+    }
+  }
+  ctx->status_word = ctx->d_status;
+  ar.off += (size_t)S * slice;
+  return rc;
+}
+
+static size_t path_multi_workspace_bytes(gg_context* ctx, int B, int H, int W, const gg_path_config& pc) {
+  const int S = std::max(1, std::min(ctx->n_sub, B));
+  const int per = (B + S - 1) / S;
+  return std::max(path_workspace_bytes(ctx, B, H, W, pc), (size_t)S * path_workspace_bytes(ctx, per, H, W, pc));
 }
 
 }  // namespace gg
@@ -173,6 +239,7 @@ int gg_create(gg_handle* out, int device) {
   c->cc_minor = prop.minor;
   GG_CUDA_OK(cudaMalloc((void**)&c->d_status, 64));
   GG_CUDA_OK(cudaMemset(c->d_status, 0, 64));
+  c->status_word = c->d_status;
   double lin[256];
   for (int v = 0; v < 256; ++v) lin[v] = srgb_linear(v);
   GG_CUDA_OK(cudaMalloc((void**)&c->d_lin, sizeof(lin)));
@@ -180,7 +247,10 @@ int gg_create(gg_handle* out, int device) {
   GG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
   GG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_run, cudaStreamNonBlocking));
   GG_CUDA_OK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-  c->ev.resize(16);
+  for (auto& sst : c->s_sub) GG_CUDA_OK(cudaStreamCreateWithFlags(&sst, cudaStreamNonBlocking));
+  if (const char* ns = getenv("GG_SUBBATCH")) c->n_sub = std::max(1, std::min(4, atoi(ns)));
+  if (const char* sg = getenv("GG_STAGGER")) c->stagger = atoi(sg) != 0;
+  c->ev.resize(24);
   for (auto& ev : c->ev) GG_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   const char* impl = getenv("GG_GEMM_IMPL");
   c->gemm_impl = 1;
@@ -204,12 +274,14 @@ void gg_destroy(gg_handle h) {
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_run) cudaStreamDestroy(h->s_run);
   if (h->s_out) cudaStreamDestroy(h->s_out);
+  for (auto& sst : h->s_sub) if (sst) cudaStreamDestroy(sst);
   delete h;
 }
 
 int gg_set_option(gg_handle h, const char* key, int value) {
   GG_REQUIRE(h && key, "gg_set_option: null");
   if (!strcmp(key, "gemm_impl")) { h->gemm_impl = value; return GG_OK; }
+  if (!strcmp(key, "n_sub")) { h->n_sub = std::max(1, std::min(4, value)); return GG_OK; }
   set_error("gg_set_option: unknown key %s", key);
   return GG_ERR_INVALID;
 }
@@ -310,9 +382,9 @@ int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* la
   GG_REQUIRE(h && bgr_dev && labels_dev && cfg && trimap_dev, "gg_trimap_path_device: null argument");
   GG_CUDA_OK(cudaSetDevice(h->device));
   if (!h->net.loaded) { set_error("gg_trimap_path_device: call gg_load_weights first"); return GG_ERR_STATE; }
-  GG_TRY(h->arena.reserve(path_workspace_bytes(h, B, H, W, *cfg)));
-  return run_path(h, h->arena, bgr_dev, labels_dev, B, H, W, *cfg, trimap_dev, probs_dev, node_off_dev,
-                  nullptr, nullptr, (cudaStream_t)stream);
+  GG_TRY(h->arena.reserve(path_multi_workspace_bytes(h, B, H, W, *cfg)));
+  return run_path_multi(h, h->arena, bgr_dev, labels_dev, B, H, W, *cfg, trimap_dev, probs_dev, node_off_dev,
+                        nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // Host buffers in, host trimaps out.  The batch is cut into chunks; chunk i+1 is copied in
@@ -327,7 +399,7 @@ int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* lab
   GG_CUDA_OK(cudaSetDevice(h->device));
   if (!h->net.loaded) { set_error("gg_trimap_path_host: call gg_load_weights first"); return GG_ERR_STATE; }
   const size_t npx = (size_t)H * W;
-  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)((32u << 20) / (npx * 7) + 1)));
+  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)((68u << 20) / (npx * 7) + 1)));
   chunk = std::min(chunk, B);
   const int n_chunks = (B + chunk - 1) / chunk;
   const int n_slots = std::min(n_chunks, 3);
@@ -354,19 +426,25 @@ int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* lab
     GG_CUDA_OK(cudaMemcpyAsync(d_bgr, bgr_host + (size_t)b0 * npx * 3, (size_t)nb * npx * 3, cudaMemcpyHostToDevice, h->s_in));
     GG_CUDA_OK(cudaMemcpyAsync(d_lab, labels_host + (size_t)b0 * npx, (size_t)nb * npx * 4, cudaMemcpyHostToDevice, h->s_in));
     GG_CUDA_OK(cudaEventRecord(ev_in[s], h->s_in));
-    GG_CUDA_OK(cudaStreamWaitEvent(h->s_run, ev_in[s], 0));
+    // consecutive chunks alternate between two compute streams, so that the (latency-bound)
+    // kernels of two chunks overlap on the device
+    cudaStream_t rs = (ci & 1) ? h->s_sub[3] : h->s_run;
+    GG_CUDA_OK(cudaStreamWaitEvent(rs, ev_in[s], 0));
+    h->status_word = h->d_status + 2 + (ci & 1);
     int st = run_path(h, ar, d_bgr, d_lab, nb, H, W, *cfg, d_tri, nullptr, nullptr,
                       n_nodes_host ? n_nodes_host + b0 : nullptr, n_edges_host ? n_edges_host + b0 : nullptr,
-                      h->s_run);
+                      rs);
+    h->status_word = h->d_status;
     if (st != GG_OK) { cudaDeviceSynchronize(); return st; }
-    // accumulate the per-chunk device status (run_path's build resets word 0)
-    GG_LAUNCH(h, k_status_or, 1, 1, 0, h->s_run, h->d_status, h->d_status + 1);
-    GG_CUDA_OK(cudaEventRecord(ev_run[s], h->s_run));
+    // accumulate the per-chunk device status into the sticky word
+    GG_LAUNCH(h, k_status_or, 1, 1, 0, rs, h->d_status + 2 + (ci & 1), h->d_status + 1);
+    GG_CUDA_OK(cudaEventRecord(ev_run[s], rs));
     GG_CUDA_OK(cudaStreamWaitEvent(h->s_out, ev_run[s], 0));
     GG_CUDA_OK(cudaMemcpyAsync(trimap_host + (size_t)b0 * npx, d_tri, (size_t)nb * npx, cudaMemcpyDeviceToHost, h->s_out));
     GG_CUDA_OK(cudaEventRecord(ev_out[s], h->s_out));
   }
   GG_CUDA_OK(cudaStreamSynchronize(h->s_run));
+  GG_CUDA_OK(cudaStreamSynchronize(h->s_sub[3]));
   GG_CUDA_OK(cudaStreamSynchronize(h->s_out));
   GG_CUDA_OK(cudaStreamSynchronize(h->s_in));
   int bits = 0;

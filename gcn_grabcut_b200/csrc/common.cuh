@@ -97,12 +97,16 @@ struct gg_context {
   gg::Arena arena;        // device-pointer entry points (caller's stream)
   gg::Arena host_arena;   // gg_trimap_path_host chunk workspaces
   gg::NetWeights net;
-  int* d_status = nullptr;
+  int* d_status = nullptr;   // [16] words: 0 last call, 1 sticky (host path), 8.. per sub-batch
+  int* status_word = nullptr;  // word the kernels being enqueued right now report into
   double* d_lin = nullptr;   // sRGB linearisation table (256 doubles), built in gg_create
   int64_t launches = 0;
   uint64_t attr_done = 0;   // one bit per kernel whose max-dynamic-smem attribute is already set
   int gemm_impl = 1;      // 0 = SIMT fp32 (validation), 1 = tcgen05 bf16x3
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  cudaStream_t s_sub[4] = {nullptr, nullptr, nullptr, nullptr};   // concurrent sub-batch streams
+  int n_sub = 2;
+  bool stagger = false;
   std::vector<cudaEvent_t> ev;
   // per-kernel CUDA-event timing (gg_profile_enable / gg_profile_report)
   bool prof_on = false;

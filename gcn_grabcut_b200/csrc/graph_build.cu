@@ -1183,7 +1183,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
   GG_CUDA_OK(cudaMemsetAsync(pcnts, 0, (size_t)B * tc * sizeof(int), st));
   GG_CUDA_OK(cudaMemsetAsync(gradmax, 0, (size_t)B * 4 * sizeof(int), st));
   GG_CUDA_OK(cudaMemsetAsync(label_max, 0xFF, (size_t)B * 4 * sizeof(int), st));
-  GG_CUDA_OK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));
+  GG_CUDA_OK(cudaMemsetAsync(ctx->status_word, 0, sizeof(int), st));
 
   {
     dim3 grid(ceil_div(W, K0_TX), ceil_div(H, K0_TY), B);
@@ -1194,7 +1194,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     RegionStatsParams p;
     p.bgr = bgr; p.gray = gray; p.labels = labels; p.gradmax_sq = gradmax; p.coord = coord;
     p.lin_lut = lin; p.acc = acc; p.label_max = label_max; p.pair_keys = pkeys;
-    p.pair_cnts = pcnts; p.status = ctx->d_status; p.B = B; p.H = H; p.W = W; p.node_cap = nc;
+    p.pair_cnts = pcnts; p.status = ctx->status_word; p.B = B; p.H = H; p.W = W; p.node_cap = nc;
     p.table_cap = tc; p.connectivity = cfg.connectivity;
     p.n_sx = ceil_div(W, 32); p.n_sy = ceil_div(H, RS_ROWS);
     p.lab = make_lab_matrix();
@@ -1213,7 +1213,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     GG_LAUNCH(ctx, k_finalize_regions, grid, 256, 0, st, acc, label_max, stats, B, H, W, nc);
   }
   GG_LAUNCH(ctx, k_adj_sort, B, 512, 0, st, pkeys, pcnts, label_max, pairs, shared, start_adj,
-            cursor, n_adj, max_shared, ctx->d_status, nc, tc, pc);
+            cursor, n_adj, max_shared, ctx->status_word, nc, tc, pc);
   if (k > 0) {
     dim3 grid(ceil_div(nc, 8), B);
     if (k <= 4) GG_TRY(launch_knn<4>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
@@ -1222,7 +1222,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     else GG_TRY(launch_knn<32>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
   }
   GG_LAUNCH(ctx, k_nl_pairs, B, 512, 0, st, picks, label_max, n_adj, pairs, start_nl, cursor, n_nl,
-            ctx->d_status, nc, pc, k);
+            ctx->status_word, nc, pc, k);
   GG_LAUNCH(ctx, k_offsets, 1, 1024, 0, st, label_max, n_adj, n_nl, B, nc, out.n_nodes,
             out.n_edges, out.node_off, out.edge_off, out.n_adj_pairs, out.n_nl_pairs);
   GG_LAUNCH(ctx, k_node_features, B, 256, 0, st, stats, label_max, out.node_off, out.x,

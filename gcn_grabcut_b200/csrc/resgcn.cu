@@ -653,7 +653,7 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   const int* n_edges_p = sizes + 1;
 
   const int warp_blocks = ceil_div(node_cap, 8);   // warp-per-node kernels, 8 warps per block
-  GG_LAUNCH(ctx, k_sizes, 1, 1, 0, st, graph_off, n_graphs, rowptr, sizes, node_cap, edge_cap, ctx->d_status);
+  GG_LAUNCH(ctx, k_sizes, 1, 1, 0, st, graph_off, n_graphs, rowptr, sizes, node_cap, edge_cap, ctx->status_word);
   GG_LAUNCH(ctx, k_node_meta, ceil_div(node_cap, 256), 256, 0, st, graph_off, n_graphs, rowptr, src,
             sizes, node_graph, dinv);
 
@@ -783,8 +783,8 @@ int coo_to_csr(gg_context* ctx, Arena& ar, const int64_t* ei, long long E, long 
   GG_REQUIRE(N > 0 && E >= 0 && N < (1ll << 31) && E < (1ll << 31), "coo_to_csr: bad sizes");
   int* cnt = ar.take<int>((size_t)N);
   GG_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)N * sizeof(int), st));
-  GG_CUDA_OK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));
-  if (E > 0) GG_LAUNCH(ctx, k_coo_count, ceil_div(E, 256), 256, 0, st, ei, E, N, cnt, ctx->d_status);
+  GG_CUDA_OK(cudaMemsetAsync(ctx->status_word, 0, sizeof(int), st));
+  if (E > 0) GG_LAUNCH(ctx, k_coo_count, ceil_div(E, 256), 256, 0, st, ei, E, N, cnt, ctx->status_word);
   GG_LAUNCH(ctx, k_coo_scan, 1, 1024, 0, st, cnt, rowptr, N);
   if (E > 0) GG_LAUNCH(ctx, k_coo_fill, ceil_div(E, 256), 256, 0, st, ei, E, N, rowptr, cnt, src, eid);
   GG_LAUNCH(ctx, k_coo_sort_rows, ceil_div(N, 256), 256, 0, st, rowptr, N, src, eid);

@@ -60,7 +60,9 @@ int gg_create(gg_handle* out, int device);
 void gg_destroy(gg_handle h);
 
 /* Runtime options.  "gemm_impl": 1 = tcgen05 tensor-core transforms (default),
- * 0 = SIMT fp32 transforms (validation of the tensor-core path; same device, same API). */
+ * 0 = SIMT fp32 transforms (validation of the tensor-core path; same device, same API).
+ * "n_sub": number of concurrent sub-batches (internal streams) the whole-path entry points
+ * cut a batch into, 1..4 (default 2; env GG_SUBBATCH). */
 int gg_set_option(gg_handle h, const char* key, int value);
 
 /* Device-side status word written by the kernels of the last enqueued call:

@@ -348,3 +348,55 @@ def test_trimap_path_host_vs_oracle(gg, edge_aware):
     # device-resident entry point gives the same trimaps
     td = path.run_device(torch.from_numpy(imgs).cuda(), torch.from_numpy(labs).cuda())
     assert np.array_equal(td.cpu().numpy(), tri)
+
+
+# ----------------------------------------------------------------------------- larger configurations
+def test_config_c_full_hd_dense_nonlocal(gg):
+    """BASELINE config C shape: 1080x1920, ~2000 superpixels, dense non-local edges (k=16),
+    against the oracle on one image (the CPU side takes a few seconds per image)."""
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import model_port, trimap_port
+    H, W, nseg, k = 1080, 1920, 2000, 16
+    imgs, labs = make_batch(2, H, W, nseg, seed0=11, scale=min(H, W) / 320)
+    cfg = gg.SuperpixelGraphConfig(n_segments=nseg, n_nonlocal=k)
+    graphs = gg.build_graph_batch(imgs, labs, cfg).to_graphs(labs)
+    ref = _oracle_graph(imgs[0], labs[0], 4, k)
+    _assert_graph_matches(graphs[0], ref, int(ref.stages["knn_ties"]))
+    print(f"config C: N={ref.n_nodes} E={ref.n_edges} knn ties={int(ref.stages['knn_ties'])}")
+    state = model_port.random_state_dict(128, 6, seed=0)
+    path = gg.TrimapPath(state, cfg, node_cap=int(labs.max()) + 1)
+    tri = path(imgs, labs)
+    probs = model_port.predict_probs(state, torch.tensor(ref.node_input()), torch.tensor(ref.edge_index),
+                                     torch.tensor(ref.edge_attr))
+    rt, rbg, rfg = trimap_port.refine_trimap(probs, labs[0], imgs[0], return_planes=True)
+    near = trimap_port.near_threshold_mask(rbg, rfg, 0.55, 0.55, 2e-4)
+    assert int(((tri[0] != rt) & ~near).sum()) == 0
+
+
+def test_config_e_4k_invariants(gg):
+    """BASELINE config E shape: 2160x3840, ~10k regions, wider/deeper network (D=256, n=8; the
+    SIMT transforms): size-independent properties only (the oracle's N x N matrices need GBs)."""
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import model_port
+    H, W, nseg = 2160, 3840, 10000
+    imgs, labs = make_batch(1, H, W, nseg, seed0=5, scale=min(H, W) / 320)
+    cfg = gg.SuperpixelGraphConfig(n_segments=nseg, n_nonlocal=4)
+    batch = gg.build_graph_batch(imgs, labs, cfg)
+    g = batch.to_graphs(labs)[0]
+    n = int(labs.max()) + 1
+    assert g.n_nodes == n
+    counts = np.bincount(labs[0].ravel(), minlength=n)
+    np.testing.assert_allclose(g.node_areas, counts / float(H * W), rtol=1e-6)        # exact counts
+    from oracle import graph_port
+    adj, cnt = graph_port.adjacency_pairs(labs[0], n, 4)                               # integer oracle, cheap
+    na = int(batch.n_adj_pairs[0])
+    assert na == len(adj) and np.array_equal(g.edge_index[:, :na].T, adj)
+    assert np.array_equal(batch.shared_cnt.cpu().numpy()[:na], cnt)
+    half = g.n_edges // 2
+    assert np.array_equal(g.edge_index[0, :half], g.edge_index[1, half:])
+    assert np.isfinite(g.node_input()).all() and np.isfinite(g.edge_attr).all()
+    assert g.prior_features.min() >= 0 and g.prior_features.max() <= 1
+    state = model_port.random_state_dict(256, 8, seed=0)
+    path = gg.TrimapPath(state, cfg, node_cap=n)
+    tri = path(imgs, labs)
+    assert tri.shape == (1, H, W) and set(np.unique(tri)).issubset({0, 1, 2, 3})
