@@ -92,7 +92,8 @@ EXPORTED_SYMBOLS = (
     "gg_abi_version", "gg_last_error", "gg_create", "gg_destroy", "gg_set_option",
     "gg_check_device_status", "gg_build_graphs", "gg_pixel_planes", "gg_load_weights",
     "gg_coo_to_csr", "gg_resgcn_forward", "gg_refine_trimap", "gg_project_trimap",
-    "gg_guided_filter", "gg_trimap_path_host", "gg_trimap_path_device", "gg_kernel_launch_count",
+    "gg_guided_filter", "gg_trimap_path_host", "gg_trimap_path_host_submit", "gg_trimap_path_host_wait",
+    "gg_trimap_path_device", "gg_kernel_launch_count",
     "gg_profile_enable", "gg_profile_report")
 
 _lib = None
@@ -137,6 +138,10 @@ def lib() -> C.CDLL:
             L.gg_trimap_path_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                               C.c_int, C.POINTER(PathConfig), C.c_void_p, C.c_void_p,
                                               C.c_void_p]
+            L.gg_trimap_path_host_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                     C.c_int, C.POINTER(PathConfig), C.c_void_p, C.c_void_p,
+                                                     C.c_void_p, C.POINTER(C.c_int)]
+            L.gg_trimap_path_host_wait.argtypes = [C.c_void_p, C.c_int]
             L.gg_trimap_path_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                 C.c_int, C.POINTER(PathConfig), C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]

@@ -252,6 +252,7 @@ int gg_create(gg_handle* out, int device) {
   if (const char* sg = getenv("GG_STAGGER")) c->stagger = atoi(sg) != 0;
   c->ev.resize(24);
   for (auto& ev : c->ev) GG_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : c->ticket_ev) GG_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
   const char* impl = getenv("GG_GEMM_IMPL");
   c->gemm_impl = 1;
   if (impl && !strcmp(impl, "simt")) c->gemm_impl = 0;
@@ -270,6 +271,7 @@ void gg_destroy(gg_handle h) {
   if (h->d_status) cudaFree(h->d_status);
   if (h->d_lin) cudaFree(h->d_lin);
   for (auto& ev : h->ev) cudaEventDestroy(ev);
+  for (auto& ev : h->ticket_ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->prof_pool) cudaEventDestroy(ev);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_run) cudaStreamDestroy(h->s_run);
@@ -388,32 +390,44 @@ int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* la
 }
 
 // Host buffers in, host trimaps out.  The batch is cut into chunks; chunk i+1 is copied in
-// (stream s_in) and chunk i-1 copied out (s_out) while chunk i runs (s_run).  Up to three
-// chunk slots (inputs + workspace + trimaps) rotate, so the copy-in stream never waits for
-// the compute of the chunk it is about to overwrite.
-int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H, int W,
-                        const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
-                        int32_t* n_edges_host) {
-  GG_REQUIRE(h && bgr_host && labels_host && cfg && trimap_host, "gg_trimap_path_host: null argument");
-  GG_REQUIRE(B > 0 && H >= 2 && W >= 2, "gg_trimap_path_host: bad shape");
+// (stream s_in) and chunk i-1 copied out (s_out) while chunk i runs (s_run / s_sub[3],
+// alternating, so that the latency-bound kernels of two chunks overlap).  Three chunk slots
+// (inputs + workspace + trimaps) rotate, across calls as well: a submitted call only enqueues
+// work, so the copy-in of call n+1 overlaps the kernels of call n and the host<->device link
+// stays busy (one call alone pays the fill and drain of the pipeline).
+int gg_trimap_path_host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H,
+                               int W, const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
+                               int32_t* n_edges_host, int* ticket) {
+  GG_REQUIRE(h && bgr_host && labels_host && cfg && trimap_host && ticket, "gg_trimap_path_host_submit: null argument");
+  GG_REQUIRE(B > 0 && H >= 2 && W >= 2, "gg_trimap_path_host_submit: bad shape");
   GG_CUDA_OK(cudaSetDevice(h->device));
-  if (!h->net.loaded) { set_error("gg_trimap_path_host: call gg_load_weights first"); return GG_ERR_STATE; }
+  if (!h->net.loaded) { set_error("gg_trimap_path_host_submit: call gg_load_weights first"); return GG_ERR_STATE; }
+  if (h->tickets_open >= gg_context::MAX_TICKETS) {
+    set_error("gg_trimap_path_host_submit: %d calls already in flight; wait for one first", gg_context::MAX_TICKETS);
+    return GG_ERR_STATE;
+  }
   const size_t npx = (size_t)H * W;
   int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)((68u << 20) / (npx * 7) + 1)));
   chunk = std::min(chunk, B);
   const int n_chunks = (B + chunk - 1) / chunk;
-  const int n_slots = std::min(n_chunks, 3);
+  const int n_slots = 3;
   const size_t in_bytes = Arena::padded((size_t)chunk * npx * 3, 1) + Arena::padded((size_t)chunk * npx, 4) +
                           Arena::padded((size_t)chunk * npx, 1);
   const size_t slot_bytes = in_bytes + path_workspace_bytes(h, chunk, H, W, *cfg) + 4096;
-  GG_TRY(h->host_arena.reserve(slot_bytes * n_slots));
+  if (slot_bytes != h->slot_bytes) {
+    // a different chunk geometry: let the calls in flight finish, then lay the slots out anew
+    GG_CUDA_OK(cudaDeviceSynchronize());
+    GG_TRY(h->host_arena.reserve(slot_bytes * n_slots));
+    h->slot_bytes = slot_bytes;
+    for (bool& u : h->slot_used) u = false;
+  }
   char* base = h->host_arena.base;
   cudaEvent_t* ev_in = &h->ev[0];     // [3] input of slot s landed
   cudaEvent_t* ev_run = &h->ev[3];    // [3] compute of slot s done
   cudaEvent_t* ev_out = &h->ev[6];    // [3] output of slot s copied out
-  GG_CUDA_OK(cudaMemsetAsync(h->d_status + 1, 0, sizeof(int), h->s_run));
   for (int ci = 0; ci < n_chunks; ++ci) {
-    const int s = ci % n_slots;
+    const long long seq = h->chunk_seq++;
+    const int s = (int)(seq % n_slots), par = (int)(seq & 1);
     const int b0 = ci * chunk, nb = std::min(chunk, B - b0);
     Arena ar;
     ar.base = base + (size_t)s * slot_bytes;
@@ -422,38 +436,64 @@ int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* lab
     int32_t* d_lab = ar.take<int32_t>((size_t)chunk * npx);
     uint8_t* d_tri = ar.take<uint8_t>((size_t)chunk * npx);
     // the slot is free again once its previous trimaps have been copied out
-    if (ci >= n_slots) GG_CUDA_OK(cudaStreamWaitEvent(h->s_in, ev_out[s], 0));
+    if (h->slot_used[s]) GG_CUDA_OK(cudaStreamWaitEvent(h->s_in, ev_out[s], 0));
+    h->slot_used[s] = true;
     GG_CUDA_OK(cudaMemcpyAsync(d_bgr, bgr_host + (size_t)b0 * npx * 3, (size_t)nb * npx * 3, cudaMemcpyHostToDevice, h->s_in));
     GG_CUDA_OK(cudaMemcpyAsync(d_lab, labels_host + (size_t)b0 * npx, (size_t)nb * npx * 4, cudaMemcpyHostToDevice, h->s_in));
     GG_CUDA_OK(cudaEventRecord(ev_in[s], h->s_in));
-    // consecutive chunks alternate between two compute streams, so that the (latency-bound)
-    // kernels of two chunks overlap on the device
-    cudaStream_t rs = (ci & 1) ? h->s_sub[3] : h->s_run;
+    cudaStream_t rs = par ? h->s_sub[3] : h->s_run;
     GG_CUDA_OK(cudaStreamWaitEvent(rs, ev_in[s], 0));
-    h->status_word = h->d_status + 2 + (ci & 1);
+    h->status_word = h->d_status + 2 + par;
     int st = run_path(h, ar, d_bgr, d_lab, nb, H, W, *cfg, d_tri, nullptr, nullptr,
                       n_nodes_host ? n_nodes_host + b0 : nullptr, n_edges_host ? n_edges_host + b0 : nullptr,
                       rs);
     h->status_word = h->d_status;
     if (st != GG_OK) { cudaDeviceSynchronize(); return st; }
     // accumulate the per-chunk device status into the sticky word
-    GG_LAUNCH(h, k_status_or, 1, 1, 0, rs, h->d_status + 2 + (ci & 1), h->d_status + 1);
+    GG_LAUNCH(h, k_status_or, 1, 1, 0, rs, h->d_status + 2 + par, h->d_status + 1);
     GG_CUDA_OK(cudaEventRecord(ev_run[s], rs));
     GG_CUDA_OK(cudaStreamWaitEvent(h->s_out, ev_run[s], 0));
     GG_CUDA_OK(cudaMemcpyAsync(trimap_host + (size_t)b0 * npx, d_tri, (size_t)nb * npx, cudaMemcpyDeviceToHost, h->s_out));
     GG_CUDA_OK(cudaEventRecord(ev_out[s], h->s_out));
   }
-  GG_CUDA_OK(cudaStreamSynchronize(h->s_run));
-  GG_CUDA_OK(cudaStreamSynchronize(h->s_sub[3]));
-  GG_CUDA_OK(cudaStreamSynchronize(h->s_out));
+  // s_out has waited for the compute of every chunk of this call, in order
+  int t = 0;
+  while (h->ticket_open[t]) ++t;
+  GG_CUDA_OK(cudaEventRecord(h->ticket_ev[t], h->s_out));
+  h->ticket_open[t] = true;
+  h->tickets_open++;
+  *ticket = t;
+  return GG_OK;
+}
+
+// Blocks until the call that returned `ticket` has delivered its trimaps.  The device status
+// is sticky over the calls in flight: a capacity error is reported by the first wait after it.
+int gg_trimap_path_host_wait(gg_handle h, int ticket) {
+  GG_REQUIRE(h && ticket >= 0 && ticket < gg_context::MAX_TICKETS && h->ticket_open[ticket],
+             "gg_trimap_path_host_wait: unknown ticket");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  h->ticket_open[ticket] = false;
+  h->tickets_open--;
+  GG_CUDA_OK(cudaEventSynchronize(h->ticket_ev[ticket]));
+  int dev_bits = 0;
+  GG_CUDA_OK(cudaMemcpyAsync(&dev_bits, h->d_status + 1, sizeof(int), cudaMemcpyDeviceToHost, h->s_in));
   GG_CUDA_OK(cudaStreamSynchronize(h->s_in));
-  int bits = 0;
-  GG_CUDA_OK(cudaMemcpy(&bits, h->d_status + 1, sizeof(int), cudaMemcpyDeviceToHost));
-  if (bits) {
-    set_error("gg_trimap_path_host: device status 0x%x (label >= node_cap or pair capacity exceeded)", bits);
+  if (dev_bits) {
+    GG_CUDA_OK(cudaDeviceSynchronize());
+    GG_CUDA_OK(cudaMemset(h->d_status + 1, 0, sizeof(int)));
+    set_error("gg_trimap_path_host: device status 0x%x (label >= node_cap or pair capacity exceeded)", dev_bits);
     return GG_ERR_CAPACITY;
   }
   return GG_OK;
+}
+
+int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H, int W,
+                        const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
+                        int32_t* n_edges_host) {
+  int ticket = -1;
+  GG_TRY(gg_trimap_path_host_submit(h, bgr_host, labels_host, B, H, W, cfg, trimap_host, n_nodes_host,
+                                    n_edges_host, &ticket));
+  return gg_trimap_path_host_wait(h, ticket);
 }
 
 int64_t gg_kernel_launch_count(gg_handle h) { return h ? h->launches : 0; }

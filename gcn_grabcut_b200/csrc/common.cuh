@@ -108,6 +108,14 @@ struct gg_context {
   int n_sub = 2;
   bool stagger = false;
   std::vector<cudaEvent_t> ev;
+  // gg_trimap_path_host_submit / _wait: chunk slots rotate across calls
+  static constexpr int MAX_TICKETS = 8;
+  cudaEvent_t ticket_ev[MAX_TICKETS] = {};
+  bool ticket_open[MAX_TICKETS] = {};
+  int tickets_open = 0;
+  long long chunk_seq = 0;
+  size_t slot_bytes = 0;
+  bool slot_used[3] = {false, false, false};
   // per-kernel CUDA-event timing (gg_profile_enable / gg_profile_report)
   bool prof_on = false;
   struct ProfRec { const char* name; cudaEvent_t e0, e1; };

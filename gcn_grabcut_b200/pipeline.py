@@ -111,6 +111,17 @@ class TrimapPath:
     def __call__(self, images, labels, out: Optional[np.ndarray] = None,
                  return_counts: bool = False):
         """Host buffers (numpy or pinned torch CPU tensors) in, host trimaps out; copies included."""
+        return self.submit(images, labels, out, return_counts).result()
+
+    def submit(self, images, labels, out=None, return_counts: bool = False) -> "PendingTrimaps":
+        """
+        Asynchronous ``__call__`` for streaming many batches: enqueues the copies and kernels of
+        this batch (``gg_trimap_path_host_submit``) and returns at once; ``.result()`` of the
+        returned object blocks until the trimaps are in the host buffer.  With two or three
+        batches in flight the copy-in of the next batch overlaps the kernels of the current one.
+        The input and output buffers must not be modified until ``.result()`` returns (pinned
+        buffers are needed for the copies to overlap).
+        """
         import torch
         self._ensure_weights()
         img = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
@@ -126,14 +137,13 @@ class TrimapPath:
         tri_t = tri if torch.is_tensor(tri) else torch.from_numpy(tri)
         nn_ = torch.empty(B, dtype=torch.int32) if return_counts else None
         ne_ = torch.empty(B, dtype=torch.int32) if return_counts else None
+        img, lab = img.contiguous(), lab.contiguous()
+        ticket = C.c_int(-1)
         with torch.cuda.device(self.dev):
-            nat.check(nat.lib().gg_trimap_path_host(self.h.ptr, nat.ptr(img.contiguous()), nat.ptr(lab.contiguous()),
-                                                    B, H, W, C.byref(self.pc), nat.ptr(tri_t), nat.ptr(nn_),
-                                                    nat.ptr(ne_)))
-        res = tri_t.numpy() if not torch.is_tensor(out) else tri_t
-        if return_counts:
-            return res, nn_.numpy(), ne_.numpy()
-        return res
+            nat.check(nat.lib().gg_trimap_path_host_submit(self.h.ptr, nat.ptr(img), nat.ptr(lab), B, H, W,
+                                                           C.byref(self.pc), nat.ptr(tri_t), nat.ptr(nn_),
+                                                           nat.ptr(ne_), C.byref(ticket)))
+        return PendingTrimaps(self, ticket.value, (img, lab), tri_t, torch.is_tensor(out), nn_, ne_)
 
     def run_device(self, images_t, labels_t, trimap_t=None, probs_t=None, node_off_t=None):
         """CUDA tensors in, CUDA trimaps out, on the current stream, no host synchronisation."""
@@ -152,6 +162,35 @@ class TrimapPath:
     def shard(self, n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
         """Contiguous block [lo, hi) of a batch of ``n_items`` images owned by ``rank``."""
         return shard_range(n_items, rank, world_size)
+
+
+class PendingTrimaps:
+    """A batch submitted with ``TrimapPath.submit``; ``result()`` waits for it (once)."""
+
+    def __init__(self, path: TrimapPath, ticket: int, keep, tri_t, as_tensor: bool, nn_, ne_):
+        self._path, self._ticket, self._keep = path, ticket, keep
+        self._tri, self._as_tensor, self._nn, self._ne = tri_t, as_tensor, nn_, ne_
+        self._done = False
+
+    def result(self):
+        if not self._done:
+            import torch
+            with torch.cuda.device(self._path.dev):
+                self._done = True
+                nat.check(nat.lib().gg_trimap_path_host_wait(self._path.h.ptr, self._ticket))
+            self._keep = None
+        res = self._tri if self._as_tensor else self._tri.numpy()
+        if self._nn is not None:
+            return res, self._nn.numpy(), self._ne.numpy()
+        return res
+
+    def __del__(self):
+        # an abandoned submission still has to release its ticket (and the buffers it writes to)
+        if not self._done:
+            try:
+                self.result()
+            except Exception:
+                pass
 
 
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:

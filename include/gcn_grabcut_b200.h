@@ -224,6 +224,19 @@ int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* lab
                         int H, int W, const gg_path_config* cfg, uint8_t* trimap_host /*[B,H,W]*/,
                         int32_t* n_nodes_host /*optional [B]*/, int32_t* n_edges_host /*optional [B]*/);
 
+/* Asynchronous form of the same call, for streaming: _submit enqueues the copies and kernels
+ * of one batch and returns a ticket at once; _wait blocks until that batch's trimaps (and
+ * counts) are in the host buffers, which must stay valid (and should be pinned) until then.
+ * Up to 8 calls may be in flight; the chunk slots rotate across calls, so the copy-in of
+ * batch n+1 overlaps the kernels of batch n.  gg_trimap_path_host == _submit + _wait.
+ * The device status is sticky over the calls in flight: _wait reports GG_ERR_CAPACITY if any
+ * batch submitted so far overflowed. */
+int gg_trimap_path_host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host,
+                               int B, int H, int W, const gg_path_config* cfg,
+                               uint8_t* trimap_host, int32_t* n_nodes_host,
+                               int32_t* n_edges_host, int* ticket);
+int gg_trimap_path_host_wait(gg_handle h, int ticket);
+
 /* Same path with inputs and outputs resident on the device (caller's stream, no host sync). */
 int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, int B,
                           int H, int W, const gg_path_config* cfg, uint8_t* trimap_dev,

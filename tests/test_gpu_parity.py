@@ -400,3 +400,43 @@ def test_config_e_4k_invariants(gg):
     path = gg.TrimapPath(state, cfg, node_cap=n)
     tri = path(imgs, labs)
     assert tri.shape == (1, H, W) and set(np.unique(tri)).issubset({0, 1, 2, 3})
+
+
+def test_trimap_path_streaming_submit_result(gg):
+    """submit/result with several batches in flight (chunk slots rotate across calls) gives the
+    same trimaps and counts as one synchronous call per batch; a capacity overflow in any batch in
+    flight is reported by a wait and the handle stays usable."""
+    import gcn_grabcut_b200._native as nat
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import model_port
+    H, W = 120, 168
+    batches = [make_batch(b, H, W, 60, seed0=70 + 10 * i) for i, b in enumerate((7, 3, 9, 1, 6))]
+    node_cap = max(int(l.max()) for _, l in batches) + 1
+    state = model_port.random_state_dict(64, 2, seed=2)
+    path = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=node_cap, chunk=2)
+    want = [path(i, l, return_counts=True) for i, l in batches]
+    pins = [(torch.from_numpy(i).pin_memory(), torch.from_numpy(l).pin_memory()) for i, l in batches]
+    for rep in range(2):
+        pending = [path.submit(i, l, return_counts=True) for i, l in pins]
+        got = [p.result() for p in reversed(pending)][::-1]        # waits may come in any order
+        for (t0, n0, e0), (t1, n1, e1) in zip(want, got):
+            assert np.array_equal(t0, t1) and np.array_equal(n0, n1) and np.array_equal(e0, e1)
+    # more than 8 calls in flight are refused, not queued
+    pending = [path.submit(*pins[3]) for _ in range(8)]
+    with pytest.raises(nat.NativeError):
+        path.submit(*pins[3])
+    for p in pending:
+        assert np.array_equal(p.result(), want[3][0])
+    # overflow: a label >= node_cap
+    bad = batches[1][1].copy()
+    bad[0, 0, 0] = node_cap + 5
+    p_ok, p_bad = path.submit(*pins[0]), path.submit(batches[1][0], bad)
+    with pytest.raises(nat.NativeError):
+        p_ok.result()
+        p_bad.result()
+    for p in (p_ok, p_bad):
+        try:
+            p.result()
+        except nat.NativeError:
+            pass
+    assert np.array_equal(path(*batches[2]), want[2][0])
