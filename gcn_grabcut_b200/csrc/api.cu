@@ -395,11 +395,11 @@ int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* la
 // (inputs + workspace + trimaps) rotate, across calls as well: a submitted call only enqueues
 // work, so the copy-in of call n+1 overlaps the kernels of call n and the host<->device link
 // stays busy (one call alone pays the fill and drain of the pipeline).
-int gg_trimap_path_host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H,
-                               int W, const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
-                               int32_t* n_edges_host, int* ticket) {
-  GG_REQUIRE(h && bgr_host && labels_host && cfg && trimap_host && ticket, "gg_trimap_path_host_submit: null argument");
-  GG_REQUIRE(B > 0 && H >= 2 && W >= 2, "gg_trimap_path_host_submit: bad shape");
+static int host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H,
+                       int W, const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
+                       int32_t* n_edges_host, int* ticket, size_t chunk_input_bytes) {
+  GG_REQUIRE(h && bgr_host && labels_host && cfg && trimap_host && ticket, "gg_trimap_path_host: null argument");
+  GG_REQUIRE(B > 0 && H >= 2 && W >= 2, "gg_trimap_path_host: bad shape");
   GG_CUDA_OK(cudaSetDevice(h->device));
   if (!h->net.loaded) { set_error("gg_trimap_path_host_submit: call gg_load_weights first"); return GG_ERR_STATE; }
   if (h->tickets_open >= gg_context::MAX_TICKETS) {
@@ -407,7 +407,7 @@ int gg_trimap_path_host_submit(gg_handle h, const uint8_t* bgr_host, const int32
     return GG_ERR_STATE;
   }
   const size_t npx = (size_t)H * W;
-  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)((68u << 20) / (npx * 7) + 1)));
+  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)(chunk_input_bytes / (npx * 7) + 1)));
   chunk = std::min(chunk, B);
   const int n_chunks = (B + chunk - 1) / chunk;
   const int n_slots = 3;
@@ -487,12 +487,22 @@ int gg_trimap_path_host_wait(gg_handle h, int ticket) {
   return GG_OK;
 }
 
+// Default chunk sizes (cfg->chunk == 0), measured on B200 at 320x480: a streamed call keeps the
+// pipeline full across calls and prefers large chunks (kernel efficiency: ~128 images, 138 MB of
+// input); a single synchronous call pays the fill and drain itself and prefers ~64 images.
+int gg_trimap_path_host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H,
+                               int W, const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
+                               int32_t* n_edges_host, int* ticket) {
+  return host_submit(h, bgr_host, labels_host, B, H, W, cfg, trimap_host, n_nodes_host, n_edges_host, ticket,
+                     (size_t)137 << 20);
+}
+
 int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H, int W,
                         const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
                         int32_t* n_edges_host) {
   int ticket = -1;
-  GG_TRY(gg_trimap_path_host_submit(h, bgr_host, labels_host, B, H, W, cfg, trimap_host, n_nodes_host,
-                                    n_edges_host, &ticket));
+  GG_TRY(host_submit(h, bgr_host, labels_host, B, H, W, cfg, trimap_host, n_nodes_host, n_edges_host, &ticket,
+                     (size_t)68 << 20));
   return gg_trimap_path_host_wait(h, ticket);
 }
 

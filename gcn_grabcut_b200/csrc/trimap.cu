@@ -11,14 +11,17 @@
 //
 // Two column-walker kernels: (1) means of {g, g^2, s_c, g s_c} -> a_c, b_c planes;
 //                            (2) means of {a_c, b_c} -> q_c = mean(a_c) g + mean(b_c) -> clip -> labels.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "pixel_math.cuh"
 #include "trimap.cuh"
 
 namespace gg {
 
-constexpr int GF_NT = 128;          // threads per block = halo columns per block
-constexpr int GF_SY = 64;           // output rows per block (strip height)
+constexpr int GF_MAX_STRIP = 160;   // output rows per block (strip height), runtime <= this
 constexpr int GF_MAX_RADIUS = 24;
 constexpr int GF_PROB_TABLE = 1024;  // labels whose (p_bg, p_fg) are staged in shared memory
 
@@ -38,7 +41,7 @@ struct GuidedParams {
   uint8_t* trimap;
   float* q0;                // optional filtered planes (p_bg / out)
   float* q1;                // optional (p_fg)
-  int H, W, radius;
+  int H, W, radius, strip;
   float eps, thr_fg, thr_bg;
 };
 
@@ -51,75 +54,62 @@ struct GfTraits {
 
 // Column walker.  Thread t owns halo column x0 - r + t of a strip and walks down its rows with
 // float64 vertical running sums of all NP planes in registers (add row y+r, subtract row
-// y-r-1; old rows are re-read through L1/L2).  Per row the sums go to a small shared row
-// buffer and (plane, segment) tasks slide the horizontal window over it; segment lengths are
-// odd so that the 64-bit reads of a warp hit distinct banks.  Means = float32(sum * 1/k^2),
-// exactly cv2.blur's float32 path.  RT > 0: radius known at compile time (loops unrolled);
-// RT == 0: runtime radius.
-template <int NP>
+// y-r-1; old rows are re-read through L1/L2; the reflected row offsets of the strip come from a
+// small shared table).  Per row the sums go to a shared row buffer and (plane, segment) tasks
+// slide the horizontal window over it; segment lengths are odd so that the 64-bit reads of a
+// warp hit distinct banks.  Means = float32(sum * 1/k^2), exactly cv2.blur's float32 path.
+// RT > 0: radius known at compile time (loops unrolled); RT == 0: runtime radius.
+// NT = threads per block = halo columns per block (128 or 256, whichever wastes fewer columns).
+template <int NP, int NT>
 struct HorizontalPlan {
   int seglen, nseg, tx;
   int off, len;          // this thread's task: elements [off, off+len) of plane-major row buffers
   __device__ HorizontalPlan(int radius) {
-    tx = GF_NT - 2 * radius;
-    const int per = GF_NT / NP;
+    tx = NT - 2 * radius;
+    const int per = NT / NP;
     seglen = ((tx + per - 1) / per) | 1;
     nseg = (tx + seglen - 1) / seglen;
     const int t = threadIdx.x;
     const int pl = t / nseg, seg = t - pl * nseg;
     const int o0 = seg * seglen;
-    off = pl * GF_NT + o0;
+    off = pl * NT + o0;
     len = (t < NP * nseg) ? min(seglen, tx - o0) : 0;
   }
 };
 
-constexpr int GF_RB = 1;   // rows reduced per barrier interval (2 costs occupancy: measured slower on B200)
-
-template <int NP, int RT>
-GG_D void horizontal_means(const double* sV, float* sM, const HorizontalPlan<NP>& hp, int radius,
+template <int NP, int NT, int RT>
+GG_D void horizontal_means(const double* sV, float* sM, const HorizontalPlan<NP, NT>& hp, int radius,
                            double scale) {
-  // sV / sM: [GF_RB][NP][GF_NT]; one task = one (plane, segment) for all GF_RB rows
+  // sV / sM: [NP][NT]; one task = one (plane, segment)
   if (hp.len > 0) {
     const int len = hp.len;
     const double* in = sV + hp.off;
     float* out = sM + hp.off;
-    constexpr int RS = NP * GF_NT;       // row stride
     if (RT > 0) {
       constexpr int K = 2 * RT + 1;
-      constexpr int PER = GF_NT / NP;
-      constexpr int SEG = (((GF_NT - 2 * RT) + PER - 1) / PER) | 1;      // == hp.seglen
-      double s[GF_RB];
+      constexpr int PER = NT / NP;
+      constexpr int SEG = (((NT - 2 * RT) + PER - 1) / PER) | 1;      // == hp.seglen
+      double s = 0.0;
 #pragma unroll
-      for (int j = 0; j < GF_RB; ++j) s[j] = 0.0;
-#pragma unroll
-      for (int d = 0; d < K; ++d)
-#pragma unroll
-        for (int j = 0; j < GF_RB; ++j) s[j] += in[j * RS + d];
-#pragma unroll
-      for (int j = 0; j < GF_RB; ++j) out[j * RS] = (float)(s[j] * scale);
+      for (int d = 0; d < K; ++d) s += in[d];
+      out[0] = (float)(s * scale);
 #pragma unroll
       for (int i = 1; i < SEG; ++i) {
         if (i < len) {
-#pragma unroll
-          for (int j = 0; j < GF_RB; ++j) {
-            s[j] += in[j * RS + i + K - 1];
-            s[j] -= in[j * RS + i - 1];
-            out[j * RS + i] = (float)(s[j] * scale);
-          }
+          s += in[i + K - 1];
+          s -= in[i - 1];
+          out[i] = (float)(s * scale);
         }
       }
     } else {
       const int k = 2 * radius + 1;
-#pragma unroll
-      for (int j = 0; j < GF_RB; ++j) {
-        double s = 0.0;
-        for (int d = 0; d < k; ++d) s += in[j * RS + d];
-        out[j * RS] = (float)(s * scale);
-        for (int i = 1; i < len; ++i) {
-          s += in[j * RS + i + k - 1];
-          s -= in[j * RS + i - 1];
-          out[j * RS + i] = (float)(s * scale);
-        }
+      double s = 0.0;
+      for (int d = 0; d < k; ++d) s += in[d];
+      out[0] = (float)(s * scale);
+      for (int i = 1; i < len; ++i) {
+        s += in[i + k - 1];
+        s -= in[i - 1];
+        out[i] = (float)(s * scale);
       }
     }
   }
@@ -132,20 +122,34 @@ GG_D int reflect_row(int y, int n) {
   return (y < 0 || y >= n) ? reflect101(y, n) : y;
 }
 
-template <bool kTrimap, int RT>
-__global__ void __launch_bounds__(GF_NT)
+// element offsets (row * W) of rows y_begin - r - 1 .. y_end + r - 1 of the strip, reflected
+GG_D void fill_row_table(int* sRow, int y_begin, int y_end, int r, int H, int W) {
+  const int n = (y_end - y_begin) + 2 * r + 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sRow[i] = reflect_row(y_begin - r - 1 + i, H) * W;
+}
+
+// float32 division whose zero numerators (very common: cov == 0 wherever the posterior is constant
+// over the window) do not take the slow path of __fdiv_rn; the sign of a zero is kept.
+GG_D float fdiv_zero_guard(float num, float den) {
+  const float q = __fdiv_rn(num == 0.0f ? den : num, den);
+  return num == 0.0f ? num : q;
+}
+
+template <bool kTrimap, int RT, int NT>
+__global__ void __launch_bounds__(NT)
 k_guided_ab(const GuidedParams p) {
   using T = GfTraits<kTrimap>;
   constexpr int NP = T::NPLANE1;
   constexpr int NS = T::NSRC;
-  __shared__ double sV[GF_RB * NP * GF_NT];
-  __shared__ float sM[GF_RB * NP * GF_NT];
-  __shared__ float sLut[256];
+  __shared__ double sV[NP * NT];
+  __shared__ float sM[NP * NT];
+  __shared__ int sRow[GF_MAX_STRIP + 2 * GF_MAX_RADIUS + 2];
+  __shared__ float sLut[kTrimap ? 256 : 1];
   __shared__ float2 sProb[kTrimap ? GF_PROB_TABLE : 1];     // (p_bg, p_fg) per label, if it fits
   const int r = RT > 0 ? RT : p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
-  const HorizontalPlan<NP> hp(r);
+  const HorizontalPlan<NP, NT> hp(r);
   const int x0 = blockIdx.x * hp.tx;
-  const int y_begin = blockIdx.y * GF_SY, y_end = min(H, y_begin + GF_SY);
+  const int y_begin = blockIdx.y * p.strip, y_end = min(H, y_begin + p.strip);
   const int xs = reflect101(x0 - r + t, W);
   const double scale = 1.0 / ((double)(2 * r + 1) * (double)(2 * r + 1));
   const size_t img_off = (size_t)b * H * W;
@@ -156,146 +160,141 @@ k_guided_ab(const GuidedParams p) {
   const float* scol = kTrimap ? nullptr : p.src + img_off + xs;
   const float* prob0 = nullptr;
   int nn = 0;
+  fill_row_table(sRow, y_begin, y_end, r, H, W);
   if (kTrimap) {
     const int64_t no = p.node_off[b];
     nn = (int)(p.node_off[b + 1] - no);
     prob0 = p.probs + (size_t)no * 3;
-    for (int i = t; i < 256; i += GF_NT) sLut[i] = __fdiv_rn((float)i, 255.0f);   // guide = gray/255
+    for (int i = t; i < 256; i += NT) sLut[i] = __fdiv_rn((float)i, 255.0f);   // guide = gray/255
     if (nn <= GF_PROB_TABLE)
-      for (int i = t; i < nn; i += GF_NT) sProb[i] = make_float2(prob0[(size_t)i * 3], prob0[(size_t)i * 3 + 2]);
-    __syncthreads();
+      for (int i = t; i < nn; i += NT) sProb[i] = make_float2(prob0[(size_t)i * 3], prob0[(size_t)i * 3 + 2]);
   }
+  __syncthreads();
   const bool prob_in_smem = kTrimap && nn <= GF_PROB_TABLE;
+  const int* rowtab = sRow + (r + 1) - y_begin;     // rowtab[yy] for yy in [y_begin-r-1, y_end+r)
+
   // base planes of one pixel of this thread's column: g and the NSRC source planes
-  auto fetch = [&](int yy, float& g, float (&sv)[NS]) {
-    const size_t ro = (size_t)reflect_row(yy, H) * W;
+  struct Px { float g, sv[NS]; };
+  auto fetch = [&](int yy, Px& px) {
+    const int ro = rowtab[yy];
     if (kTrimap) {
       const int gr = gcol[ro];
       const int l = lcol[ro];
-      g = sLut[gr];
-      sv[0] = 0.0f;
-      sv[NS - 1] = 0.0f;                            // project_to_pixels zero padding
+      px.g = sLut[gr];
+      px.sv[0] = 0.0f;
+      px.sv[NS - 1] = 0.0f;                            // project_to_pixels zero padding
       if (l >= 0 && l < nn) {
         if (prob_in_smem) {
           const float2 pr = sProb[l];
-          sv[0] = pr.x;
-          sv[NS - 1] = pr.y;
+          px.sv[0] = pr.x;
+          px.sv[NS - 1] = pr.y;
         } else {
           const float* row = prob0 + (size_t)l * 3;
-          sv[0] = row[0];
-          sv[NS - 1] = row[2];
+          px.sv[0] = row[0];
+          px.sv[NS - 1] = row[2];
         }
       }
     } else {
-      g = ucol[ro];
-      sv[0] = scol[ro];
+      px.g = ucol[ro];
+      px.sv[0] = scol[ro];
     }
   };
   double vs[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) vs[q] = 0.0;
-  auto add = [&](float g, const float (&sv)[NS]) {
-    vs[0] += (double)g;
-    vs[1] += (double)__fmul_rn(g, g);
+  auto add = [&](const Px& px) {
+    vs[0] += (double)px.g;
+    vs[1] += (double)__fmul_rn(px.g, px.g);
 #pragma unroll
     for (int c = 0; c < NS; ++c) {
-      vs[2 + 2 * c] += (double)sv[c];
-      vs[3 + 2 * c] += (double)__fmul_rn(g, sv[c]);
+      vs[2 + 2 * c] += (double)px.sv[c];
+      vs[3 + 2 * c] += (double)__fmul_rn(px.g, px.sv[c]);
     }
   };
-  auto sub = [&](float g, const float (&sv)[NS]) {
-    vs[0] -= (double)g;
-    vs[1] -= (double)__fmul_rn(g, g);
+  auto sub = [&](const Px& px) {
+    vs[0] -= (double)px.g;
+    vs[1] -= (double)__fmul_rn(px.g, px.g);
 #pragma unroll
     for (int c = 0; c < NS; ++c) {
-      vs[2 + 2 * c] -= (double)sv[c];
-      vs[3 + 2 * c] -= (double)__fmul_rn(g, sv[c]);
+      vs[2 + 2 * c] -= (double)px.sv[c];
+      vs[3 + 2 * c] -= (double)__fmul_rn(px.g, px.sv[c]);
     }
   };
   for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
-    float g, sv[NS];
-    fetch(yy, g, sv);
-    add(g, sv);
+    Px px;
+    fetch(yy, px);
+    add(px);
   }
-  // software pipeline: the rows entering / leaving the windows of the NEXT batch of GF_RB rows
-  // are in flight while the current batch is reduced
-  struct Batch { float gn[GF_RB], go[GF_RB], svn[GF_RB][NS], svo[GF_RB][NS]; };
-  auto load_batch = [&](int y0, Batch& bt) {
+  // software pipeline: the rows entering / leaving the window of the NEXT row are in flight
+  // while the current row is reduced
+  Px cn, co, nn_, no_;
+  co.g = 0.f; nn_.g = 0.f; no_.g = 0.f;
 #pragma unroll
-    for (int j = 0; j < GF_RB; ++j) {
-      bt.gn[j] = bt.go[j] = 0.f;
-#pragma unroll
-      for (int c = 0; c < NS; ++c) bt.svn[j][c] = bt.svo[j][c] = 0.f;
-      if (y0 + j < y_end) {
-        fetch(y0 + j + r, bt.gn[j], bt.svn[j]);
-        if (y0 + j > y_begin) fetch(y0 + j - r - 1, bt.go[j], bt.svo[j]);
-      }
+  for (int c = 0; c < NS; ++c) co.sv[c] = nn_.sv[c] = no_.sv[c] = 0.f;
+  fetch(y_begin + r, cn);
+  for (int y = y_begin; y < y_end; ++y) {
+    if (y + 1 < y_end) {
+      fetch(y + 1 + r, nn_);
+      fetch(y - r, no_);
     }
-  };
-  Batch cur, nxt;
-  load_batch(y_begin, cur);
-  for (int y = y_begin; y < y_end; y += GF_RB) {
-    if (y + GF_RB < y_end) load_batch(y + GF_RB, nxt);
+    add(cn);
+    if (y > y_begin) sub(co);
 #pragma unroll
-    for (int j = 0; j < GF_RB; ++j) {
-      if (y + j < y_end) {
-        add(cur.gn[j], cur.svn[j]);
-        if (y + j > y_begin) sub(cur.go[j], cur.svo[j]);
-      }
-#pragma unroll
-      for (int q = 0; q < NP; ++q) sV[(j * NP + q) * GF_NT + t] = vs[q];
-    }
+    for (int q = 0; q < NP; ++q) sV[q * NT + t] = vs[q];
     __syncthreads();
-    horizontal_means<NP, RT>(sV, sM, hp, r, scale);
+    horizontal_means<NP, NT, RT>(sV, sM, hp, r, scale);
     __syncthreads();
     const int o = t - r, x = x0 + o;
     if (o >= 0 && o < hp.tx && x < W) {
+      const float* m = sM + o;
+      const float mg = m[0], mgg = m[NT];
+      const float var = __fsub_rn(mgg, __fmul_rn(mg, mg));
+      const float den = __fadd_rn(var, p.eps);
+      const size_t op = img_off + (size_t)y * W + x;
 #pragma unroll
-      for (int j = 0; j < GF_RB; ++j) {
-        if (y + j < y_end) {
-          const float* m = sM + j * NP * GF_NT + o;
-          const float mg = m[0], mgg = m[GF_NT];
-          const float var = __fsub_rn(mgg, __fmul_rn(mg, mg));
-          const float den = __fadd_rn(var, p.eps);
-          const size_t op = img_off + (size_t)(y + j) * W + x;
-#pragma unroll
-          for (int c = 0; c < NS; ++c) {
-            const float ms = m[(2 + 2 * c) * GF_NT], mgs = m[(3 + 2 * c) * GF_NT];
-            const float cov = __fsub_rn(mgs, __fmul_rn(mg, ms));
-            const float a = __fdiv_rn(cov, den);
-            const float bb = __fsub_rn(ms, __fmul_rn(a, mg));
-            p.ab[(size_t)(2 * c) * p.plane_stride + op] = a;
-            p.ab[(size_t)(2 * c + 1) * p.plane_stride + op] = bb;
-          }
-        }
+      for (int c = 0; c < NS; ++c) {
+        const float ms = m[(2 + 2 * c) * NT], mgs = m[(3 + 2 * c) * NT];
+        const float cov = __fsub_rn(mgs, __fmul_rn(mg, ms));
+        const float a = fdiv_zero_guard(cov, den);
+        const float bb = __fsub_rn(ms, __fmul_rn(a, mg));
+        p.ab[(size_t)(2 * c) * p.plane_stride + op] = a;
+        p.ab[(size_t)(2 * c + 1) * p.plane_stride + op] = bb;
       }
     }
-    cur = nxt;
+    cn = nn_;
+    co = no_;
   }
 }
 
-template <bool kTrimap, int RT>
-__global__ void __launch_bounds__(GF_NT)
+template <bool kTrimap, int RT, int NT>
+__global__ void __launch_bounds__(NT)
 k_guided_out(const GuidedParams p) {
   using T = GfTraits<kTrimap>;
   constexpr int NP = T::NPLANE2;
-  __shared__ double sV[GF_RB * NP * GF_NT];
-  __shared__ float sM[GF_RB * NP * GF_NT];
+  __shared__ double sV[NP * NT];
+  __shared__ float sM[NP * NT];
+  __shared__ int sRow[GF_MAX_STRIP + 2 * GF_MAX_RADIUS + 2];
+  __shared__ float sLut[kTrimap ? 256 : 1];
   const int r = RT > 0 ? RT : p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
-  const HorizontalPlan<NP> hp(r);
+  const HorizontalPlan<NP, NT> hp(r);
   const int x0 = blockIdx.x * hp.tx;
-  const int y_begin = blockIdx.y * GF_SY, y_end = min(H, y_begin + GF_SY);
+  const int y_begin = blockIdx.y * p.strip, y_end = min(H, y_begin + p.strip);
   const int xs = reflect101(x0 - r + t, W);
   const size_t img_off = (size_t)b * H * W;
   const double scale = 1.0 / ((double)(2 * r + 1) * (double)(2 * r + 1));
   const float* col = p.ab + img_off + xs;
+  fill_row_table(sRow, y_begin, y_end, r, H, W);
+  if (kTrimap)
+    for (int i = t; i < 256; i += NT) sLut[i] = __fdiv_rn((float)i, 255.0f);
+  __syncthreads();
+  const int* rowtab = sRow + (r + 1) - y_begin;
   double vs[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) vs[q] = 0.0;
   auto load_row = [&](int yy, float (&v)[NP]) {
-    const size_t ro = (size_t)reflect_row(yy, H) * W;
+    const float* rp = col + rowtab[yy];
 #pragma unroll
-    for (int q = 0; q < NP; ++q) v[q] = __ldg(col + (size_t)q * p.plane_stride + ro);
+    for (int q = 0; q < NP; ++q) v[q] = __ldg(rp + (size_t)q * p.plane_stride);
   };
   for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
     float v[NP];
@@ -303,81 +302,99 @@ k_guided_out(const GuidedParams p) {
 #pragma unroll
     for (int q = 0; q < NP; ++q) vs[q] += (double)v[q];
   }
-  struct Batch { float vn[GF_RB][NP], vo[GF_RB][NP]; };
-  auto load_batch = [&](int y0, Batch& bt) {
+  float cn[NP], co[NP], nn_[NP], no_[NP];
 #pragma unroll
-    for (int j = 0; j < GF_RB; ++j) {
-#pragma unroll
-      for (int q = 0; q < NP; ++q) bt.vn[j][q] = bt.vo[j][q] = 0.f;
-      if (y0 + j < y_end) {
-        load_row(y0 + j + r, bt.vn[j]);
-        if (y0 + j > y_begin) load_row(y0 + j - r - 1, bt.vo[j]);
-      }
+  for (int q = 0; q < NP; ++q) co[q] = nn_[q] = no_[q] = 0.f;
+  load_row(y_begin + r, cn);
+  for (int y = y_begin; y < y_end; ++y) {
+    if (y + 1 < y_end) {
+      load_row(y + 1 + r, nn_);
+      load_row(y - r, no_);
     }
-  };
-  Batch cur, nxt;
-  load_batch(y_begin, cur);
-  for (int y = y_begin; y < y_end; y += GF_RB) {
-    if (y + GF_RB < y_end) load_batch(y + GF_RB, nxt);
 #pragma unroll
-    for (int j = 0; j < GF_RB; ++j) {
-      if (y + j < y_end) {
+    for (int q = 0; q < NP; ++q) vs[q] += (double)cn[q];
+    if (y > y_begin) {
 #pragma unroll
-        for (int q = 0; q < NP; ++q) vs[q] += (double)cur.vn[j][q];
-        if (y + j > y_begin) {
-#pragma unroll
-          for (int q = 0; q < NP; ++q) vs[q] -= (double)cur.vo[j][q];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < NP; ++q) sV[(j * NP + q) * GF_NT + t] = vs[q];
+      for (int q = 0; q < NP; ++q) vs[q] -= (double)co[q];
     }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) sV[q * NT + t] = vs[q];
     __syncthreads();
-    horizontal_means<NP, RT>(sV, sM, hp, r, scale);
+    horizontal_means<NP, NT, RT>(sV, sM, hp, r, scale);
     __syncthreads();
     const int o = t - r, x = x0 + o;
     if (o >= 0 && o < hp.tx && x < W) {
+      const float* m = sM + o;
+      const size_t op = img_off + (size_t)y * W + x;
+      const float g = kTrimap ? sLut[p.gray[op]] : p.guide[op];
+      float q[T::NSRC];
 #pragma unroll
-      for (int j = 0; j < GF_RB; ++j) {
-        if (y + j < y_end) {
-          const float* m = sM + j * NP * GF_NT + o;
-          const size_t op = img_off + (size_t)(y + j) * W + x;
-          const float g = kTrimap ? __fdiv_rn((float)p.gray[op], 255.0f) : p.guide[op];
-          float q[T::NSRC];
-#pragma unroll
-          for (int c = 0; c < T::NSRC; ++c)
-            q[c] = __fadd_rn(__fmul_rn(m[(2 * c) * GF_NT], g), m[(2 * c + 1) * GF_NT]);
-          if (kTrimap) {
-            const float pbg = fminf(fmaxf(q[0], 0.0f), 1.0f);          // np.clip(., 0, 1)
-            const float pfg = fminf(fmaxf(q[T::NSRC - 1], 0.0f), 1.0f);
-            uint8_t tv = (pfg > pbg) ? 3 : 2;                          // pipeline.py:143-145
-            if (pbg >= p.thr_bg) tv = 0;
-            if (pfg >= p.thr_fg) tv = 1;
-            p.trimap[op] = tv;
-            if (p.q0) p.q0[op] = pbg;
-            if (p.q1) p.q1[op] = pfg;
-          } else {
-            p.q0[op] = q[0];
-          }
-        }
+      for (int c = 0; c < T::NSRC; ++c)
+        q[c] = __fadd_rn(__fmul_rn(m[(2 * c) * NT], g), m[(2 * c + 1) * NT]);
+      if (kTrimap) {
+        const float pbg = fminf(fmaxf(q[0], 0.0f), 1.0f);          // np.clip(., 0, 1)
+        const float pfg = fminf(fmaxf(q[T::NSRC - 1], 0.0f), 1.0f);
+        uint8_t tv = (pfg > pbg) ? 3 : 2;                          // pipeline.py:143-145
+        if (pbg >= p.thr_bg) tv = 0;
+        if (pfg >= p.thr_fg) tv = 1;
+        p.trimap[op] = tv;
+        if (p.q0) p.q0[op] = pbg;
+        if (p.q1) p.q1[op] = pfg;
+      } else {
+        p.q0[op] = q[0];
       }
     }
-    cur = nxt;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) { cn[q] = nn_[q]; co[q] = no_[q]; }
   }
 }
 
+// Block width: 128 or 256 halo columns, whichever covers W with fewer wasted columns; strip
+// height: the image is cut into equal strips of at most GF_MAX_STRIP rows.
+static int gf_block_width(int W, int radius) {
+  const long long w128 = (long long)ceil_div(W, 128 - 2 * radius) * 128;
+  const long long w256 = (long long)ceil_div(W, 256 - 2 * radius) * 256;
+  return w256 <= w128 ? 256 : 128;
+}
+static int gf_strip(int H) {
+  static int forced = getenv("GG_GF_STRIP") ? atoi(getenv("GG_GF_STRIP")) : 0;
+  const int target = forced > 0 ? std::min(forced, GF_MAX_STRIP) : 64;
+  const int n = ceil_div(H, target);
+  return std::min(GF_MAX_STRIP, ceil_div(H, n));
+}
+
+template <bool kTrimap, int NT>
+static int launch_guided_ab(gg_context* ctx, GuidedParams p, int B, cudaStream_t st) {
+  p.strip = gf_strip(p.H);
+  dim3 grid(ceil_div(p.W, NT - 2 * p.radius), ceil_div(p.H, p.strip), B);
+  if (p.radius == 8) GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 8, NT>), grid, NT, 0, st, p);
+  else if (p.radius == 4) GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 4, NT>), grid, NT, 0, st, p);
+  else GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 0, NT>), grid, NT, 0, st, p);
+  return GG_OK;
+}
+
+template <bool kTrimap, int NT>
+static int launch_guided_out(gg_context* ctx, GuidedParams p, int B, cudaStream_t st) {
+  p.strip = gf_strip(p.H);
+  dim3 grid(ceil_div(p.W, NT - 2 * p.radius), ceil_div(p.H, p.strip), B);
+  if (p.radius == 8) GG_LAUNCH(ctx, (k_guided_out<kTrimap, 8, NT>), grid, NT, 0, st, p);
+  else if (p.radius == 4) GG_LAUNCH(ctx, (k_guided_out<kTrimap, 4, NT>), grid, NT, 0, st, p);
+  else GG_LAUNCH(ctx, (k_guided_out<kTrimap, 0, NT>), grid, NT, 0, st, p);
+  return GG_OK;
+}
+
+// Measured on B200 (320x480, r=8): stage 1 (6 planes, more registers and shared memory per
+// thread) is fastest with 128-column blocks, stage 2 (4 planes) with 256-column blocks.
 template <bool kTrimap>
-static int launch_guided(gg_context* ctx, const GuidedParams& p, dim3 grid, cudaStream_t st) {
-  if (p.radius == 8) {
-    GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 8>), grid, GF_NT, 0, st, p);
-    GG_LAUNCH(ctx, (k_guided_out<kTrimap, 8>), grid, GF_NT, 0, st, p);
-  } else if (p.radius == 4) {
-    GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 4>), grid, GF_NT, 0, st, p);
-    GG_LAUNCH(ctx, (k_guided_out<kTrimap, 4>), grid, GF_NT, 0, st, p);
-  } else {
-    GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 0>), grid, GF_NT, 0, st, p);
-    GG_LAUNCH(ctx, (k_guided_out<kTrimap, 0>), grid, GF_NT, 0, st, p);
-  }
+static int launch_guided(gg_context* ctx, const GuidedParams& p, int B, cudaStream_t st) {
+  static int f_ab = getenv("GG_GF_NT_AB") ? atoi(getenv("GG_GF_NT_AB")) : 0;
+  static int f_out = getenv("GG_GF_NT_OUT") ? atoi(getenv("GG_GF_NT_OUT")) : 0;
+  const int nt_ab = f_ab == 256 ? 256 : 128;
+  const int nt_out = (f_out == 128 || f_out == 256) ? f_out : gf_block_width(p.W, p.radius);
+  if (nt_ab == 256) GG_TRY((launch_guided_ab<kTrimap, 256>(ctx, p, B, st)));
+  else GG_TRY((launch_guided_ab<kTrimap, 128>(ctx, p, B, st)));
+  if (nt_out == 256) GG_TRY((launch_guided_out<kTrimap, 256>(ctx, p, B, st)));
+  else GG_TRY((launch_guided_out<kTrimap, 128>(ctx, p, B, st)));
   return GG_OK;
 }
 
@@ -436,8 +453,7 @@ int refine_trimap(gg_context* ctx, Arena& ar, const uint8_t* bgr, const uint8_t*
   p.gray = gray; p.labels = labels; p.probs = probs; p.node_off = node_off;
   p.ab = ab; p.plane_stride = npx; p.trimap = trimap; p.q0 = p_bg; p.q1 = p_fg;
   p.H = H; p.W = W; p.radius = radius; p.eps = eps; p.thr_fg = thr_fg; p.thr_bg = thr_bg;
-  dim3 grid(ceil_div(W, GF_NT - 2 * radius), ceil_div(H, GF_SY), B);
-  GG_TRY(launch_guided<true>(ctx, p, grid, st));
+  GG_TRY(launch_guided<true>(ctx, p, B, st));
   return GG_OK;
 }
 
@@ -451,8 +467,7 @@ int guided_filter_plane(gg_context* ctx, Arena& ar, const float* guide, const fl
   GuidedParams p{};
   p.guide = guide; p.src = src; p.ab = ab; p.plane_stride = npx; p.q0 = out;
   p.H = H; p.W = W; p.radius = radius; p.eps = eps;
-  dim3 grid(ceil_div(W, GF_NT - 2 * radius), ceil_div(H, GF_SY), 1);
-  GG_TRY(launch_guided<false>(ctx, p, grid, st));
+  GG_TRY(launch_guided<false>(ctx, p, 1, st));
   return GG_OK;
 }
 

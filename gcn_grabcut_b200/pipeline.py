@@ -110,10 +110,11 @@ class TrimapPath:
 
     def __call__(self, images, labels, out: Optional[np.ndarray] = None,
                  return_counts: bool = False):
-        """Host buffers (numpy or pinned torch CPU tensors) in, host trimaps out; copies included."""
-        return self.submit(images, labels, out, return_counts).result()
+        """Host buffers (numpy or pinned torch CPU tensors) in, host trimaps out; copies included
+        (``gg_trimap_path_host``: synchronous, one batch at a time)."""
+        return self.submit(images, labels, out, return_counts, _sync=True).result()
 
-    def submit(self, images, labels, out=None, return_counts: bool = False) -> "PendingTrimaps":
+    def submit(self, images, labels, out=None, return_counts: bool = False, _sync: bool = False) -> "PendingTrimaps":
         """
         Asynchronous ``__call__`` for streaming many batches: enqueues the copies and kernels of
         this batch (``gg_trimap_path_host_submit``) and returns at once; ``.result()`` of the
@@ -140,6 +141,10 @@ class TrimapPath:
         img, lab = img.contiguous(), lab.contiguous()
         ticket = C.c_int(-1)
         with torch.cuda.device(self.dev):
+            if _sync:
+                nat.check(nat.lib().gg_trimap_path_host(self.h.ptr, nat.ptr(img), nat.ptr(lab), B, H, W,
+                                                        C.byref(self.pc), nat.ptr(tri_t), nat.ptr(nn_), nat.ptr(ne_)))
+                return PendingTrimaps(self, -1, None, tri_t, torch.is_tensor(out), nn_, ne_)
             nat.check(nat.lib().gg_trimap_path_host_submit(self.h.ptr, nat.ptr(img), nat.ptr(lab), B, H, W,
                                                            C.byref(self.pc), nat.ptr(tri_t), nat.ptr(nn_),
                                                            nat.ptr(ne_), C.byref(ticket)))
@@ -170,7 +175,7 @@ class PendingTrimaps:
     def __init__(self, path: TrimapPath, ticket: int, keep, tri_t, as_tensor: bool, nn_, ne_):
         self._path, self._ticket, self._keep = path, ticket, keep
         self._tri, self._as_tensor, self._nn, self._ne = tri_t, as_tensor, nn_, ne_
-        self._done = False
+        self._done = ticket < 0
 
     def result(self):
         if not self._done:
