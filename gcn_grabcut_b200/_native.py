@@ -94,7 +94,7 @@ EXPORTED_SYMBOLS = (
     "gg_coo_to_csr", "gg_resgcn_forward", "gg_refine_trimap", "gg_project_trimap",
     "gg_guided_filter", "gg_trimap_path_host", "gg_trimap_path_host_submit", "gg_trimap_path_host_wait",
     "gg_trimap_path_device", "gg_kernel_launch_count",
-    "gg_profile_enable", "gg_profile_report")
+    "gg_profile_enable", "gg_profile_report", "gg_selftest_math")
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -145,6 +145,7 @@ def lib() -> C.CDLL:
             L.gg_trimap_path_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                 C.c_int, C.POINTER(PathConfig), C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]
+            L.gg_selftest_math.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
             L.gg_profile_enable.argtypes = [C.c_void_p, C.c_int]
             L.gg_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
             _lib = L

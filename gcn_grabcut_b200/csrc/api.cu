@@ -506,6 +506,16 @@ int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* lab
   return gg_trimap_path_host_wait(h, ticket);
 }
 
+int gg_selftest_math(gg_handle h, int64_t* mismatches) {
+  GG_REQUIRE(h && mismatches, "gg_selftest_math: null");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_TRY(h->arena.reserve(4096));
+  long long m[4] = {0, 0, 0, 0};
+  GG_TRY(selftest_math(h, h->arena, m, nullptr));
+  for (int i = 0; i < 4; ++i) mismatches[i] = m[i];
+  return GG_OK;
+}
+
 int64_t gg_kernel_launch_count(gg_handle h) { return h ? h->launches : 0; }
 
 int gg_profile_enable(gg_handle h, int enable) {

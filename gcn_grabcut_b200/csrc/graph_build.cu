@@ -62,6 +62,8 @@ k_gray_gradmax(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray,
 // tab[0..H)      double(float(y)/float(H))   graph_builder.py:207  (float32 coordinates)
 // tab[H..2H)     double(y)/double(H)         graph_builder.py:401  (float64 coordinates)
 // tab[2H..2H+W)  double(float(x)/float(W));  tab[2H+W..2H+2W)  double(x)/double(W)
+// tab[2H+2W ..)  exclusive prefix sums of the two y tables, H+1 entries each: the sum of y/H over
+//                a vertical run [y0, y1) is P[y1] - P[y0]
 __global__ void k_coord_tables(double* __restrict__ tab, int H, int W) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < H) {
@@ -72,27 +74,41 @@ __global__ void k_coord_tables(double* __restrict__ tab, int H, int W) {
     tab[2 * H + i] = (double)__fdiv_rn((float)i, (float)W);
     tab[2 * H + W + i] = (double)i / (double)W;
   }
+  if (i < 2) {     // two threads, one sequential prefix each (H <= 4096 additions)
+    double* P = tab + 2 * (H + W) + i * (H + 1);
+    double s = 0.0;
+    for (int y = 0; y < H; ++y) {
+      P[y] = s;
+      s += i == 0 ? (double)__fdiv_rn((float)y, (float)H) : (double)y / (double)H;
+    }
+    P[H] = s;
+  }
 }
 
 // ============================================================================ K1
-// One warp walks down a strip of 32 columns x RS_ROWS rows, lane = column.  Each lane
-// keeps fp64 register accumulators for the vertical run of its current label and hands
-// them to a per-warp shared-memory table when the label changes (plain read-modify-write,
-// no atomics: 64-bit shared atomics are CAS loops on sm_100).  Table slots go to the global
-// per-region accumulators with one RED.F64 per field when evicted / at the end of the strip.
+// One warp walks down a strip of 32 columns x `rows` rows, lane = column.  Each lane keeps fp64
+// register accumulators for the vertical run of its current label and hands them to a per-warp
+// shared-memory table when the label changes (plain read-modify-write, no atomics: 64-bit
+// shared atomics are CAS loops on sm_100).  Table slots go to the global per-region
+// accumulators with one RED.F64 per field when evicted / at the end of the strip.
 //
 // Per-region fields (RS_NF doubles): 0-2 sum Lab, 3-5 sum Lab^2, 6-8 sum HSV, 9 sum y/H (f32
 // coords), 10 sum x/W (f32 coords), 11 sum |grad|, 12 sum |grad|/(max+1e-6), 13 sum y/H
 // (f64 coords), 14 sum x/W (f64 coords), 15 pixel count, 16 boundary pixels, 17 frame pixels
-// (the three counters are integers, exact in float64).
-constexpr int RS_ROWS = 64;
+// (the three counters are integers, exact in float64).  Fields that are functions of the run
+// geometry alone (9, 10, 13, 14, 15, 17) are produced when a run is handed over, not per pixel.
+//
+// Everything the pixel loop needs from the neighbouring columns comes from warp shuffles; the two
+// edge lanes fetch their outer neighbour one row ahead with one predicated load.  Out-of-image
+// neighbours are replaced by the pixel's own label, so that "differs from a neighbour" needs no
+// bounds tests.  Labels are only range-checked where they are used as an index (run hand-over,
+// pair emission).
 constexpr int RS_WARPS = 8;
 constexpr int RS_SLOTS = 16;
 constexpr int RS_NF = 18;
 constexpr int RS_STAGE_LD = 19;  // doubles per lane in the staging area (odd: conflict-free)
 constexpr size_t RS_SMEM_BYTES =
-    (256 + RS_WARPS * RS_SLOTS * RS_NF + RS_WARPS * 32 * RS_STAGE_LD + RS_WARPS * 32) * sizeof(double) +
-    (256 + RS_WARPS * RS_SLOTS + RS_WARPS * 32) * sizeof(int);
+    (256 + 256 + RS_WARPS * RS_SLOTS * RS_NF + RS_WARPS * 32 * RS_STAGE_LD) * sizeof(double);
 
 struct RegionStatsParams {
   const uint8_t* bgr;
@@ -107,7 +123,7 @@ struct RegionStatsParams {
   int* pair_cnts;                 // [B][table_cap]
   int* status;
   int B, H, W, node_cap, table_cap, connectivity;
-  int n_sx, n_sy;
+  int n_sx, n_sy, rows;
   LabMatrix lab;
 };
 
@@ -117,10 +133,10 @@ GG_D uint32_t pair_hash(uint32_t lo, uint32_t hi) {
   return h;
 }
 
-// Insert / increment an undirected pair in the per-image open-addressing table.
-__device__ __noinline__ void pair_emit(unsigned long long* keys, int* cnts, int cap, int a, int b,
+// Insert / increment an undirected pair (lo < hi) in the per-image open-addressing table.
+__device__ __noinline__ void pair_emit(unsigned long long* keys, int* cnts, int cap, int lo_, int hi_,
                                        int count, int* status) {
-  const uint32_t lo = (uint32_t)min(a, b), hi = (uint32_t)max(a, b);
+  const uint32_t lo = (uint32_t)lo_, hi = (uint32_t)hi_;
   const unsigned long long key = ((unsigned long long)lo << 32) | hi;
   const unsigned long long EMPTY = ~0ull;
   uint32_t h = pair_hash(lo, hi) & (uint32_t)(cap - 1);
@@ -136,44 +152,23 @@ __device__ __noinline__ void pair_emit(unsigned long long* keys, int* cnts, int 
   atomicOr(status, ST_PAIR_TABLE);
 }
 
-// float32 division that never takes the slow (subnormal / zero) path of __fdiv_rn: callers
-// pass num >= 0, den > 0, both normal; a zero numerator is substituted and selected away.
-GG_D float fdiv_pos(float num, float den) {
-  const float q = __fdiv_rn(num == 0.0f ? 1.0f : num, den);
-  return num == 0.0f ? 0.0f : q;
-}
-
-GG_D int reflect_row1(int y, int n) {       // BORDER_REFLECT_101 for y in [-1, n]
-  return y < 0 ? (n > 1 ? 1 : 0) : (y >= n ? (n > 1 ? n - 2 : 0) : y);
-}
-
 template <int MINB>
 __global__ void __launch_bounds__(RS_WARPS * 32, MINB)
 k_region_stats(const RegionStatsParams p) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
-  double* s_lin = reinterpret_cast<double*>(rs_smem);                       // [256]
-  double* s_vals_all = s_lin + 256;                                         // [W][SLOTS][NF]
+  double* s_lin = reinterpret_cast<double*>(rs_smem);                       // [256] sRGB -> linear
+  double* s_vd = s_lin + 256;                                               // [256] (double)float(v/255)
+  double* s_vals_all = s_vd + 256;                                          // [W][SLOTS][NF]
   double* s_stage_all = s_vals_all + RS_WARPS * RS_SLOTS * RS_NF;           // [W][32*LD]
-  unsigned long long* s_pkey_all =
-      reinterpret_cast<unsigned long long*>(s_stage_all + RS_WARPS * 32 * RS_STAGE_LD);  // [W][32]
-  float* s_vlut = reinterpret_cast<float*>(s_pkey_all + RS_WARPS * 32);                  // [256]
-  int* s_tags_all = reinterpret_cast<int*>(s_vlut + 256);                                // [W][SLOTS]
-  int* s_pcnt_all = s_tags_all + RS_WARPS * RS_SLOTS;                                    // [W][32]
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double* vals = s_vals_all + wid * RS_SLOTS * RS_NF;
   double* stage = s_stage_all + wid * 32 * RS_STAGE_LD;
-  int* tags = s_tags_all + wid * RS_SLOTS;
-  unsigned long long* pkey = s_pkey_all + wid * 32;   // per-warp cache of label pairs (lane = slot)
-  int* pcnt = s_pcnt_all + wid * 32;
-  pkey[lane] = ~0ull;
-  pcnt[lane] = 0;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     s_lin[i] = p.lin_lut[i];
-    s_vlut[i] = __fdiv_rn((float)i, 255.0f);          // HSV value channel: max/255
+    s_vd[i] = (double)__fdiv_rn((float)i, 255.0f);          // HSV value channel: max/255
   }
   for (int i = lane; i < RS_SLOTS * RS_NF; i += 32) vals[i] = 0.0;
-  if (lane < RS_SLOTS) tags[lane] = -1;
   __syncthreads();
 
   const long long task = (long long)blockIdx.x * RS_WARPS + wid;
@@ -186,7 +181,7 @@ k_region_stats(const RegionStatsParams p) {
   const int x = sx * 32 + lane;
   const bool valid = x < W;
   const int xc = valid ? x : W - 1;
-  const int y_begin = sy * RS_ROWS, y_end = min(H, y_begin + RS_ROWS);
+  const int y_begin = sy * p.rows, y_end = min(H, y_begin + p.rows);
 
   const uint8_t* img = p.bgr + (size_t)b * H * W * 3;
   const uint8_t* gry = p.gray + (size_t)b * H * W;
@@ -194,40 +189,59 @@ k_region_stats(const RegionStatsParams p) {
   double* acc_g = p.acc + (size_t)b * p.node_cap * RS_NF;
   unsigned long long* keys = p.pair_keys + (size_t)b * p.table_cap;
   int* cnts = p.pair_cnts + (size_t)b * p.table_cap;
+  const unsigned node_cap = (unsigned)p.node_cap;
 
-  const int xl = reflect101(xc - 1, W), xr = reflect101(xc + 1, W);
+  // loop-invariant lane roles
+  const bool is_l0 = lane == 0, is_l31 = lane == 31;
+  const bool own_r = x >= W - 1;                       // no pixel to the right
+  const bool edge_lane = (is_l0 || is_l31) && valid;
+  // outer neighbour of the edge lanes: labels -> own pixel when outside, grey -> REFLECT_101
+  const int ldelta = is_l0 ? (x > 0 ? -1 : 0) : (x + 1 < W ? 1 : 0);
+  const int gdelta = is_l0 ? (x > 0 ? -1 : (W > 1 ? 1 : 0)) : (x + 1 < W ? 1 : (W > 1 ? -1 : 0));
   const double xtf = p.coord[2 * H + xc], xtd = p.coord[2 * H + W + xc];
+  const double* PF = p.coord + 2 * (H + W);            // prefix of y/H, float32 coordinates
+  const double* PD = PF + (H + 1);                     // prefix of y/H, float64 coordinates
   const int gm = p.gradmax_sq[b];
   const float gden = __fadd_rn(__fsqrt_rn((float)gm), 1e-6f);  // grad.max() + 1e-6 (float32)
+  const float grcp = __frcp_rn(gden);
   const int frame_x = (x == 0) + (x == W - 1);
-  const bool has_l = valid && x > 0, has_r = valid && x + 1 < W;
 
-  // horizontal Sobel partials of a grey row: hs = g[x-1]+2g[x]+g[x+1], hd = g[x+1]-g[x-1]
-  auto row_partials = [&](int yy, int& hs, int& hd) {
-    const uint8_t* r = gry + (size_t)reflect_row1(yy, H) * W;
-    const int gl = r[xl], gc = r[xc], gr = r[xr];
+  // ---- grey rows y_begin-1 and y_begin: horizontal Sobel partials
+  //      hs = g[x-1] + 2 g[x] + g[x+1], hd = g[x+1] - g[x-1]
+  auto grey_row = [&](int off, int& hs, int& hd) {
+    const int gc = gry[off];
+    int ge = 0;
+    if (edge_lane) ge = gry[off + gdelta];
+    int gl = __shfl_up_sync(0xffffffffu, gc, 1);
+    int gr = __shfl_down_sync(0xffffffffu, gc, 1);
+    if (is_l0) gl = ge;
+    if (is_l31) gr = ge;
+    if (own_r) gr = gl;                                // REFLECT_101 at the last column
+    if (W == 1) gl = gr = gc;
     hs = gl + 2 * gc + gr;
     hd = gr - gl;
   };
-
-  int hs_m, hd_m, hs_c, hd_c, hs_p, hd_p;
-  row_partials(y_begin - 1, hs_m, hd_m);
-  row_partials(y_begin, hs_c, hd_c);
-  const int32_t* lrow = lab + (size_t)y_begin * W + xc;      // label row pointer at (y, x)
-  const uint8_t* prow = img + ((size_t)y_begin * W + xc) * 3;
-  int lab_up = (valid && y_begin > 0) ? lrow[-W] : -1;
-  int lab_c = valid ? lrow[0] : -1;
+  int off = y_begin * W + xc;                          // pixel offset of (y, xc) in the image
+  int hs_m, hd_m, hs_c, hd_c;
+  grey_row((y_begin > 0 ? y_begin - 1 : (H > 1 ? 1 : 0)) * W + xc, hs_m, hd_m);
+  grey_row(off, hs_c, hd_c);
+  int lab_c = valid ? lab[off] : -1;
+  int lab_up = (valid && y_begin > 0) ? lab[off - W] : lab_c;
+  int e_lab = edge_lane ? lab[off + ldelta] : 0;       // outer label neighbour of the edge lanes
+  int pb = img[3 * off], pg = img[3 * off + 1], pr = img[3 * off + 2];
 
   // per-lane run accumulators
-  int cur = -1, cnt = 0, bnd = 0, brd = 0;
-  double aL = 0, aA = 0, aB = 0, aL2 = 0, aA2 = 0, aB2 = 0, aH = 0, aS = 0, aV = 0;
-  double aYf = 0, aG = 0, aGs = 0, aYd = 0;
-  // vertical-boundary pair run (right neighbour)
+  int cur = -1, cnt = 0, bnd = 0, ys = y_begin;
+  double aL = 0, aA = 0, aB = 0, aL2 = 0, aA2 = 0, aB2 = 0, aH = 0, aS = 0, aV = 0, aG = 0, aGs = 0;
+  // run of identical right-neighbour transitions (a | b) down the column
   int rp_a = -1, rp_b = -1, rp_cnt = 0;
+  // region table tags (lane s < RS_SLOTS owns the tag of slot s) and the label-pair cache
+  // (lane = slot): registers, looked up with shuffles / ballots
+  int mytag = -1;
+  int pk_lo = -1, pk_hi = -1, pk_n = 0, victim = 0;
   int lmax = -1;
 
-  auto evict_slot = [&](int slot) {  // warp-uniform
-    const int tag = tags[slot];
+  auto evict_slot = [&](int slot, int tag) {  // warp-uniform arguments
     if (tag >= 0 && lane < RS_NF) {
       const double v = vals[slot * RS_NF + lane];
       if (v != 0.0) atomicAdd(acc_g + (size_t)tag * RS_NF + lane, v);
@@ -235,197 +249,179 @@ k_region_stats(const RegionStatsParams p) {
     }
   };
 
-  auto flush_lanes = [&](unsigned mask) {  // warp-uniform mask of lanes whose run ends
+  // one undirected pair (a, b, n), warp-uniform: bump the cached slot or take a slot over
+  auto pair_add = [&](int a, int b_, int n) {
+    const int lo = min(a, b_), hi = max(a, b_);
+    if (lo == hi || (unsigned)lo >= node_cap || (unsigned)hi >= node_cap) return;
+    const unsigned hit = __ballot_sync(0xffffffffu, pk_lo == lo && pk_hi == hi);
+    if (hit) {
+      if (lane == __ffs(hit) - 1) pk_n += n;
+      return;
+    }
+    const unsigned empty = __ballot_sync(0xffffffffu, pk_lo < 0);
+    const int slot = empty ? __ffs(empty) - 1 : victim;
+    if (!empty) victim = (victim + 1) & 31;
+    if (lane == slot) {
+      if (pk_lo >= 0) pair_emit(keys, cnts, p.table_cap, pk_lo, pk_hi, pk_n, p.status);
+      pk_lo = lo; pk_hi = hi; pk_n = n;
+    }
+  };
+
+  // hand the finished runs of the lanes in `mask` (warp-uniform) to the warp table; y_now = first
+  // row after the runs; nxt = the label that follows each run (its down-neighbour pair)
+  auto flush_lanes = [&](unsigned mask, int y_now, int nxt) {
     if (mask >> lane & 1u) {
       double* st = stage + lane * RS_STAGE_LD;
+      const double dc = (double)cnt;
       st[0] = aL; st[1] = aA; st[2] = aB; st[3] = aL2; st[4] = aA2; st[5] = aB2;
-      st[6] = aH; st[7] = aS; st[8] = aV; st[9] = aYf; st[10] = (double)cnt * xtf;
-      st[11] = aG; st[12] = aGs; st[13] = aYd; st[14] = (double)cnt * xtd;
-      st[15] = (double)cnt; st[16] = (double)bnd; st[17] = (double)brd;
-      cnt = bnd = brd = 0;
-      aL = aA = aB = aL2 = aA2 = aB2 = aH = aS = aV = aYf = aG = aGs = aYd = 0.0;
+      st[6] = aH; st[7] = aS; st[8] = aV;
+      st[9] = PF[y_now] - PF[ys]; st[10] = dc * xtf;
+      st[11] = aG; st[12] = aGs;
+      st[13] = PD[y_now] - PD[ys]; st[14] = dc * xtd;
+      st[15] = dc; st[16] = (double)bnd;
+      st[17] = (double)(cnt * frame_x + (ys == 0) + (y_now == H));   // corners count twice
+      cnt = bnd = 0;
+      aL = aA = aB = aL2 = aA2 = aB2 = aH = aS = aV = aG = aGs = 0.0;
+      lmax = max(lmax, cur);
     }
-    const int myslot = (int)(((uint32_t)cur * 0x9E3779B1u) >> 28) & (RS_SLOTS - 1);
     __syncwarp();
     unsigned m = mask;
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
       const int L = __shfl_sync(0xffffffffu, cur, src);
-      const int slot = __shfl_sync(0xffffffffu, myslot, src);
-      if (tags[slot] != L) {
-        evict_slot(slot);
-        __syncwarp();
-        if (lane == 0) tags[slot] = L;
-        __syncwarp();
+      const int Ln = __shfl_sync(0xffffffffu, nxt, src);
+      if ((unsigned)L < node_cap) {
+        const int slot = (int)(((uint32_t)L * 0x9E3779B1u) >> 28);
+        const int tag = __shfl_sync(0xffffffffu, mytag, slot);
+        if (tag != L) {
+          evict_slot(slot, tag);
+          if (lane == slot) mytag = L;
+        }
+        // field f is always handled by lane f: no cross-lane hazard between iterations
+        if (lane < RS_NF) vals[slot * RS_NF + lane] += stage[src * RS_STAGE_LD + lane];
+      } else {
+        if (lane == 0) atomicOr(p.status, ST_LABEL_RANGE);
       }
-      // field f is always handled by lane f: no cross-lane hazard between iterations
-      if (lane < RS_NF) vals[slot * RS_NF + lane] += stage[src * RS_STAGE_LD + lane];
+      pair_add(L, Ln, 1);      // vertical transition between the run and the pixel below it
     }
     __syncwarp();
   };
 
-  // Label pairs go through a per-warp shared-memory cache (lane = slot, looked up with one
-  // ballot) so that the global hash table sees one atomic per distinct pair and strip
-  // instead of one per boundary segment.  want: this lane has (a, b, n) to record.
-  int victim = 0;
-  auto pair_add = [&](bool want, int a, int bq, int n) {
-    unsigned em = __ballot_sync(0xffffffffu, want);
-    const unsigned long long mykey =
-        ((unsigned long long)(uint32_t)min(a, bq) << 32) | (uint32_t)max(a, bq);
-    while (em) {
-      const int src = __ffs(em) - 1;
-      em &= em - 1;
-      const unsigned long long key = __shfl_sync(0xffffffffu, mykey, src);
-      const int n_add = __shfl_sync(0xffffffffu, n, src);
-      const unsigned long long mine = pkey[lane];
-      const unsigned hit = __ballot_sync(0xffffffffu, mine == key);
-      if (hit) {
-        if (lane == __ffs(hit) - 1) pcnt[lane] += n_add;
-      } else {
-        const unsigned empty = __ballot_sync(0xffffffffu, mine == ~0ull);
-        const int slot = empty ? __ffs(empty) - 1 : victim;
-        if (!empty) victim = (victim + 1) & 31;
-        if (lane == slot) {
-          if (mine != ~0ull)
-            pair_emit(keys, cnts, p.table_cap, (int)(mine >> 32), (int)(mine & 0xFFFFFFFFull), pcnt[lane], p.status);
-          pkey[lane] = key;
-          pcnt[lane] = n_add;
-        }
-      }
-      __syncwarp();
-    }
-  };
-
-  // BGR of the first row
-  int pb = 0, pg = 0, pr = 0;
-  if (valid) { pb = prow[0]; pg = prow[1]; pr = prow[2]; }
-
   for (int y = y_begin; y < y_end; ++y) {
-    // ---- look ahead: next grey row partials, next label row, next BGR
-    row_partials(y + 1, hs_p, hd_p);
-    const bool has_dn = valid && (y + 1 < H);
-    const int lab_dn = has_dn ? lrow[W] : -1;
-    int nb_ = 0, ng_ = 0, nr_ = 0;
-    if (valid && y + 1 < y_end) {
-      const uint8_t* px = prow + (size_t)W * 3;
-      nb_ = px[0]; ng_ = px[1]; nr_ = px[2];
+    // ---- look ahead one row: grey, labels (incl. the edge lanes' outer neighbours), BGR
+    const bool has_dn = y + 1 < H;
+    const int offn = off + W;
+    const int goff = has_dn ? offn : (H > 1 ? off - W : off);      // REFLECT_101 below the last row
+    const int gcn = gry[goff];
+    int gen = 0, e_lab_n = 0, lab_dn = lab_c;
+    if (edge_lane) gen = gry[goff + gdelta];
+    if (has_dn) {
+      if (valid) lab_dn = lab[offn];
+      if (edge_lane) e_lab_n = lab[offn + ldelta];
     }
-    // ---- horizontal neighbours of the label row
-    int lab_r = __shfl_down_sync(0xffffffffu, lab_c, 1);
-    int lab_l = __shfl_up_sync(0xffffffffu, lab_c, 1);
-    if (lane == 31) lab_r = has_r ? lrow[1] : -1;
-    if (lane == 0) lab_l = has_l ? lrow[-1] : -1;
+    int nb_ = 0, ng_ = 0, nr_ = 0;
+    if (y + 1 < y_end) { nb_ = img[3 * offn]; ng_ = img[3 * offn + 1]; nr_ = img[3 * offn + 2]; }
 
-    const bool in_range = valid && lab_c >= 0 && lab_c < p.node_cap;
-    if (valid && !in_range) atomicOr(p.status, ST_LABEL_RANGE);
+    // ---- horizontal neighbours: labels of this row, grey of the next row
+    int lab_l = __shfl_up_sync(0xffffffffu, lab_c, 1);
+    int lab_r = __shfl_down_sync(0xffffffffu, lab_c, 1);
+    if (is_l0) lab_l = e_lab;
+    if (is_l31) lab_r = e_lab;
+    if (own_r) lab_r = lab_c;
+    int gl = __shfl_up_sync(0xffffffffu, gcn, 1);
+    int gr = __shfl_down_sync(0xffffffffu, gcn, 1);
+    if (is_l0) gl = gen;
+    if (is_l31) gr = gen;
+    if (own_r) gr = gl;
+    if (W == 1) gl = gr = gcn;
+    const int hs_p = gl + 2 * gcn + gr, hd_p = gr - gl;
 
     // ---- run bookkeeping: hand finished runs to the warp table
-    const bool ends = in_range && cnt > 0 && lab_c != cur;
-    const unsigned fm = __ballot_sync(0xffffffffu, ends);
-    if (fm) flush_lanes(fm);
-    if (in_range) {
-      cur = lab_c;
-      lmax = max(lmax, lab_c);
-      // ---- per-pixel quantities
+    const unsigned fm = __ballot_sync(0xffffffffu, cnt > 0 && lab_c != cur);
+    if (fm) flush_lanes(fm, y, lab_c);
+    if (cnt == 0) ys = y;
+    cur = lab_c;
+
+    // ---- per-pixel quantities (all lanes; lanes beyond the image feed a dead run)
+    {
       float L, A, Bv;
-      bgr_to_lab(s_lin, p.lab.m, pb, pg, pr, L, A, Bv);
-      // HSV (see pixel_math.cuh bgr_to_hsv; divisions guarded against the slow path)
+      bgr_to_lab_fast(s_lin, p.lab.m, pb, pg, pr, L, A, Bv);
       const int mx = max(pr, max(pg, pb)), mn = min(pr, min(pg, pb));
-      const int d = mx - mn;
-      const float vv = s_vlut[mx];
-      int hp_;
-      if (pb == mx) hp_ = 4 * d + (pr - pg);
-      else if (pg == mx) hp_ = 2 * d + (pb - pr);
-      else { hp_ = pg - pb; if (hp_ < 0) hp_ += 6 * d; }
-      const float dsafe = d > 0 ? (float)d : 1.0f;
-      const float ss = d > 0 ? __fdiv_rn(dsafe, (float)max(mx, 1)) : 0.0f;
-      const float hh = d > 0 ? fdiv_pos((float)hp_, 6.0f * dsafe) : 0.0f;
+      float hh, ss;
+      hsv_hs_fast(pb, pg, pr, mx, mn, hh, ss);
       const int gx = hd_m + 2 * hd_c + hd_p;
       const int gy = hs_p - hs_m;
-      const float g = __fsqrt_rn((float)(gx * gx + gy * gy));
-      const float gs = fdiv_pos(g, gden);
+      const float g = fsqrt_int((float)(gx * gx + gy * gy));
+      const float gs = fdiv_rcp(g, gden, grcp);
       aL += (double)L; aA += (double)A; aB += (double)Bv;
       aL2 += (double)__fmul_rn(L, L); aA2 += (double)__fmul_rn(A, A); aB2 += (double)__fmul_rn(Bv, Bv);
-      aH += (double)hh; aS += (double)ss; aV += (double)vv;
-      aYf += p.coord[y]; aYd += p.coord[H + y];
+      aH += (double)hh; aS += (double)ss; aV += s_vd[mx];
       aG += (double)g; aGs += (double)gs;
       cnt += 1;
       // find_boundaries(mode="inner"): differs from an in-bounds 4-neighbour and label != 0
-      const bool diff = (lab_up >= 0 && lab_up != lab_c) || (lab_dn >= 0 && lab_dn != lab_c) ||
-                        (lab_l >= 0 && lab_l != lab_c) || (lab_r >= 0 && lab_r != lab_c);
+      const bool diff = (lab_up != lab_c) | (lab_dn != lab_c) | (lab_l != lab_c) | (lab_r != lab_c);
       bnd += (diff && lab_c != 0) ? 1 : 0;
-      brd += (y == 0) + (y == H - 1) + frame_x;   // corners count twice
     }
 
     // ---- adjacency transitions (graph_builder.py:267-281)
-    // right neighbour: aggregated down the column in registers
+    // right neighbour: identical transitions are run-aggregated down the column in registers;
+    // down neighbour: emitted with the run hand-over above.
     {
-      const bool tr = in_range && lab_r >= 0 && lab_r != lab_c && lab_r < p.node_cap;
-      const bool same = tr && lab_c == rp_a && lab_r == rp_b;
-      const bool emit = tr && !same && rp_cnt > 0;
-      if (__any_sync(0xffffffffu, emit)) pair_add(emit, rp_a, rp_b, rp_cnt);
-      if (same) rp_cnt += 1;
-      else if (tr) { rp_a = lab_c; rp_b = lab_r; rp_cnt = 1; }
-    }
-    // down neighbour (and the two diagonals for connectivity 8): aggregated across lanes
-    {
-      const bool t = in_range && lab_dn >= 0 && lab_dn != lab_c && lab_dn < p.node_cap;
-      const unsigned tm = __ballot_sync(0xffffffffu, t);
-      if (tm) {
-        bool lead = false;
-        int n = 0;
-        if (t) {
-          const unsigned long long key =
-              ((unsigned long long)(uint32_t)min(lab_c, lab_dn) << 32) | (uint32_t)max(lab_c, lab_dn);
-          const unsigned grp = __match_any_sync(tm, key);
-          lead = (__ffs(grp) - 1) == lane;
-          n = __popc(grp);
-        }
-        pair_add(lead, lab_c, lab_dn, n);
+      const int cb = (lab_r != lab_c) ? lab_r : -1;
+      const bool changed = (lab_c != rp_a) | (cb != rp_b);
+      unsigned em = __ballot_sync(0xffffffffu, changed && rp_b >= 0 && valid);
+      while (em) {
+        const int src = __ffs(em) - 1;
+        em &= em - 1;
+        pair_add(__shfl_sync(0xffffffffu, rp_a, src), __shfl_sync(0xffffffffu, rp_b, src),
+                 __shfl_sync(0xffffffffu, rp_cnt, src));
       }
+      if (changed) { rp_a = lab_c; rp_b = cb; rp_cnt = 0; }
+      rp_cnt += 1;
     }
     if (p.connectivity == 8) {
+      // the two diagonals below: (y+1, x+1) and (y+1, x-1); outside the image -> own label
       int dn_r = __shfl_down_sync(0xffffffffu, lab_dn, 1);
       int dn_l = __shfl_up_sync(0xffffffffu, lab_dn, 1);
-      if (lane == 31) dn_r = (has_r && has_dn) ? lrow[W + 1] : -1;
-      if (lane == 0) dn_l = (has_l && has_dn) ? lrow[W - 1] : -1;
+      if (is_l31) dn_r = e_lab_n;
+      if (is_l0) dn_l = e_lab_n;
+      if (own_r || !has_dn) dn_r = lab_c;
+      if (x == 0 || !has_dn) dn_l = lab_c;
 #pragma unroll
       for (int sdir = 0; sdir < 2; ++sdir) {
         const int o = sdir ? dn_l : dn_r;
-        const bool t = in_range && o >= 0 && o != lab_c && o < p.node_cap;
-        const unsigned tm = __ballot_sync(0xffffffffu, t);
-        if (tm) {
-          bool lead = false;
-          int n = 0;
-          if (t) {
-            const unsigned long long key =
-                ((unsigned long long)(uint32_t)min(lab_c, o) << 32) | (uint32_t)max(lab_c, o);
-            const unsigned grp = __match_any_sync(tm, key);
-            lead = (__ffs(grp) - 1) == lane;
-            n = __popc(grp);
-          }
-          pair_add(lead, lab_c, o, n);
+        unsigned tm = __ballot_sync(0xffffffffu, valid && o != lab_c);
+        while (tm) {
+          const int src = __ffs(tm) - 1;
+          tm &= tm - 1;
+          pair_add(__shfl_sync(0xffffffffu, lab_c, src), __shfl_sync(0xffffffffu, o, src), 1);
         }
       }
     }
 
     // ---- roll
     hs_m = hs_c; hd_m = hd_c; hs_c = hs_p; hd_c = hd_p;
-    lab_up = lab_c; lab_c = lab_dn;
+    lab_up = lab_c; lab_c = lab_dn; e_lab = e_lab_n;
     pb = nb_; pg = ng_; pr = nr_;
-    lrow += W;
-    prow += (size_t)W * 3;
+    off = offn;
   }
 
-  // ---- end of strip: flush runs, pairs, table, label max
-  const unsigned fm = __ballot_sync(0xffffffffu, cnt > 0);
-  if (fm) flush_lanes(fm);
-  pair_add(rp_cnt > 0, rp_a, rp_b, rp_cnt);
-  __syncwarp();
-  if (pkey[lane] != ~0ull)
-    pair_emit(keys, cnts, p.table_cap, (int)(pkey[lane] >> 32), (int)(pkey[lane] & 0xFFFFFFFFull), pcnt[lane], p.status);
-  for (int s = 0; s < RS_SLOTS; ++s) evict_slot(s);
+  // ---- end of strip: flush runs (lab_c now holds the label below the strip, or the own label
+  //      at the bottom of the image), pending right-neighbour runs, the pair cache, the table
+  const unsigned fm = __ballot_sync(0xffffffffu, cnt > 0 && valid);
+  if (fm) flush_lanes(fm, y_end, lab_c);
+  {
+    unsigned em = __ballot_sync(0xffffffffu, rp_b >= 0 && valid);
+    while (em) {
+      const int src = __ffs(em) - 1;
+      em &= em - 1;
+      pair_add(__shfl_sync(0xffffffffu, rp_a, src), __shfl_sync(0xffffffffu, rp_b, src),
+               __shfl_sync(0xffffffffu, rp_cnt, src));
+    }
+  }
+  if (pk_lo >= 0) pair_emit(keys, cnts, p.table_cap, pk_lo, pk_hi, pk_n, p.status);
+  for (int s_ = 0; s_ < RS_SLOTS; ++s_) evict_slot(s_, __shfl_sync(0xffffffffu, mytag, s_));
   lmax = warp_max_i(lmax);
   if (lane == 0 && lmax >= 0) atomicMax(&p.label_max[b], lmax);
 }
@@ -1083,8 +1079,13 @@ __global__ void k_pixel_planes(const uint8_t* __restrict__ bgr, const double* __
   const uint8_t* px = img + i * 3;
   const size_t o = (size_t)b * H * W + i;
   float L, A, Bv, hh, ss, vv;
-  bgr_to_lab(s_lin, lab.m, px[0], px[1], px[2], L, A, Bv);
-  bgr_to_hsv(px[0], px[1], px[2], hh, ss, vv);
+  // the same fast paths as k_region_stats, so that the all-colours parity test covers them
+  bgr_to_lab_fast(s_lin, lab.m, px[0], px[1], px[2], L, A, Bv);
+  {
+    const int mx = max(px[2], max(px[1], px[0])), mn = min(px[2], min(px[1], px[0]));
+    hsv_hs_fast(px[0], px[1], px[2], mx, mn, hh, ss);
+    vv = __fdiv_rn((float)mx, 255.0f);
+  }
   if (o_lab) { o_lab[o * 3] = L; o_lab[o * 3 + 1] = A; o_lab[o * 3 + 2] = Bv; }
   if (o_hsv) { o_hsv[o * 3] = hh; o_hsv[o * 3 + 1] = ss; o_hsv[o * 3 + 2] = vv; }
   auto G = [&](int yy, int xx) {
@@ -1097,11 +1098,69 @@ __global__ void k_pixel_planes(const uint8_t* __restrict__ bgr, const double* __
                    (G(y - 1, x - 1) + 2 * G(y, x - 1) + G(y + 1, x - 1));
     const int gy = (G(y + 1, x - 1) + 2 * G(y + 1, x) + G(y + 1, x + 1)) -
                    (G(y - 1, x - 1) + 2 * G(y - 1, x) + G(y - 1, x + 1));
-    o_grad[o] = __fsqrt_rn((float)(gx * gx + gy * gy));
+    o_grad[o] = fsqrt_int((float)(gx * gx + gy * gy));
   }
 }
 
+// ============================================================================ self test
+// The float32 fast paths of pixel_math.cuh against the IEEE intrinsics: bad[0] fsqrt_int over all
+// integers < 2^24; bad[1] saturation quotients d/max; bad[2] hue quotients p/(6d) (both exhaustive);
+// bad[3] normalised gradient g/(gmax+1e-6) for every Sobel magnitude and 64 image maxima each.
+__global__ void k_selftest_math(unsigned long long* __restrict__ bad) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;      // grid covers [0, 2^24)
+  unsigned long long b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  {
+    const float a = (float)idx;
+    b0 += fsqrt_int(a) != __fsqrt_rn(a);
+  }
+  if (idx < 256u * 256u) {
+    const int d = idx >> 8, mx = idx & 255;
+    if (mx >= 1 && d <= mx) b1 += fdiv_small((float)d, (float)mx) != __fdiv_rn((float)d, (float)mx);
+  }
+  if (idx < 256u * 1536u) {
+    const int d = idx / 1536, pn = idx - d * 1536;
+    if (d >= 1 && pn < 6 * d) b2 += fdiv_small((float)pn, (float)(6 * d)) != __fdiv_rn((float)pn, (float)(6 * d));
+  }
+  if (idx <= 2080800u) {                                             // 2 * (4 * 255)^2
+    const float g = __fsqrt_rn((float)idx);
+    for (unsigned j = 0; j < 64; ++j) {
+      const unsigned gm = min(idx + j * j * 517u + j, 2080800u);
+      const float gden = __fadd_rn(__fsqrt_rn((float)gm), 1e-6f);
+      if (gden > 0.0f) b3 += fdiv_rcp(g, gden, __frcp_rn(gden)) != __fdiv_rn(g, gden);
+    }
+  }
+  b0 = (unsigned long long)warp_sum((double)b0);
+  b1 = (unsigned long long)warp_sum((double)b1);
+  b2 = (unsigned long long)warp_sum((double)b2);
+  b3 = (unsigned long long)warp_sum((double)b3);
+  if ((threadIdx.x & 31) == 0) {
+    if (b0) atomicAdd(&bad[0], b0);
+    if (b1) atomicAdd(&bad[1], b1);
+    if (b2) atomicAdd(&bad[2], b2);
+    if (b3) atomicAdd(&bad[3], b3);
+  }
+}
+
+int selftest_math(gg_context* ctx, Arena& ar, long long* mismatches, cudaStream_t st) {
+  unsigned long long* bad = ar.take<unsigned long long>(4);
+  GG_CUDA_OK(cudaMemsetAsync(bad, 0, 4 * sizeof(unsigned long long), st));
+  GG_LAUNCH(ctx, k_selftest_math, (1 << 24) / 256, 256, 0, st, bad);
+  unsigned long long hb[4];
+  GG_CUDA_OK(cudaMemcpyAsync(hb, bad, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  GG_CUDA_OK(cudaStreamSynchronize(st));
+  for (int i = 0; i < 4; ++i) mismatches[i] = (long long)hb[i];
+  return GG_OK;
+}
+
 // ============================================================================ host driver
+// strip height of k_region_stats: the image is cut into equal strips of about 107 rows (every
+// strip boundary costs one hand-over per column; shorter strips give more warps)
+static int rs_rows(int H) {
+  static int target = getenv("GG_RS_ROWS") ? atoi(getenv("GG_RS_ROWS")) : 107;
+  const int n = ceil_div(H, target > 0 ? target : 107);
+  return ceil_div(H, n);
+}
+
 static int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -1113,7 +1172,7 @@ size_t graph_workspace_bytes(int B, int H, int W, const gg_graph_config& cfg) {
   const int k = cfg.n_nonlocal > 0 ? cfg.n_nonlocal : 1;
   size_t s = 0;
   s += Arena::padded((size_t)B * H * W, 1);                 // gray
-  s += Arena::padded(2 * (size_t)(H + W), 8);               // coord tables
+  s += Arena::padded(2 * (size_t)(H + W) + 2 * (size_t)(H + 1), 8);   // coord tables + prefixes
   s += Arena::padded((size_t)B * nc * RS_NF, 8);            // acc
   s += Arena::padded((size_t)B * tc, 8);                    // pair keys
   s += Arena::padded((size_t)B * tc, 4);                    // pair counts
@@ -1156,7 +1215,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
   const int k = cfg.n_nonlocal;
 
   uint8_t* gray = ar.take<uint8_t>((size_t)B * H * W);
-  double* coord = ar.take<double>(2 * (size_t)(H + W));
+  double* coord = ar.take<double>(2 * (size_t)(H + W) + 2 * (size_t)(H + 1));
   const double* lin = ctx->d_lin;
   double* acc = ar.take<double>((size_t)B * nc * RS_NF);
   unsigned long long* pkeys = ar.take<unsigned long long>((size_t)B * tc);
@@ -1196,7 +1255,8 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     p.lin_lut = lin; p.acc = acc; p.label_max = label_max; p.pair_keys = pkeys;
     p.pair_cnts = pcnts; p.status = ctx->status_word; p.B = B; p.H = H; p.W = W; p.node_cap = nc;
     p.table_cap = tc; p.connectivity = cfg.connectivity;
-    p.n_sx = ceil_div(W, 32); p.n_sy = ceil_div(H, RS_ROWS);
+    p.rows = rs_rows(H);
+    p.n_sx = ceil_div(W, 32); p.n_sy = ceil_div(H, p.rows);
     p.lab = make_lab_matrix();
     const long long tasks = (long long)B * p.n_sx * p.n_sy;
     static const int occ = getenv("GG_RS_OCC") ? atoi(getenv("GG_RS_OCC")) : 2;

@@ -26,4 +26,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
 int pixel_planes(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, int W, float* lab,
                  float* hsv, float* gray, float* grad, cudaStream_t st);
 
+// float32 fast paths of pixel_math.cuh vs the IEEE intrinsics; mismatches[4] (see k_selftest_math)
+int selftest_math(gg_context* ctx, Arena& ar, long long* mismatches, cudaStream_t st);
+
 }  // namespace gg

@@ -97,6 +97,106 @@ GG_HD void bgr_to_hsv(int b, int g, int r, float& h, float& s, float& v) {
   h = GG_FDIV((float)p, (float)(6 * d));
 }
 
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// Device fast paths.  They return the same correctly rounded float32 values as the IEEE
+// intrinsics on the domains they are used on, with a third of the instructions and no
+// slow-path branches; gg_selftest_math checks them against __fsqrt_rn / __fdiv_rn on the GPU
+// (exhaustively where the domain is finite) and the all-colours parity test covers Lab / HSV.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// num / den for small non-negative integers held in floats (den >= 1): approximate reciprocal,
+// one exact residual (FMA) and one correction.  The quotients are rationals with denominators
+// <= 1530, never closer than 2^-35 (relative) to a float32 rounding boundary, and the corrected
+// value is within 2^-45 of the true quotient, so the final rounding is the correct one.
+__device__ __forceinline__ float fdiv_small(float num, float den) {
+  const float r = rcp_approx(den);
+  const float q = __fmul_rn(num, r);
+  const float e = __fmaf_rn(-q, den, num);
+  return __fmaf_rn(e, r, q);
+}
+
+// num / den with rden = RN(1/den) precomputed (Markstein's sequence); num >= 0, den > 0 normal.
+__device__ __forceinline__ float fdiv_rcp(float num, float den, float rden) {
+  const float q = __fmul_rn(num, rden);
+  const float e = __fmaf_rn(-q, den, num);
+  return __fmaf_rn(e, rden, q);
+}
+
+// sqrt of a non-negative integer < 2^24 held in a float (Sobel magnitude): rsqrt seed and one
+// Newton correction with an exact residual.  sqrt(0) = 0 through the clamped seed.
+__device__ __forceinline__ float fsqrt_int(float a) {
+  const float r = rsqrt_approx(fmaxf(a, 1.0f));
+  const float s = __fmul_rn(a, r);
+  const float h = __fmul_rn(0.5f, r);
+  const float e = __fmaf_rn(-s, s, a);
+  return __fmaf_rn(e, h, s);
+}
+
+// cbrt(t) for t in (0.008, 2): float32 seed of t^(-1/3) (lg2 / ex2), one third-order correction
+// in float64 (relative error ~e^3 with e ~ 1e-6), then t * r * r: ~1 ulp of float64, i.e. the
+// same float32 after rounding as the reference's libm cbrt except with probability ~1e-8.
+__device__ __forceinline__ double cbrt_unit(double t) {
+  const float tf = (float)t;
+  const double r0 = (double)ex2_approx(__fmul_rn(lg2_approx(tf), -0.33333334f));
+  const double e = __fma_rn(-__dmul_rn(t, r0), __dmul_rn(r0, r0), 1.0);       // 1 - t r^3
+  const double c = __fma_rn(e, 2.0 / 9.0, 1.0 / 3.0);
+  const double r = __fma_rn(__dmul_rn(r0, e), c, r0);                        // r (1 + e/3 + 2e^2/9)
+  return __dmul_rn(__dmul_rn(t, r), r);
+}
+
+// bgr_to_lab with one branch for "some channel above the linear segment" instead of three.
+__device__ __forceinline__ void bgr_to_lab_fast(const double* __restrict__ lin, const double* __restrict__ mat,
+                                                int b, int g, int r, float& L, float& A, float& B) {
+  const double lr = lin[r], lg = lin[g], lb = lin[b];
+  const double x = GG_DFMA(mat[2], lb, GG_DFMA(mat[1], lg, mat[0] * lr));
+  const double y = GG_DFMA(mat[5], lb, GG_DFMA(mat[4], lg, mat[3] * lr));
+  const double z = GG_DFMA(mat[8], lb, GG_DFMA(mat[7], lg, mat[6] * lr));
+  double fx = GG_DFMA(7.787, x, 16.0 / 116.0);
+  double fy = GG_DFMA(7.787, y, 16.0 / 116.0);
+  double fz = GG_DFMA(7.787, z, 16.0 / 116.0);
+  if (fmax(x, fmax(y, z)) > 0.008856) {
+    if (x > 0.008856) fx = cbrt_unit(x);
+    if (y > 0.008856) fy = cbrt_unit(y);
+    if (z > 0.008856) fz = cbrt_unit(z);
+  }
+  L = (float)(116.0 * fy - 16.0);
+  A = (float)(500.0 * (fx - fy));
+  B = (float)(200.0 * (fy - fz));
+}
+
+// hue and saturation of bgr_to_hsv, branch-free (d == 0 gives 0 / 1 = 0 for both).
+__device__ __forceinline__ void hsv_hs_fast(int b, int g, int r, int mx, int mn, float& h, float& s) {
+  const int d = mx - mn;
+  int pr_ = g - b;
+  pr_ += pr_ < 0 ? 6 * d : 0;                   // python-style (h/6) % 1 on the red sector
+  const int pg_ = 2 * d + (b - r);
+  const int pb_ = 4 * d + (r - g);
+  const int p = (b == mx) ? pb_ : ((g == mx) ? pg_ : pr_);   // "blue is max" overwrites (skimage order)
+  s = fdiv_small((float)d, (float)max(mx, 1));
+  h = fdiv_small((float)p, (float)max(6 * d, 1));
+}
+#endif  // __CUDACC__
+
 // BORDER_REFLECT_101 index (cv2 default for Sobel / blur): -1 -> 1, n -> n-2.
 GG_HD int reflect101(int i, int n) {
   if (n == 1) return 0;

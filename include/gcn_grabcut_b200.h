@@ -243,6 +243,14 @@ int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* la
                           float* probs_dev /*optional [B*node_cap,3]*/,
                           int64_t* node_off_dev /*optional [B+1]*/, void* stream);
 
+/* Device self test of the float32 fast paths the pixel kernels use instead of the IEEE
+ * division / square-root sequences (csrc/pixel_math.cuh), against __fdiv_rn / __fsqrt_rn:
+ * mismatches[0] sqrt of every integer < 2^24 (Sobel magnitudes), [1] saturation quotients
+ * d/max, [2] hue quotients p/(6d) (both exhaustive over uint8 colours), [3] normalised gradient
+ * g/(gmax+1e-6) for every Sobel magnitude and 64 image maxima each.  All four must be 0 for the
+ * per-pixel planes to be the reference's float32 values (graph_builder.py:142-154). */
+int gg_selftest_math(gg_handle h, int64_t* mismatches /*[4]*/);
+
 /* Number of kernels of this library launched by this handle so far (bench bookkeeping). */
 int64_t gg_kernel_launch_count(gg_handle h);
 

@@ -440,3 +440,15 @@ def test_trimap_path_streaming_submit_result(gg):
         except nat.NativeError:
             pass
     assert np.array_equal(path(*batches[2]), want[2][0])
+
+
+def test_fast_float32_paths_selftest(gg):
+    """Device self test: the short division / square-root sequences of the pixel kernels return
+    the IEEE round-to-nearest results on their whole domains (csrc/pixel_math.cuh)."""
+    import ctypes as C
+    from gcn_grabcut_b200 import _native as nat
+    h = nat.handle(0)
+    out = (C.c_int64 * 4)()
+    nat.check(nat.lib().gg_selftest_math(h.ptr, out))
+    print("selftest mismatches [sqrt, sat, hue, gradn]:", list(out))
+    assert list(out) == [0, 0, 0, 0]
