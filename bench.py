@@ -43,8 +43,8 @@ UNIT = "images/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--height", type=int, default=320)
@@ -159,41 +159,83 @@ def run_reference(a):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, polled through NVML every ~2 ms on a thread (the
+    timed region lasts tens of milliseconds: `nvidia-smi -lms` is too coarse); falls back to an
+    `nvidia-smi -lms 20` reader when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, uuid=None):
+        self.rows, self.proc, self.alive, self.max_mhz = [], None, True, None
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:        # CUDA_VISIBLE_DEVICES may renumber: prefer the UUID of the CUDA device
+                self.hdl = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                self.hdl = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.hdl, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        while self.alive:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.hdl, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.hdl))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.hdl))
+                self.rows.append((time.perf_counter(), mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+            f = [x.strip() for x in line.split(",")]
+            try:
+                mhz = float(f[1])
+                self.max_mhz = float(f[2])
+            except Exception:
+                continue
+            bits = 0
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    bits |= self.BITS[name]
+            self.rows.append((time.perf_counter(), mhz, bits))
 
     def window(self, t0, t1):
-        sm, mx, reasons = [], [], set()
-        for t, line in self.rows:
-            if t0 <= t <= t1 + 0.15:
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
-                except Exception:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
+        sm, reasons = [], set()
+        for t, mhz, bits in list(self.rows):
+            if t0 <= t <= t1:
+                sm.append(mhz)
+                for name, bit in self.BITS.items():
+                    if bits & bit:
                         reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
     def stop(self):
+        self.alive = False
         if self.proc:
             self.proc.terminate()
 
@@ -244,6 +286,8 @@ def run_ours(a):
 
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     state = random_state_dict(a.hidden, a.layers, seed=0)
@@ -271,7 +315,7 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
 
     # ---- device-resident throughput
     for _ in range(a.warmup):
@@ -324,7 +368,7 @@ def run_ours(a):
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "algorithmic_model": what,
                 "avg_launch_ms": avg_launch_ms, "share_of_step": top[2] / total_prof_ms,
-                "kernels_ms_per_step": {r[0]: round(r[2] / a.steps, 4) for r in rows[:12]},
+                "kernels_ms_per_step": {r[0]: round(r[2] / a.steps, 4) for r in rows[:40]},
                 "profiled_step_ms": total_prof_ms / a.steps}
 
     # ---- end to end through the host-buffer entry point.  Every step copies its 256 images and

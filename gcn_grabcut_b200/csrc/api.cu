@@ -270,6 +270,7 @@ void gg_destroy(gg_handle h) {
   if (h->net.tc_blob) cudaFree(h->net.tc_blob);
   if (h->d_status) cudaFree(h->d_status);
   if (h->d_lin) cudaFree(h->d_lin);
+  if (h->d_coord) cudaFree(h->d_coord);
   for (auto& ev : h->ev) cudaEventDestroy(ev);
   for (auto& ev : h->ticket_ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->prof_pool) cudaEventDestroy(ev);

@@ -100,6 +100,8 @@ struct gg_context {
   int* d_status = nullptr;   // [16] words: 0 last call, 1 sticky (host path), 8.. per sub-batch
   int* status_word = nullptr;  // word the kernels being enqueued right now report into
   double* d_lin = nullptr;   // sRGB linearisation table (256 doubles), built in gg_create
+  double* d_coord = nullptr;  // k_coord_tables of the last (H, W) seen
+  int coord_H = 0, coord_W = 0;
   int64_t launches = 0;
   uint64_t attr_done = 0;   // one bit per kernel whose max-dynamic-smem attribute is already set
   int gemm_impl = 1;      // 0 = SIMT fp32 (validation), 1 = tcgen05 bf16x3

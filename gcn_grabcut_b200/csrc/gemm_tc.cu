@@ -7,16 +7,19 @@
 // (x1w1, x1w2, x2w1, x2w2, x1w3, x3w1) are accumulated in fp32 in TMEM -- the dropped terms
 // are O(2^-24) relative, i.e. fp32-class accuracy, at 6 MMA passes.
 //
-// Kernel structure (one persistent CTA per SM, 256 threads):
+// Kernel structure (one persistent CTA per SM, 768 threads, warp-specialised):
 //   * the weight operand W is pre-split and pre-swizzled ON THE HOST at gg_load_weights
 //     time into the exact shared-memory image (canonical K-major SWIZZLE_128B atoms); each CTA
 //     pulls it in once with a single 1-D bulk TMA copy (cp.async.bulk + mbarrier tx-count);
-//   * per 128-row tile: all warps load the fp32 A rows (coalesced float4), split them and
-//     store the three bf16 images with the 128B swizzle applied by hand; fence.proxy.async;
-//   * one thread issues the 6 x K/16 tcgen05.mma (M=128, N, K=16; accumulator in TMEM) and
-//     commits to an mbarrier;
-//   * all warps read the accumulator back with tcgen05.ld (32 lanes x 32 columns per
-//     instruction), apply bias / activation / accumulate and store fp32 rows.
+//   * producer warps 0-15 (8 rows each), per 128-row tile: load the fp32 A rows (coalesced float4; the loads of
+//     tile i+1 are in flight while MMA(i) runs), run the fused prologue, split the values and store
+//     the three bf16 images with the 128B swizzle applied by hand; fence.proxy.async; then one
+//     producer thread issues the 6 x K/16 tcgen05.mma (M=128, N, K=16) into one of TWO TMEM
+//     accumulators and commits to that accumulator's mbarrier;
+//   * epilogue warps 16-23 wait for the commit, read the accumulator back with tcgen05.ld (32 lanes
+//     x 32 columns per instruction), apply bias / activation / accumulate, store fp32 rows and
+//     hand the accumulator back (mbarrier) -- the epilogue of tile i overlaps the producers'
+//     work on tile i+1 and MMA(i+1).
 // SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UBLKCP (bulk TMA).
 #include <cuda_bf16.h>
 
@@ -26,7 +29,8 @@
 namespace gg {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 768;       // 16 producer warps + 8 epilogue warps
+constexpr int TC_PRODUCERS = 512;
 
 // ----------------------------------------------------------------------------- PTX wrappers
 GG_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -37,6 +41,10 @@ GG_D void mbar_init(uint32_t bar, uint32_t count) {
 GG_D void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+GG_D void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+GG_D void producers_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 GG_D void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -133,15 +141,20 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
   const uint32_t sA = base, sB = base + 3 * a_split;
   unsigned char* pA = smem;
   const uint32_t ctrl = sB + 3 * b_split;                         // barriers + tmem pointer
-  const uint32_t bar_b = ctrl, bar_mma = ctrl + 8, tmem_slot = ctrl + 16;
-  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem + 3 * a_split + 3 * b_split + 16);
+  // ctrl: +0 weights landed, +8/+16 MMA done (accumulator 0/1), +24/+32 accumulator drained, +40 TMEM ptr
+  const uint32_t bar_b = ctrl, bar_mma0 = ctrl + 8, bar_free0 = ctrl + 24, tmem_slot = ctrl + 40;
+  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem + 3 * a_split + 3 * b_split + 40);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tmem_cols = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  const uint32_t acc_cols = N <= 32 ? 32 : (N <= 64 ? 64 : 128);   // columns of one accumulator
+  const uint32_t tmem_cols = 2 * acc_cols;
 
   if (tid == 0) {
     mbar_init(bar_b, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(bar_mma0, 1);
+    mbar_init(bar_mma0 + 8, 1);
+    mbar_init(bar_free0, TC_THREADS / 32 - TC_PRODUCERS / 32);    // one arrival per epilogue warp
+    mbar_init(bar_free0 + 8, TC_THREADS / 32 - TC_PRODUCERS / 32);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
@@ -149,6 +162,9 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
+  float* s_bias = reinterpret_cast<float*>(smem + 3 * a_split + 3 * b_split + 64);   // [N], zeros if no bias
+  for (int i = tid; i < N; i += TC_THREADS) s_bias[i] = bias ? __ldg(bias + i) : 0.0f;
+  __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(bar_b, 3 * b_split);
     bulk_g2s(sB, Bimg, 3 * b_split, bar_b);
@@ -156,29 +172,33 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
   const uint32_t idesc = umma_idesc_bf16(TC_BM, N);
   const int k4 = K >> 2;                                           // float4 per row
 
-  uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int row0 = tile * TC_BM;
-    // ---- A tile: fp32 rows -> three swizzled bf16 images.  Each warp owns 16 rows; all the
-    // global loads of the warp are issued before the first conversion (one latency, not 16).
-    {
-      // Work items are (row, float4 chunk): a warp covers 32/k4 rows per pass (1 for K = 128,
-      // 2 for K = 64), so that all lanes are busy for both widths.
-      constexpr int RPW = TC_BM / (TC_THREADS / 32);          // rows per warp
-      const int rpp = 32 / k4;                                 // rows per pass
-      const int sub = lane / k4, ch = lane - sub * k4;        // row within the pass, chunk within the row
-      const int n_pass = RPW / rpp;
+  if (warp < TC_PRODUCERS / 32) {
+    // =========================================================================== producers
+    constexpr int RPW = TC_BM / (TC_PRODUCERS / 32);          // rows per warp
+    // Work items are (row, float4 chunk): a warp covers 32/k4 rows per pass (1 for K = 128,
+    // 2 for K = 64), so that all lanes are busy for both widths.
+    const int rpp = 32 / k4;                                 // rows per pass
+    const int sub = lane / k4, ch = lane - sub * k4;        // row within the pass, chunk within the row
+    const int n_pass = RPW / rpp;
+    float w0[4][5], b0[4];
+    if (PRO == 2) {
+      // edge attributes (5 floats per row) -> 4 hidden units per lane
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = 4 * ch + u;
+        b0[u] = __ldg(pro.b0 + kk);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) w0[u][j] = __ldg(pro.w0 + kk * 5 + j);
+      }
+    }
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int row0 = tile * TC_BM;
+      // ---- A tile: fp32 rows (or the fused prologue's values) in registers.  All the global
+      // loads of the warp are issued before the first use (one latency, not 16), and before
+      // waiting for the previous tile's MMA, which is still reading the shared A images.
       float4 v[RPW];
       if (PRO == 2) {
-        // edge attributes (5 floats per row) -> 4 hidden units per lane
-        float w0[4][5], b0[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int kk = 4 * ch + u;
-          b0[u] = __ldg(pro.b0 + kk);
-#pragma unroll
-          for (int j = 0; j < 5; ++j) w0[u][j] = __ldg(pro.w0 + kk * 5 + j);
-        }
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -235,6 +255,8 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
           }
         }
       }
+      // ---- the shared A images are free once the previous tile's MMA has completed
+      if (it > 0) mbar_wait(bar_mma0 + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
       // exact 3-way split by truncation: x = x1 + x2 + x3 with x1 = top 8 mantissa bits of x,
       // x2 = top 8 bits of the (exact) remainder, x3 = what is left (<= 8 bits): ALU-only.
 #pragma unroll
@@ -260,60 +282,70 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
           }
         }
       }
-    }
-    fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core
-    __syncthreads();
+      fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core
+      producers_sync();
 
-    // ---- MMA: one thread issues 6 x (K/16) tcgen05.mma, accumulator in TMEM
-    if (tid == 0) {
-      if (it == 0) mbar_wait(bar_b, 0);
-      tc_fence_after();
-      const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
-      uint32_t acc = 0;
+      // ---- MMA: one thread issues 6 x (K/16) tcgen05.mma into accumulator it & 1
+      if (tid == 0) {
+        const uint32_t s_ = it & 1, u_ = it >> 1;
+        if (it == 0) mbar_wait(bar_b, 0);
+        if (u_ > 0) mbar_wait(bar_free0 + 8 * s_, (u_ - 1) & 1);     // the epilogue has drained it
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + s_ * acc_cols;
+        const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+        uint32_t acc = 0;
 #pragma unroll
-      for (int t = 5; t >= 0; --t) {     // small terms first
-        for (int a = 0; a < n_atoms; ++a) {
+        for (int t = 5; t >= 0; --t) {     // small terms first
+          for (int a = 0; a < n_atoms; ++a) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t ad = umma_desc(sA + pa[t] * a_split + a * (TC_BM * 128) + kk * 32);
-            const uint64_t bd = umma_desc(sB + pb[t] * b_split + a * (N * 128) + kk * 32);
-            umma_bf16(tmem_base, ad, bd, idesc, acc);
-            acc = 1;
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = umma_desc(sA + pa[t] * a_split + a * (TC_BM * 128) + kk * 32);
+              const uint64_t bd = umma_desc(sB + pb[t] * b_split + a * (N * 128) + kk * 32);
+              umma_bf16(tmem_d, ad, bd, idesc, acc);
+              acc = 1;
+            }
           }
         }
+        umma_commit(bar_mma0 + 8 * s_);
       }
-      umma_commit(bar_mma);
     }
-    mbar_wait(bar_mma, it & 1);
-    tc_fence_after();
-
-    // ---- epilogue: TMEM -> registers -> bias / activation / accumulate -> global
-    {
-      const int q = warp & 3, hh = warp >> 2;
-      const int row = row0 + 32 * q + lane;
-      const int ncol_w = N >> 1;                        // columns per warp
+  } else {
+    // =========================================================================== epilogue
+    // TMEM -> registers -> bias / activation / accumulate -> global.  Warp w reads TMEM lanes
+    // 32 (w % 4) ..; the two warps of a lane quarter take one half of the columns each.
+    const int ew = warp - TC_PRODUCERS / 32;
+    const int q = ew & 3, hh = ew >> 2;
+    const int ncol_w = N >> 1;                        // columns per warp
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t s_ = it & 1, u_ = it >> 1;
+      const int row = tile * TC_BM + 32 * q + lane;
+      mbar_wait(bar_mma0 + 8 * s_, u_ & 1);
+      tc_fence_after();
       for (int c0 = 0; c0 < ncol_w; c0 += 32) {
         const int col0 = hh * ncol_w + c0;
         uint32_t rr[32];
-        tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, rr);
+        tmem_ld32(tmem_base + s_ * acc_cols + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, rr);
         tmem_ld_wait();
+        if (c0 + 32 >= ncol_w) {          // last read of this accumulator: hand it back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_free0 + 8 * s_);
+        }
         if (row < M) {
           float* crow = C + (size_t)row * N + col0;
-          float4 prev[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) prev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (accumulate) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) prev[i] = *reinterpret_cast<const float4*>(crow + 4 * i);
-          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 o;
             float* op = reinterpret_cast<float*>(&o);
-            const float* pp = reinterpret_cast<const float*>(&prev[i]);
+            float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (accumulate) prev = *reinterpret_cast<const float4*>(crow + 4 * i);
+            const float* pp = reinterpret_cast<const float*>(&prev);
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * i);
+            const float* bp = reinterpret_cast<const float*>(&b4);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float vv = __uint_as_float(rr[4 * i + u]) + (bias ? __ldg(bias + col0 + 4 * i + u) : 0.0f) + pp[u];
+              float vv = __uint_as_float(rr[4 * i + u]) + bp[u] + pp[u];
               if (ACT == 1) vv = gelu_erf_tc(vv);
               if (ACT == 2) vv = 1.0f / (1.0f + expf(-vv));
               op[u] = vv;
@@ -323,10 +355,13 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();                      // TMEM and the A images may be overwritten
   }
-  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -390,8 +425,8 @@ int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const f
             const TcPrologue* prologue) {
   const NetWeights& nw = ctx->net;
   const uint8_t* img = reinterpret_cast<const uint8_t*>(nw.tc_blob) + nw.tc_off[which];
-  const size_t smem = (size_t)3 * (K / 64) * TC_BM * 128 + tc_image_bytes(N, K) + 64 + 1024;
-  const size_t smem_max = (size_t)3 * 2 * TC_BM * 128 + tc_image_bytes(128, 128) + 64 + 1024;   // K = N = 128
+  const size_t smem = (size_t)3 * (K / 64) * TC_BM * 128 + tc_image_bytes(N, K) + 64 + 512 + 1024;
+  const size_t smem_max = (size_t)3 * 2 * TC_BM * 128 + tc_image_bytes(128, 128) + 64 + 512 + 1024;   // K = N = 128
   const int tiles_cap = ceil_div(m_cap, TC_BM);
   const int grid = tiles_cap < ctx->sm_count ? tiles_cap : ctx->sm_count;
   TcPrologue pro{};

@@ -206,12 +206,26 @@ k_region_stats(const RegionStatsParams p) {
   const float grcp = __frcp_rn(gden);
   const int frame_x = (x == 0) + (x == W - 1);
 
-  // ---- grey rows y_begin-1 and y_begin: horizontal Sobel partials
-  //      hs = g[x-1] + 2 g[x] + g[x+1], hd = g[x+1] - g[x-1]
-  auto grey_row = [&](int off, int& hs, int& hd) {
-    const int gc = gry[off];
-    int ge = 0;
-    if (edge_lane) ge = gry[off + gdelta];
+  // ---- software pipeline.  Iteration y hands over / accumulates row y with the per-pixel values
+  // computed one iteration earlier, computes the values of row y+1 (independent instruction
+  // chains, interleaved by the scheduler) and issues the loads two rows ahead:
+  //   BGR(y+2), labels(y+2), grey(y+3) -- so no load is consumed in the iteration that issues it.
+  struct PixelVals { float L, A, Bv, hh, ss, g, gs; int mx; };
+  auto pixel_math = [&](int b_, int g_, int r_, int hs_a, int hd_a, int hd_b, int hs_c_, int hd_c_) {
+    PixelVals v;
+    bgr_to_lab_fast(s_lin, p.lab.m, b_, g_, r_, v.L, v.A, v.Bv);
+    const int mx = max(r_, max(g_, b_)), mn = min(r_, min(g_, b_));
+    hsv_hs_fast(b_, g_, r_, mx, mn, v.hh, v.ss);
+    v.mx = mx;
+    const int gx = hd_a + 2 * hd_b + hd_c_;          // rows r-1, r, r+1
+    const int gy = hs_c_ - hs_a;
+    v.g = fsqrt_int((float)(gx * gx + gy * gy));
+    v.gs = fdiv_rcp(v.g, gden, grcp);
+    return v;
+  };
+  // horizontal Sobel partials of a grey row from its centre values and the edge lanes' outer
+  // neighbours: hs = g[x-1] + 2 g[x] + g[x+1], hd = g[x+1] - g[x-1]
+  auto partials = [&](int gc, int ge, int& hs, int& hd) {
     int gl = __shfl_up_sync(0xffffffffu, gc, 1);
     int gr = __shfl_down_sync(0xffffffffu, gc, 1);
     if (is_l0) gl = ge;
@@ -221,14 +235,37 @@ k_region_stats(const RegionStatsParams p) {
     hs = gl + 2 * gc + gr;
     hd = gr - gl;
   };
-  int off = y_begin * W + xc;                          // pixel offset of (y, xc) in the image
-  int hs_m, hd_m, hs_c, hd_c;
-  grey_row((y_begin > 0 ? y_begin - 1 : (H > 1 ? 1 : 0)) * W + xc, hs_m, hd_m);
-  grey_row(off, hs_c, hd_c);
-  int lab_c = valid ? lab[off] : -1;
-  int lab_up = (valid && y_begin > 0) ? lab[off - W] : lab_c;
-  int e_lab = edge_lane ? lab[off + ldelta] : 0;       // outer label neighbour of the edge lanes
-  int pb = img[3 * off], pg = img[3 * off + 1], pr = img[3 * off + 2];
+  auto grey_row_off = [&](int r) -> uint32_t {         // BORDER_REFLECT_101 row, clamped
+    r = r < 0 ? -r : r;
+    r = r >= H ? 2 * H - 2 - r : r;
+    return (uint32_t)(min(max(r, 0), H - 1) * W + xc);
+  };
+  auto load_grey = [&](int r, int& gc, int& ge) {
+    const uint32_t o = grey_row_off(r);
+    gc = gry[o];
+    ge = 0;
+    if (edge_lane) ge = gry[o + gdelta];
+  };
+  const uint32_t off0 = (uint32_t)(y_begin * W + xc);  // pixel offset of (y_begin, xc) in the image
+  int hs_m, hd_m, hs_c, hd_c, g2c, g2e;
+  PixelVals cv;
+  int pb, pg, pr;
+  {
+    int gc, ge, hs_a, hd_a, hs_p0, hd_p0;
+    load_grey(y_begin - 1, gc, ge); partials(gc, ge, hs_a, hd_a);
+    load_grey(y_begin, gc, ge);     partials(gc, ge, hs_m, hd_m);
+    load_grey(y_begin + 1, gc, ge); partials(gc, ge, hs_p0, hd_p0);
+    load_grey(y_begin + 2, g2c, g2e);
+    cv = pixel_math(img[3 * off0], img[3 * off0 + 1], img[3 * off0 + 2], hs_a, hd_a, hd_m, hs_p0, hd_p0);
+    hs_c = hs_p0; hd_c = hd_p0;
+    const uint32_t o1 = (uint32_t)(min(y_begin + 1, H - 1) * W + xc);
+    pb = img[3 * o1]; pg = img[3 * o1 + 1]; pr = img[3 * o1 + 2];
+  }
+  int lab_c = valid ? lab[off0] : -1;
+  int lab_up = (valid && y_begin > 0) ? lab[off0 - W] : lab_c;
+  int lab_dn = (valid && y_begin + 1 < H) ? lab[off0 + W] : lab_c;
+  int e_lab = edge_lane ? lab[off0 + ldelta] : 0;       // outer label neighbour of the edge lanes
+  int e_lab_n = (edge_lane && y_begin + 1 < H) ? lab[off0 + W + ldelta] : 0;
 
   // per-lane run accumulators
   int cur = -1, cnt = 0, bnd = 0, ys = y_begin;
@@ -309,33 +346,26 @@ k_region_stats(const RegionStatsParams p) {
   };
 
   for (int y = y_begin; y < y_end; ++y) {
-    // ---- look ahead one row: grey, labels (incl. the edge lanes' outer neighbours), BGR
-    const bool has_dn = y + 1 < H;
-    const int offn = off + W;
-    const int goff = has_dn ? offn : (H > 1 ? off - W : off);      // REFLECT_101 below the last row
-    const int gcn = gry[goff];
-    int gen = 0, e_lab_n = 0, lab_dn = lab_c;
-    if (edge_lane) gen = gry[goff + gdelta];
-    if (has_dn) {
-      if (valid) lab_dn = lab[offn];
-      if (edge_lane) e_lab_n = lab[offn + ldelta];
+    // ---- loads two rows ahead (row indices are warp-uniform)
+    int g3c, g3e;
+    load_grey(y + 3, g3c, g3e);
+    const uint32_t ob = (uint32_t)(min(y + 2, H - 1) * W + xc);
+    const int nb_ = img[3 * ob], ng_ = img[3 * ob + 1], nr_ = img[3 * ob + 2];
+    int lab_dn2 = lab_dn, e_lab_n2 = 0;                 // below the image: the own label
+    if (y + 2 < H) {
+      if (valid) lab_dn2 = lab[ob];
+      if (edge_lane) e_lab_n2 = lab[ob + ldelta];
     }
-    int nb_ = 0, ng_ = 0, nr_ = 0;
-    if (y + 1 < y_end) { nb_ = img[3 * offn]; ng_ = img[3 * offn + 1]; nr_ = img[3 * offn + 2]; }
+    const bool has_dn = y + 1 < H;
 
-    // ---- horizontal neighbours: labels of this row, grey of the next row
+    // ---- horizontal neighbours: labels of this row, grey partials of row y+2
     int lab_l = __shfl_up_sync(0xffffffffu, lab_c, 1);
     int lab_r = __shfl_down_sync(0xffffffffu, lab_c, 1);
     if (is_l0) lab_l = e_lab;
     if (is_l31) lab_r = e_lab;
     if (own_r) lab_r = lab_c;
-    int gl = __shfl_up_sync(0xffffffffu, gcn, 1);
-    int gr = __shfl_down_sync(0xffffffffu, gcn, 1);
-    if (is_l0) gl = gen;
-    if (is_l31) gr = gen;
-    if (own_r) gr = gl;
-    if (W == 1) gl = gr = gcn;
-    const int hs_p = gl + 2 * gcn + gr, hd_p = gr - gl;
+    int hs_p, hd_p;
+    partials(g2c, g2e, hs_p, hd_p);
 
     // ---- run bookkeeping: hand finished runs to the warp table
     const unsigned fm = __ballot_sync(0xffffffffu, cnt > 0 && lab_c != cur);
@@ -343,21 +373,15 @@ k_region_stats(const RegionStatsParams p) {
     if (cnt == 0) ys = y;
     cur = lab_c;
 
-    // ---- per-pixel quantities (all lanes; lanes beyond the image feed a dead run)
+    // ---- values of row y+1 (BGR(y+1), grey rows y, y+1, y+2) ...
+    const PixelVals nv = pixel_math(pb, pg, pr, hs_m, hd_m, hd_c, hs_p, hd_p);
+    // ---- ... while row y is accumulated (all lanes; lanes beyond the image feed a dead run)
     {
-      float L, A, Bv;
-      bgr_to_lab_fast(s_lin, p.lab.m, pb, pg, pr, L, A, Bv);
-      const int mx = max(pr, max(pg, pb)), mn = min(pr, min(pg, pb));
-      float hh, ss;
-      hsv_hs_fast(pb, pg, pr, mx, mn, hh, ss);
-      const int gx = hd_m + 2 * hd_c + hd_p;
-      const int gy = hs_p - hs_m;
-      const float g = fsqrt_int((float)(gx * gx + gy * gy));
-      const float gs = fdiv_rcp(g, gden, grcp);
-      aL += (double)L; aA += (double)A; aB += (double)Bv;
-      aL2 += (double)__fmul_rn(L, L); aA2 += (double)__fmul_rn(A, A); aB2 += (double)__fmul_rn(Bv, Bv);
-      aH += (double)hh; aS += (double)ss; aV += s_vd[mx];
-      aG += (double)g; aGs += (double)gs;
+      aL += (double)cv.L; aA += (double)cv.A; aB += (double)cv.Bv;
+      aL2 += (double)__fmul_rn(cv.L, cv.L); aA2 += (double)__fmul_rn(cv.A, cv.A);
+      aB2 += (double)__fmul_rn(cv.Bv, cv.Bv);
+      aH += (double)cv.hh; aS += (double)cv.ss; aV += s_vd[cv.mx];
+      aG += (double)cv.g; aGs += (double)cv.gs;
       cnt += 1;
       // find_boundaries(mode="inner"): differs from an in-bounds 4-neighbour and label != 0
       const bool diff = (lab_up != lab_c) | (lab_dn != lab_c) | (lab_l != lab_c) | (lab_r != lab_c);
@@ -401,10 +425,12 @@ k_region_stats(const RegionStatsParams p) {
     }
 
     // ---- roll
+    cv = nv;
     hs_m = hs_c; hd_m = hd_c; hs_c = hs_p; hd_c = hd_p;
-    lab_up = lab_c; lab_c = lab_dn; e_lab = e_lab_n;
+    g2c = g3c; g2e = g3e;
+    lab_up = lab_c; lab_c = lab_dn; lab_dn = lab_dn2;
+    e_lab = e_lab_n; e_lab_n = e_lab_n2;
     pb = nb_; pg = ng_; pr = nr_;
-    off = offn;
   }
 
   // ---- end of strip: flush runs (lab_c now holds the label below the strip, or the own label
@@ -1172,7 +1198,6 @@ size_t graph_workspace_bytes(int B, int H, int W, const gg_graph_config& cfg) {
   const int k = cfg.n_nonlocal > 0 ? cfg.n_nonlocal : 1;
   size_t s = 0;
   s += Arena::padded((size_t)B * H * W, 1);                 // gray
-  s += Arena::padded(2 * (size_t)(H + W) + 2 * (size_t)(H + 1), 8);   // coord tables + prefixes
   s += Arena::padded((size_t)B * nc * RS_NF, 8);            // acc
   s += Arena::padded((size_t)B * tc, 8);                    // pair keys
   s += Arena::padded((size_t)B * tc, 4);                    // pair counts
@@ -1214,8 +1239,21 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
   const int nc = cfg.node_cap, pc = cfg.pair_cap, tc = next_pow2(4 * pc);
   const int k = cfg.n_nonlocal;
 
+  // coordinate tables: a function of (H, W) alone, kept in the handle between calls.  A change of
+  // shape drains the device first (concurrent sub-batches on other streams may read the old one).
+  if (ctx->coord_H != H || ctx->coord_W != W) {
+    GG_CUDA_OK(cudaDeviceSynchronize());
+    if (ctx->d_coord) GG_CUDA_OK(cudaFree(ctx->d_coord));
+    ctx->d_coord = nullptr;
+    ctx->coord_H = ctx->coord_W = 0;
+    GG_CUDA_OK(cudaMalloc((void**)&ctx->d_coord, (2 * (size_t)(H + W) + 2 * (size_t)(H + 1)) * sizeof(double)));
+    GG_LAUNCH(ctx, k_coord_tables, ceil_div(H > W ? H : W, 256), 256, 0, st, ctx->d_coord, H, W);
+    GG_CUDA_OK(cudaStreamSynchronize(st));
+    ctx->coord_H = H;
+    ctx->coord_W = W;
+  }
+  const double* coord = ctx->d_coord;
   uint8_t* gray = ar.take<uint8_t>((size_t)B * H * W);
-  double* coord = ar.take<double>(2 * (size_t)(H + W) + 2 * (size_t)(H + 1));
   const double* lin = ctx->d_lin;
   double* acc = ar.take<double>((size_t)B * nc * RS_NF);
   unsigned long long* pkeys = ar.take<unsigned long long>((size_t)B * tc);
@@ -1247,7 +1285,6 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
   {
     dim3 grid(ceil_div(W, K0_TX), ceil_div(H, K0_TY), B);
     GG_LAUNCH(ctx, k_gray_gradmax, grid, 256, 0, st, bgr, gray, gradmax, H, W);
-    GG_LAUNCH(ctx, k_coord_tables, ceil_div(H > W ? H : W, 256), 256, 0, st, coord, H, W);
   }
   {
     RegionStatsParams p;

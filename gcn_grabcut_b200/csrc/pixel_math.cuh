@@ -174,7 +174,7 @@ __device__ __forceinline__ void bgr_to_lab_fast(const double* __restrict__ lin, 
   double fx = GG_DFMA(7.787, x, 16.0 / 116.0);
   double fy = GG_DFMA(7.787, y, 16.0 / 116.0);
   double fz = GG_DFMA(7.787, z, 16.0 / 116.0);
-  if (fmax(x, fmax(y, z)) > 0.008856) {
+  if ((x > 0.008856) | (y > 0.008856) | (z > 0.008856)) {
     if (x > 0.008856) fx = cbrt_unit(x);
     if (y > 0.008856) fy = cbrt_unit(y);
     if (z > 0.008856) fz = cbrt_unit(z);
