@@ -642,6 +642,76 @@ k_knn(const float* __restrict__ st_all, const int* __restrict__ label_max,
   }
 }
 
+// Selection form of the same search for images with at most 32*T regions: each lane keeps the
+// distances to regions lane, lane+32, ... in registers; every round takes the warp-wide minimum
+// of (distance, index), retires it, and only then asks whether that region is adjacent (a
+// warp-parallel scan of the sorted pair list) -- adjacency is tested for the handful of nearest
+// regions instead of for every candidate.  Same result as k_knn (ties -> lower index).
+template <int T>
+__global__ void __launch_bounds__(256)
+k_knn_sel(const float* __restrict__ st_all, const int* __restrict__ label_max,
+          const int2* __restrict__ pairs_all, const int* __restrict__ start_all,
+          int* __restrict__ picks_all, int node_cap, int pair_cap, int k) {
+  const int b = blockIdx.y;
+  const int n = min(label_max[b] + 1, node_cap);
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
+  const float* mL = st + (size_t)ST_MEAN_L * node_cap;
+  const float* mA = mL + node_cap;
+  const float* mB = mA + node_cap;
+  const int2* pairs = pairs_all + (size_t)b * pair_cap;
+  const int* start = start_all + (size_t)b * (node_cap + 1);
+  const float INF = __int_as_float(0x7f800000);
+  const float li = mL[i], ai = mA[i], bi = mB[i];
+  float dv[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int j = lane + 32 * t;
+    float d = INF;
+    if (j < n && j != i) {
+      const float dx = __fsub_rn(li, mL[j]), dy = __fsub_rn(ai, mA[j]), dz = __fsub_rn(bi, mB[j]);
+      d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      if (!(d < INF)) d = INF;      // inf / nan never selected (np.isfinite filter, …:346)
+    }
+    dv[t] = d;
+  }
+  int* out = picks_all + ((size_t)b * node_cap + i) * k;
+  int r = 0;
+  while (r < k) {
+    // lane-local minimum; the strict '<' keeps the lowest index of equal distances
+    float md = INF;
+    int mt = 0;
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      if (dv[t] < md) { md = dv[t]; mt = t; }
+    float d = md;
+    int j = md < INF ? lane + 32 * mt : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+      if (knn_less(od, oj, d, j)) { d = od; j = oj; }
+    }
+    if (!(d < INF)) break;          // fewer than k finite candidates
+    if (lane == (j & 31)) {
+      const int wt = j >> 5;
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+        if (t == wt) dv[t] = INF;
+    }
+    const int lo = min(i, j), hi = max(i, j);
+    bool found = false;
+    for (int q = start[lo] + lane; q < start[lo + 1]; q += 32) found |= pairs[q].y == hi;
+    if (__any_sync(0xffffffffu, found)) continue;        // spatially adjacent: excluded
+    if (lane == 0) out[r] = j;
+    ++r;
+  }
+  if (lane == 0)
+    for (; r < k; ++r) out[r] = -1;
+}
+
 // ============================================================================ S4
 // Symmetrise the picks into sorted unique (lo,hi) pairs (graph_builder.py:348-350).
 __global__ void __launch_bounds__(512)
@@ -1313,7 +1383,13 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
             cursor, n_adj, max_shared, ctx->status_word, nc, tc, pc);
   if (k > 0) {
     dim3 grid(ceil_div(nc, 8), B);
-    if (k <= 4) GG_TRY(launch_knn<4>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
+    static const bool knn_legacy = getenv("GG_KNN_LEGACY") != nullptr;
+    if (!knn_legacy && nc <= 2048) {
+      if (nc <= 320) GG_LAUNCH(ctx, k_knn_sel<10>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
+      else if (nc <= 512) GG_LAUNCH(ctx, k_knn_sel<16>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
+      else if (nc <= 1024) GG_LAUNCH(ctx, k_knn_sel<32>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
+      else GG_LAUNCH(ctx, k_knn_sel<64>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
+    } else if (k <= 4) GG_TRY(launch_knn<4>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
     else if (k <= 8) GG_TRY(launch_knn<8>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
     else if (k <= 16) GG_TRY(launch_knn<16>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
     else GG_TRY(launch_knn<32>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
