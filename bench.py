@@ -364,8 +364,17 @@ def run_ours(a):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic, traffic_src = None, None
+    tpath = os.path.join(REPO, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and (H, W) == (320, 480):       # the capture is of this workload
+        base = top[0].split("<")[0]
+        ent = json.load(open(tpath))["kernels"].get(base)
+        if ent:
+            traffic = ent["bytes_per_image_per_launch"] * B / launches_per_step
+            traffic_src = "profiles/" + ent["source"]
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "algorithmic_model": what,
                 "avg_launch_ms": avg_launch_ms, "share_of_step": top[2] / total_prof_ms,
                 "kernels_ms_per_step": {r[0]: round(r[2] / a.steps, 4) for r in rows[:40]},
