@@ -18,7 +18,8 @@ try:  # torch-dependent names (same guard as the reference's __init__)
         ResGCNNet, build_model, Data, _probs_to_trimap, probs_to_node_trimap, project_to_pixels,
         TRIMAP_BG, TRIMAP_FG, TRIMAP_PROB_BG, TRIMAP_PROB_FG, CLASS_BG, CLASS_UNK, CLASS_FG,
     )
-    from .pipeline import guided_filter, refine_trimap, TrimapPath, PendingTrimaps, shard_range  # noqa: F401
+    from .pipeline import (guided_filter, refine_trimap, seed_from_prior, TrimapPath, PendingTrimaps,  # noqa: F401
+                           shard_range)  # noqa: F401
     _MODELS_AVAILABLE = True
 except ImportError:  # pragma: no cover
     _MODELS_AVAILABLE = False

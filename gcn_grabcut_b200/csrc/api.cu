@@ -106,7 +106,8 @@ static size_t path_workspace_bytes(gg_context* ctx, int B, int H, int W, const g
   const gg_graph_config cfg = norm_cfg(pc.graph);
   const long long SN = (long long)B * cfg.node_cap, SE = 2ll * B * cfg.pair_cap;
   return path_graph_arrays_bytes(B, cfg) + graph_workspace_bytes(B, H, W, cfg) +
-         resgcn_workspace_bytes(ctx->net, SN, SE, B) + trimap_workspace_bytes(B, H, W, false);
+         resgcn_workspace_bytes(ctx->net, SN, SE, B) + trimap_workspace_bytes(B, H, W, false) +
+         seed_workspace_bytes(B, SN);
 }
 
 static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* labels, int B,
@@ -143,6 +144,8 @@ static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_
   } else {
     GG_TRY(project_trimap(ctx, labels, pb.probs, pb.g.node_off, B, H, W, pc.thr_fg, pc.thr_bg, trimap, st));
   }
+  if (pc.seed_frac > 0.0)
+    GG_TRY(seed_from_prior(ctx, ar, trimap, labels, pb.g.x, pb.g.node_off, B, H, W, SN, pc.seed_frac, st));
   if (probs_out)
     GG_CUDA_OK(cudaMemcpyAsync(probs_out, pb.probs, (size_t)SN * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (node_off_out)
@@ -369,6 +372,17 @@ int gg_project_trimap(gg_handle h, const int32_t* labels_dev, const float* probs
   GG_CUDA_OK(cudaSetDevice(h->device));
   return project_trimap(h, labels_dev, probs_dev, node_off_dev, B, H, W, thr_fg, thr_bg, trimap_dev,
                         (cudaStream_t)stream);
+}
+
+int gg_seed_from_prior(gg_handle h, uint8_t* trimap_dev, const int32_t* labels_dev, const float* x_dev,
+                       const int64_t* node_off_dev, int B, int H, int W, int64_t node_cap_total,
+                       double seed_frac, void* stream) {
+  GG_REQUIRE(h && trimap_dev && labels_dev && x_dev && node_off_dev, "gg_seed_from_prior: null argument");
+  GG_REQUIRE(B > 0 && H > 0 && W > 0 && node_cap_total > 0, "gg_seed_from_prior: bad sizes");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_TRY(h->arena.reserve(seed_workspace_bytes(B, node_cap_total)));
+  return seed_from_prior(h, h->arena, trimap_dev, labels_dev, x_dev, node_off_dev, B, H, W, node_cap_total,
+                         seed_frac, (cudaStream_t)stream);
 }
 
 int gg_guided_filter(gg_handle h, const float* guide_dev, const float* src_dev, int H, int W, int radius,

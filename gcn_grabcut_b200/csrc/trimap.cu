@@ -427,6 +427,86 @@ __global__ void k_gray_only(const uint8_t* __restrict__ bgr, uint8_t* __restrict
   gray[i] = (uint8_t)gray_u8(p[0], p[1], p[2]);
 }
 
+// ----------------------------------------------------------------------------- seeding
+// _seed_from_prior (pipeline.py:149-186): a trimap without any foreground label (1, 3) or
+// without any background label (0, 2) gets the ceil-ish 10 % most confident regions of the
+// automatic prior promoted to the missing side (FG_PROBABLE = 3 / BG_PROBABLE = 2).
+// flags[b]: bit0 = some pixel is FG_DEFINITE / FG_PROBABLE, bit1 = some pixel is BG_*.
+__global__ void __launch_bounds__(256)
+k_trimap_sides(const uint8_t* __restrict__ trimap, int HW, int* __restrict__ flags) {
+  const int b = blockIdx.y;
+  const uint8_t* t = trimap + (size_t)b * HW;
+  int bits = 0;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16; i < HW; i += gridDim.x * blockDim.x * 16) {
+    if (i + 16 <= HW && (((uintptr_t)(t + i)) & 15) == 0) {
+      const uint4 v = *reinterpret_cast<const uint4*>(t + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t odd = w[k] & 0x01010101u;          // labels 1 and 3 are odd, 0 and 2 even
+        bits |= odd ? 1 : 0;
+        bits |= (odd != 0x01010101u) ? 2 : 0;
+      }
+    } else {
+      for (int k = i; k < min(HW, i + 16); ++k) bits |= (t[k] & 1) ? 1 : 2;
+    }
+  }
+  bits = __reduce_or_sync(0xffffffffu, bits);
+  if ((threadIdx.x & 31) == 0 && bits) atomicOr(&flags[b], bits);
+}
+
+// Block per image; does nothing when both sides are present.  sel[v] (node-major, the image's
+// slice of a [SN] array): 1 = promote to FG_PROBABLE, 2 = promote to BG_PROBABLE, 3 = both (the
+// background assignment comes second in the reference and wins), 0 = untouched.  Rank by the
+// prior column, descending; equal values: the larger region index first (a stable ascending
+// argsort, reversed).
+__global__ void __launch_bounds__(256)
+k_seed_select(const float* __restrict__ x, const int64_t* __restrict__ node_off,
+              const int* __restrict__ flags, double seed_frac, uint8_t* __restrict__ sel) {
+  const int b = blockIdx.x;
+  const int f = flags[b];
+  const int64_t n0 = node_off[b];
+  const int n = (int)(node_off[b + 1] - n0);
+  if (n <= 0) return;
+  uint8_t* s = sel + n0;
+  if ((f & 3) == 3) return;                     // k_seed_apply never reads sel for this image
+  const int n_seed = max(1, (int)rint(seed_frac * (double)n));
+  const float* pr = x + (size_t)n0 * GG_N_NODE_FEATS + GG_N_IMAGE_FEATS;     // prior columns 16..18
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int out = 0;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {      // 0: foreground prior (column 0), 1: background (column 1)
+      if (f & (1 << side)) continue;
+      const float pi = pr[(size_t)i * GG_N_NODE_FEATS + side];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float pj = pr[(size_t)j * GG_N_NODE_FEATS + side];
+        rank += (pj > pi) || (pj == pi && j > i);
+      }
+      if (rank < n_seed) out |= 1 << side;
+    }
+    s[i] = (uint8_t)out;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_seed_apply(const int32_t* __restrict__ labels, const int64_t* __restrict__ node_off,
+             const int* __restrict__ flags, const uint8_t* __restrict__ sel, int HW,
+             uint8_t* __restrict__ trimap) {
+  const int b = blockIdx.y;
+  if ((flags[b] & 3) == 3) return;
+  const int64_t n0 = node_off[b];
+  const int n = (int)(node_off[b + 1] - n0);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const size_t o = (size_t)b * HW + i;
+  const int l = labels[o];
+  if (l < 0 || l >= n) return;
+  const int sv = sel[n0 + l];
+  if (sv & 2) trimap[o] = 2;                    // BG_PROBABLE (applied last in the reference)
+  else if (sv & 1) trimap[o] = 3;               // FG_PROBABLE
+}
+
 // ----------------------------------------------------------------------------- host side
 size_t trimap_workspace_bytes(int B, int H, int W, bool need_gray) {
   size_t s = Arena::padded((size_t)B * H * W * 4, 4);      // a/b planes
@@ -468,6 +548,30 @@ int guided_filter_plane(gg_context* ctx, Arena& ar, const float* guide, const fl
   p.guide = guide; p.src = src; p.ab = ab; p.plane_stride = npx; p.q0 = out;
   p.H = H; p.W = W; p.radius = radius; p.eps = eps;
   GG_TRY(launch_guided<false>(ctx, p, 1, st));
+  return GG_OK;
+}
+
+size_t seed_workspace_bytes(int B, long long node_cap_total) {
+  return Arena::padded((size_t)B, 4) + Arena::padded((size_t)node_cap_total, 1) + 512;
+}
+
+int seed_from_prior(gg_context* ctx, Arena& ar, uint8_t* trimap, const int32_t* labels, const float* x,
+                    const int64_t* node_off, int B, int H, int W, long long node_cap_total,
+                    double seed_frac, cudaStream_t st) {
+  GG_REQUIRE(seed_frac > 0.0 && seed_frac <= 1.0, "seed_from_prior: seed_frac must be in (0, 1]");
+  const int HW = H * W;
+  int* flags = ar.take<int>((size_t)B);
+  uint8_t* sel = ar.take<uint8_t>((size_t)node_cap_total);
+  GG_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)B * sizeof(int), st));
+  {
+    dim3 grid(std::min(ceil_div(HW, 256 * 16), 64), B);
+    GG_LAUNCH(ctx, k_trimap_sides, grid, 256, 0, st, trimap, HW, flags);
+  }
+  GG_LAUNCH(ctx, k_seed_select, B, 256, 0, st, x, node_off, flags, seed_frac, sel);
+  {
+    dim3 grid(ceil_div(HW, 256), B);
+    GG_LAUNCH(ctx, k_seed_apply, grid, 256, 0, st, labels, node_off, flags, sel, HW, trimap);
+  }
   return GG_OK;
 }
 

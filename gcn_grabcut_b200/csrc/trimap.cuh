@@ -19,4 +19,10 @@ int project_trimap(gg_context* ctx, const int32_t* labels, const float* probs,
                    const int64_t* node_off, int B, int H, int W, float thr_fg, float thr_bg,
                    uint8_t* trimap, cudaStream_t st);
 
+// _seed_from_prior (pipeline.py:149-186) in place on device trimaps; x = node_input rows [SN,19].
+size_t seed_workspace_bytes(int B, long long node_cap_total);
+int seed_from_prior(gg_context* ctx, Arena& ar, uint8_t* trimap, const int32_t* labels, const float* x,
+                    const int64_t* node_off, int B, int H, int W, long long node_cap_total,
+                    double seed_frac, cudaStream_t st);
+
 }  // namespace gg

@@ -72,6 +72,39 @@ def refine_trimap(probs: np.ndarray, segments: np.ndarray, image: np.ndarray,
     return tri.cpu().numpy()
 
 
+def seed_from_prior(trimap: np.ndarray, graph, seed_frac: float = 0.1, device=None) -> np.ndarray:
+    """
+    Guarantee the trimap contains both a foreground and a background seed (reference
+    ``_seed_from_prior``, pipeline.py:149-186): if one side is missing, the
+    ``max(1, round(seed_frac * n_nodes))`` regions with the largest automatic prior for that side
+    are promoted to FG_PROBABLE / BG_PROBABLE.  Returns a new (H,W) uint8 array.
+    """
+    import torch
+    prior = graph.prior_features
+    if prior is None or prior.size == 0:
+        return trimap
+    dev = nat.device_index(device if device is not None else "cuda")
+    h = nat.handle(dev)
+    tdev = torch.device("cuda", dev)
+    seg = graph.segments
+    if trimap.shape != seg.shape:
+        raise ValueError(f"trimap shape {trimap.shape} != segments shape {seg.shape}")
+    H, W = seg.shape
+    n = int(graph.n_nodes)
+    x = torch.from_numpy(np.ascontiguousarray(graph.node_input(), dtype=np.float32)).to(tdev)
+    tri = torch.from_numpy(np.ascontiguousarray(trimap, dtype=np.uint8)).to(tdev)
+    lab = torch.from_numpy(np.ascontiguousarray(seg, dtype=np.int32)).to(tdev)
+    goff = torch.tensor([0, n], dtype=torch.int64, device=tdev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().gg_seed_from_prior(h.ptr, nat.ptr(tri), nat.ptr(lab), nat.ptr(x), nat.ptr(goff),
+                                               1, H, W, n, float(seed_frac),
+                                               C.c_void_p(nat.current_stream(dev))))
+    return tri.cpu().numpy()
+
+
+_seed_from_prior = seed_from_prior      # the reference's (private) name
+
+
 class TrimapPath:
     """
     The whole per-image trimap path, batched:  BGR images + label maps -> OpenCV trimaps.
@@ -83,13 +116,15 @@ class TrimapPath:
         graph  = GraphBuilder(image, cfg).build()                    (label map supplied)
         probs  = model.predict_probs(Data(graph.node_input(), graph.edge_index, graph.edge_attr))
         trimap = refine_trimap(probs, graph.segments, image, thr_fg, thr_bg, radius)
-    (pipeline.py:298-317), or ``model.predict_trimap`` when ``edge_aware=False``.
+    (pipeline.py:298-317), or ``model.predict_trimap`` when ``edge_aware=False``; with
+    ``seed_frac=0.1`` also the ``_seed_from_prior`` repair that ``segment()`` applies next
+    (pipeline.py:324), i.e. everything between ``cv2.imread`` + SLIC and ``cv2.grabCut``.
     """
 
     def __init__(self, model, sp_config: Optional[SuperpixelGraphConfig] = None, node_cap: int = 512,
                  pair_cap: int = 0, threshold_fg: float = 0.55, threshold_bg: float = 0.55,
                  filter_radius: int = 8, eps: float = 1e-3, edge_aware: bool = True, chunk: int = 0,
-                 device=None):
+                 seed_frac: float = 0.0, device=None):
         self.cfg = sp_config or SuperpixelGraphConfig()
         self.dev = nat.device_index(device if device is not None else "cuda")
         self.h = nat.handle(self.dev)
@@ -101,7 +136,7 @@ class TrimapPath:
         self.pc = nat.PathConfig(
             nat.GraphConfig(int(self.cfg.connectivity), int(self.cfg.n_nonlocal), self.node_cap, pair_cap),
             int(filter_radius), float(eps), float(threshold_fg), float(threshold_bg), int(bool(edge_aware)),
-            int(chunk))
+            int(chunk), float(seed_frac))
 
     def _ensure_weights(self):
         if self.h.weights_token is not self:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GG_ABI_VERSION 1
+#define GG_ABI_VERSION 2
 
 #define GG_N_IMAGE_FEATS 16 /* graph_builder.py:73 */
 #define GG_N_PRIOR_FEATS 3  /* graph_builder.py:74 */
@@ -200,6 +200,15 @@ int gg_project_trimap(gg_handle h, const int32_t* labels_dev, const float* probs
                       const int64_t* node_off_dev, int B, int H, int W, float thr_fg,
                       float thr_bg, uint8_t* trimap_dev, void* stream);
 
+/* _seed_from_prior(trimap, graph, seed_frac) (pipeline.py:149-186), batched and in place: an image
+ * whose trimap has no foreground label (1, 3) gets its max(1, round(seed_frac * n_nodes)) regions
+ * with the largest foreground prior (node_input column 16) set to GC_PR_FGD; likewise the
+ * background prior (column 17) and GC_PR_BGD when no background label (0, 2) exists.  Equal prior
+ * values: the larger region index is taken first.  x_dev = gg_graph_out.x ([SN,19]). */
+int gg_seed_from_prior(gg_handle h, uint8_t* trimap_dev, const int32_t* labels_dev, const float* x_dev,
+                       const int64_t* node_off_dev, int B, int H, int W, int64_t node_cap_total,
+                       double seed_frac, void* stream);
+
 /* guided_filter(guide, src, radius, eps) on single float32 planes (pipeline.py:71-100). */
 int gg_guided_filter(gg_handle h, const float* guide_dev, const float* src_dev, int H, int W,
                      int radius, float eps, float* out_dev, void* stream);
@@ -218,6 +227,8 @@ typedef struct gg_path_config {
   float thr_bg;
   int32_t edge_aware;  /* 1: refine_trimap, 0: predict_trimap (pipeline.py:312-321) */
   int32_t chunk;       /* images per pipelined chunk; 0 = choose */
+  double seed_frac;    /* > 0: repair one-sided trimaps like _seed_from_prior (pipeline.py:149-186,
+                          called by segment() with 0.1); 0 = leave the trimap as predicted */
 } gg_path_config;
 
 int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B,

@@ -63,3 +63,26 @@ def near_threshold_mask(p_bg: np.ndarray, p_fg: np.ndarray, thr_fg: float, thr_b
     """Pixels whose label decision lies within ``tol`` of a decision boundary (eq. 27)."""
     return ((np.abs(p_fg - F32(thr_fg)) <= tol) | (np.abs(p_bg - F32(thr_bg)) <= tol) |
             (np.abs(p_fg - p_bg) <= tol))
+
+
+def seed_from_prior(trimap: np.ndarray, prior: np.ndarray, seg: np.ndarray, n_nodes: int,
+                    seed_frac: float = 0.1) -> np.ndarray:
+    """pipeline.py:149-186 (_seed_from_prior) -- promote the most confident regions of the
+    automatic prior when the trimap lacks a foreground or a background label.  Equal prior values
+    are taken larger index first (stable ascending argsort, reversed); the reference's default
+    argsort leaves the order of ties to numpy's introsort."""
+    if prior is None or prior.size == 0:
+        return trimap
+    has_fg = np.isin(trimap, (1, 3)).any()
+    has_bg = np.isin(trimap, (0, 2)).any()
+    if has_fg and has_bg:
+        return trimap
+    n_seed = max(1, int(round(seed_frac * n_nodes)))
+    trimap = trimap.copy()
+    if not has_fg:
+        ids = np.argsort(prior[:, 0], kind="stable")[::-1][:n_seed]
+        trimap[np.isin(seg, ids)] = 3
+    if not has_bg:
+        ids = np.argsort(prior[:, 1], kind="stable")[::-1][:n_seed]
+        trimap[np.isin(seg, ids)] = 2
+    return trimap

@@ -452,3 +452,62 @@ def test_fast_float32_paths_selftest(gg):
     nat.check(nat.lib().gg_selftest_math(h.ptr, out))
     print("selftest mismatches [sqrt, sat, hue, gradn]:", list(out))
     assert list(out) == [0, 0, 0, 0]
+
+
+# ----------------------------------------------------------------------------- trimap hand-off
+def test_seed_from_prior_vs_reference_golden(gg):
+    """gg_seed_from_prior against the reference's own _seed_from_prior outputs
+    (tests/golden/handoff/seed_from_prior.npz): bit-exact, for graphs built by the CUDA builder."""
+    import os
+    from gcn_grabcut_b200.synthetic import geometric_sample, slic_like_labels
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "handoff",
+                             "seed_from_prior.npz"))
+    cases = sorted({k.split("/")[0] for k in z.files})
+    for name in cases:
+        H, W, seed, nseg, n_nodes = (int(v) for v in z[f"{name}/meta"])
+        img = geometric_sample(H, W, seed)[0]
+        seg = slic_like_labels(H, W, nseg, seed)
+        graph = gg.GraphBuilder(img, gg.SuperpixelGraphConfig(n_segments=nseg), segments=seg).build()
+        assert graph.n_nodes == n_nodes
+        np.testing.assert_allclose(graph.prior_features, z[f"{name}/prior"], rtol=1e-5, atol=2e-6)
+        for tname in ("all_pr_bgd", "all_fgd", "no_fg", "no_bg", "mixed"):
+            tri = z[f"{name}/{tname}/in"]
+            for frac in (0.1, 0.5):
+                got = gg.seed_from_prior(tri, graph, seed_frac=frac)
+                assert got.dtype == np.uint8 and np.array_equal(got, z[f"{name}/{tname}/{frac}"]), (name, tname, frac)
+
+
+def test_trimap_path_with_seeding(gg):
+    """TrimapPath(seed_frac=0.1) == TrimapPath() followed by the oracle's seed_from_prior per
+    image; thresholds of 2.0 make every trimap one-sided (no definite labels, and with the
+    background posterior forced above the foreground one no foreground at all)."""
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import model_port, trimap_port
+    B, H, W, nseg = 5, 128, 160, 40
+    imgs, labs = make_batch(B, H, W, nseg, seed0=300)
+    state = model_port.random_state_dict(32, 2, seed=4)
+    # bias the head towards background so that p_bg > p_fg everywhere: trimaps become all PR_BGD
+    state = {k: v.clone() for k, v in state.items()}
+    state["head.bias"] = state["head.bias"] + torch.tensor([8.0, 0.0, -8.0])
+    cap = int(labs.max()) + 1
+    plain = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=cap, threshold_fg=2.0, threshold_bg=2.0)
+    tri0 = plain(imgs, labs)
+    assert set(np.unique(tri0)) == {2}
+    seeded = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=cap, threshold_fg=2.0, threshold_bg=2.0,
+                           seed_frac=0.1)
+    tri1 = seeded(imgs, labs)
+    graphs = gg.build_graph_batch(imgs, labs, gg.SuperpixelGraphConfig()).to_graphs(labs)
+    for b in range(B):
+        want = trimap_port.seed_from_prior(tri0[b], graphs[b].prior_features, labs[b], graphs[b].n_nodes, 0.1)
+        assert (want == 3).any() and np.array_equal(tri1[b], want)
+    # a two-sided batch is left alone
+    both = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=cap, seed_frac=0.1)
+    ref = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=cap)
+    st2 = model_port.random_state_dict(32, 2, seed=4)
+    both = gg.TrimapPath(st2, gg.SuperpixelGraphConfig(), node_cap=cap, threshold_fg=0.34, threshold_bg=0.34, seed_frac=0.1)
+    t_a = both(imgs, labs)
+    ref = gg.TrimapPath(st2, gg.SuperpixelGraphConfig(), node_cap=cap, threshold_fg=0.34, threshold_bg=0.34)
+    t_b = ref(imgs, labs)
+    for b in range(B):
+        want = trimap_port.seed_from_prior(t_b[b], graphs[b].prior_features, labs[b], graphs[b].n_nodes, 0.1)
+        assert np.array_equal(t_a[b], want)

@@ -117,3 +117,38 @@ def test_find_boundaries_label0_quirk():
     seg[:, 4:] = 1
     b = find_boundaries(seg, mode="inner")
     assert not b[:, :4].any() and b[:, 4].all() and not b[:, 5:].any()
+
+
+# ----------------------------------------------------------------------------- trimap hand-off
+def _seed_fixture():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "handoff", "seed_from_prior.npz")
+    z = np.load(path)
+    cases = sorted({k.split("/")[0] for k in z.files})
+    return z, cases
+
+
+def test_seed_from_prior_port_matches_reference():
+    """oracle.trimap_port.seed_from_prior against the reference's _seed_from_prior
+    (tests/golden/make_golden_seed.py): one-sided trimaps are repaired identically, two-sided
+    ones come back untouched."""
+    from gcn_grabcut_b200.synthetic import slic_like_labels
+    z, cases = _seed_fixture()
+    assert len(cases) == 3
+    n_checked = 0
+    for name in cases:
+        H, W, seed, nseg, n_nodes = (int(v) for v in z[f"{name}/meta"])
+        seg = slic_like_labels(H, W, nseg, seed)
+        prior = z[f"{name}/prior"]
+        for tname in ("all_pr_bgd", "all_fgd", "no_fg", "no_bg", "mixed"):
+            tri = z[f"{name}/{tname}/in"]
+            for frac in (0.1, 0.5):
+                want = z[f"{name}/{tname}/{frac}"]
+                got = trimap_port.seed_from_prior(tri, prior, seg, n_nodes, frac)
+                assert np.array_equal(got, want), (name, tname, frac)
+                if tname == "mixed":
+                    assert np.array_equal(got, tri)
+                else:
+                    assert not np.array_equal(got, tri)
+                n_checked += 1
+    assert n_checked == 30
