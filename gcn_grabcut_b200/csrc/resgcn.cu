@@ -12,6 +12,10 @@
 //
 // Row counts are only known on the device: every kernel reads sizes[0] = total nodes,
 // sizes[1] = total directed edges and is launched for the capacity.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "resgcn.cuh"
 
@@ -136,6 +140,83 @@ __global__ void k_edge_enc1(const float* __restrict__ attr, const float* __restr
 #pragma unroll
   for (int kk = 0; kk < 5; ++kk) s = fmaf(w[kk], a[kk], s);
   e1[i] = gelu_erf(s);
+}
+
+// The second encoder layer is linear, so the scatter-mean commutes with it:
+//     mean_e (W2 g_e + b2) = W2 (mean_e g_e) + b2,     g_e = GELU(W0 a_e + b0)
+// (a node without incoming edges keeps ctx = 0, _scatter_mean's empty sum).  k_edge_gelu_mean
+// produces m_v = mean_{e: dst = v} g_e straight from the 5-d edge attributes -- the [E, c]
+// encodings are never materialised and W2 is applied to N node rows instead of E edge rows.
+// Warp per node; lane owns hidden units lane, lane+32, ... (c <= 256).
+template <int UPL>   // units per lane = ceil(c / 32)
+__global__ void __launch_bounds__(256)
+k_edge_gelu_mean(const float* __restrict__ attr, const int32_t* __restrict__ rowptr,
+                 const int32_t* __restrict__ eid, const float* __restrict__ wb, NetOffsets o,
+                 const int* __restrict__ sizes, float* __restrict__ m) {
+  const int c = o.c, lane = threadIdx.x & 31;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= sizes[0]) return;
+  float w[UPL][5], b[UPL], acc[UPL];
+#pragma unroll
+  for (int j = 0; j < UPL; ++j) {
+    const int u = min(lane + 32 * j, c - 1);
+    b[j] = wb[o.ee0_b + u];
+    acc[j] = 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < 5; ++kk) w[j][kk] = wb[o.ee0_w + (size_t)u * 5 + kk];
+  }
+  const int e0 = rowptr[v], e1 = rowptr[v + 1];
+  for (int e = e0; e < e1; e += 2) {
+    const bool two = e + 1 < e1;
+    const float* a0 = attr + (size_t)eid[e] * 5;
+    const float* a1 = attr + (size_t)eid[two ? e + 1 : e] * 5;
+    float x0[5], x1[5];
+#pragma unroll
+    for (int kk = 0; kk < 5; ++kk) { x0[kk] = __ldg(a0 + kk); x1[kk] = __ldg(a1 + kk); }
+#pragma unroll
+    for (int j = 0; j < UPL; ++j) {
+      float s0 = b[j], s1 = b[j];
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) { s0 = fmaf(w[j][kk], x0[kk], s0); s1 = fmaf(w[j][kk], x1[kk], s1); }
+      acc[j] += gelu_erf(s0);
+      if (two) acc[j] += gelu_erf(s1);
+    }
+  }
+  const float inv = 1.0f / (float)max(e1 - e0, 1);
+#pragma unroll
+  for (int j = 0; j < UPL; ++j) {
+    const int u = lane + 32 * j;
+    if (u < c) m[(size_t)v * c + u] = acc[j] * inv;
+  }
+}
+
+// ctx_v = LN_c(W2 m_v + b2) for nodes with incoming edges, LN_c(0) otherwise; t = W2 m (no bias)
+__global__ void __launch_bounds__(256)
+k_edge_ctx_ln(const float* __restrict__ t, const int32_t* __restrict__ rowptr,
+              const float* __restrict__ wb, NetOffsets o, const int* __restrict__ sizes,
+              float* __restrict__ ctx) {
+  const int c = o.c, lane = threadIdx.x & 31;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= sizes[0]) return;
+  const bool has = rowptr[v + 1] > rowptr[v];
+  float acc[8];
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lane + 32 * j;
+    acc[j] = (has && ch < c) ? t[(size_t)v * c + ch] + wb[o.ee2_b + ch] : 0.0f;
+    sum += acc[j];
+  }
+  const float mean = warp_sum(sum) / (float)c;
+  float sq = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) if (lane + 32 * j < c) { const float d = acc[j] - mean; sq += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)c + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < c) ctx[(size_t)v * c + ch] = (acc[j] - mean) * rstd * wb[o.eg_ln_g + ch] + wb[o.eg_ln_b + ch];
+  }
 }
 
 // ctx_v = LN_c(mean_{e: dst = v} enc_e)   (model.py:69-74, 129-139); warp per node
@@ -592,7 +673,7 @@ static NetOffsets make_offsets(const NetWeights& nw) {
   o.jk_w = nw.jk_w; o.bn_scale = nw.bn_scale; o.bn_shift = nw.bn_shift;
   o.w_in = nw.w_in; o.b_in = nw.b_in; o.ln_in_g = nw.ln_in_g; o.ln_in_b = nw.ln_in_b;
   o.pb0_w = nw.pb0_w; o.pb0_b = nw.pb0_b; o.pb2_w = nw.pb2_w; o.pb2_b = nw.pb2_b;
-  o.ee0_w = nw.ee0_w; o.ee0_b = nw.ee0_b; o.eg_ln_g = nw.eg_ln_g; o.eg_ln_b = nw.eg_ln_b;
+  o.ee0_w = nw.ee0_w; o.ee0_b = nw.ee0_b; o.ee2_b = nw.ee2_b; o.eg_ln_g = nw.eg_ln_g; o.eg_ln_b = nw.eg_ln_b;
   o.attn_w = nw.attn_w; o.attn_b = nw.attn_b; o.cmp_w = nw.cmp_w; o.cmp_b = nw.cmp_b;
   o.exp_w = nw.exp_w; o.exp_b = nw.exp_b; o.head_w = nw.head_w; o.head_b = nw.head_b;
   return o;
@@ -602,7 +683,7 @@ size_t resgcn_workspace_bytes(const NetWeights& nw, long long node_cap, long lon
   const int D = nw.D, c = nw.c;
   size_t s = 0;
   s += Arena::padded((size_t)node_cap * D, 4) * 5;      // h, z, gate, t0, t1
-  s += Arena::padded((size_t)edge_cap * c, 4) * 2;      // e1, enc
+  s += Arena::padded((size_t)std::max<long long>(std::max<long long>(edge_cap, node_cap), 1) * c, 4) * 2;   // e1, enc
   s += Arena::padded((size_t)node_cap * c, 4);          // ctx
   s += Arena::padded((size_t)node_cap, 4) * 3;          // node_graph, dinv, score
   s += Arena::padded((size_t)n_graphs * D, 4);          // gvec
@@ -641,8 +722,9 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   float* gate = ar.take<float>((size_t)node_cap * D);
   float* t0 = ar.take<float>((size_t)node_cap * D);
   float* t1 = ar.take<float>((size_t)node_cap * D);
-  float* e1 = ar.take<float>((size_t)(edge_cap > 0 ? edge_cap : 1) * c);
-  float* enc = ar.take<float>((size_t)(edge_cap > 0 ? edge_cap : 1) * c);
+  const size_t enc_rows = (size_t)std::max<long long>(std::max<long long>(edge_cap, node_cap), 1);
+  float* e1 = ar.take<float>(enc_rows * c);
+  float* enc = ar.take<float>(enc_rows * c);
   float* ctxv = ar.take<float>((size_t)node_cap * c);
   int* node_graph = ar.take<int>((size_t)node_cap);
   float* dinv = ar.take<float>((size_t)node_cap);
@@ -668,17 +750,33 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   }
   // ---- edge context -> gate
   const bool use_tc = ctx->gemm_impl == 1;
-  if (edge_cap > 0) {
-    if (use_tc && gemm_tc_supported(ctx, GEMM_ENC2, c, c) && c == 64) {
-      TcPrologue pro;                                   // first encoder layer fused into the A producer
-      pro.mode = 2; pro.w0 = wb + nw.ee0_w; pro.b0 = wb + nw.ee0_b;
-      GG_TRY(gemm_tc(ctx, st, GEMM_ENC2, edge_attr, wb + nw.ee2_b, enc, n_edges_p, edge_cap, c, c, 0, 0, &pro));
-    } else {
-      GG_LAUNCH(ctx, k_edge_enc1, ceil_div(edge_cap * c, 256), 256, 0, st, edge_attr, wb, o, sizes, e1);
-      GG_TRY(gemm(ctx, st, GEMM_ENC2, e1, wb + nw.ee2_w, wb + nw.ee2_b, enc, n_edges_p, edge_cap, c, c, 0, 0));
+  static const bool edge_legacy = getenv("GG_EDGE_LEGACY") != nullptr;
+  if (!edge_legacy && c <= 256) {
+    // mean of the first-layer features per node, then the (linear) second layer on node rows
+    float* m = e1;        // [node_cap, c] fits: e1 / enc hold max(edge_cap, node_cap) rows
+    float* tc_ = enc;
+    switch ((c + 31) / 32) {
+      case 1: GG_LAUNCH(ctx, k_edge_gelu_mean<1>, warp_blocks, 256, 0, st, edge_attr, rowptr, eid, wb, o, sizes, m); break;
+      case 2: GG_LAUNCH(ctx, k_edge_gelu_mean<2>, warp_blocks, 256, 0, st, edge_attr, rowptr, eid, wb, o, sizes, m); break;
+      case 3: GG_LAUNCH(ctx, k_edge_gelu_mean<3>, warp_blocks, 256, 0, st, edge_attr, rowptr, eid, wb, o, sizes, m); break;
+      case 4: GG_LAUNCH(ctx, k_edge_gelu_mean<4>, warp_blocks, 256, 0, st, edge_attr, rowptr, eid, wb, o, sizes, m); break;
+      default: GG_LAUNCH(ctx, k_edge_gelu_mean<8>, warp_blocks, 256, 0, st, edge_attr, rowptr, eid, wb, o, sizes, m); break;
     }
+    GG_TRY(gemm(ctx, st, GEMM_ENC2, m, wb + nw.ee2_w, nullptr, tc_, n_nodes_p, node_cap, c, c, 0, 0));
+    GG_LAUNCH(ctx, k_edge_ctx_ln, warp_blocks, 256, 0, st, tc_, rowptr, wb, o, sizes, ctxv);
+  } else {
+    if (edge_cap > 0) {
+      if (use_tc && gemm_tc_supported(ctx, GEMM_ENC2, c, c) && c == 64) {
+        TcPrologue pro;                                   // first encoder layer fused into the A producer
+        pro.mode = 2; pro.w0 = wb + nw.ee0_w; pro.b0 = wb + nw.ee0_b;
+        GG_TRY(gemm_tc(ctx, st, GEMM_ENC2, edge_attr, wb + nw.ee2_b, enc, n_edges_p, edge_cap, c, c, 0, 0, &pro));
+      } else {
+        GG_LAUNCH(ctx, k_edge_enc1, ceil_div(edge_cap * c, 256), 256, 0, st, edge_attr, wb, o, sizes, e1);
+        GG_TRY(gemm(ctx, st, GEMM_ENC2, e1, wb + nw.ee2_w, wb + nw.ee2_b, enc, n_edges_p, edge_cap, c, c, 0, 0));
+      }
+    }
+    GG_LAUNCH(ctx, k_edge_ctx, warp_blocks, 256, 0, st, enc, rowptr, eid, wb, o, sizes, ctxv);
   }
-  GG_LAUNCH(ctx, k_edge_ctx, warp_blocks, 256, 0, st, enc, rowptr, eid, wb, o, sizes, ctxv);
   GG_TRY(gemm(ctx, st, GEMM_GATE, ctxv, wb + nw.eg_w, wb + nw.eg_b, gate, n_nodes_p, node_cap, D, c, 2, 0));
 
   // ---- residual GCN blocks

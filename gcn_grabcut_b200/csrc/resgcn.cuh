@@ -8,7 +8,7 @@ namespace gg {
 struct NetOffsets {
   int D, q, c;
   unsigned jk_w, bn_scale, bn_shift, w_in, b_in, ln_in_g, ln_in_b;
-  unsigned pb0_w, pb0_b, pb2_w, pb2_b, ee0_w, ee0_b, eg_ln_g, eg_ln_b;
+  unsigned pb0_w, pb0_b, pb2_w, pb2_b, ee0_w, ee0_b, ee2_b, eg_ln_g, eg_ln_b;
   unsigned attn_w, attn_b, cmp_w, cmp_b, exp_w, exp_b, head_w, head_b;
 };
 
