@@ -21,7 +21,7 @@
 
 namespace gg {
 
-constexpr int GF_MAX_STRIP = 160;   // output rows per block (strip height), runtime <= this
+constexpr int GF_MAX_STRIP = 512;   // output rows per block (strip height), runtime <= this
 constexpr int GF_MAX_RADIUS = 24;
 constexpr int GF_PROB_TABLE = 1024;  // labels whose (p_bg, p_fg) are staged in shared memory
 
