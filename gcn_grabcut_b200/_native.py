@@ -61,7 +61,8 @@ class ResGCNWeights(C.Structure):
 class PathConfig(C.Structure):
     _fields_ = [("graph", GraphConfig), ("radius", C.c_int32), ("eps", C.c_float),
                 ("thr_fg", C.c_float), ("thr_bg", C.c_float), ("edge_aware", C.c_int32),
-                ("chunk", C.c_int32), ("seed_frac", C.c_double)]
+                ("chunk", C.c_int32), ("label_bytes", C.c_int32), ("reserved", C.c_int32),
+                ("seed_frac", C.c_double)]
 
 
 # state-dict key -> struct field (single tensors)

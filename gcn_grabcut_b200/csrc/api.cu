@@ -58,6 +58,22 @@ void prof_begin(gg_context* ctx, const char* name, cudaStream_t st) {
 }
 void prof_end(gg_context* ctx, cudaStream_t st) { cudaEventRecord(ctx->prof.back().e1, st); }
 
+// uint16 label maps (compact host transport, gg_path_config.label_bytes == 2) -> the int32 maps
+// the kernels read
+__global__ void __launch_bounds__(256)
+k_widen_labels(const uint16_t* __restrict__ in, int32_t* __restrict__ out, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n && ((uintptr_t)(in + i) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(in + i);
+    int4 a = make_int4(v.x & 0xffff, v.x >> 16, v.y & 0xffff, v.y >> 16);
+    int4 b = make_int4(v.z & 0xffff, v.z >> 16, v.w & 0xffff, v.w >> 16);
+    *reinterpret_cast<int4*>(out + i) = a;
+    *reinterpret_cast<int4*>(out + i + 4) = b;
+  } else {
+    for (size_t k = i; k < n && k < i + 8; ++k) out[k] = in[k];
+  }
+}
+
 __global__ void k_status_or(const int* __restrict__ word, int* __restrict__ sticky) {
   if (*word) atomicOr(sticky, *word);
 }
@@ -410,11 +426,15 @@ int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* la
 // (inputs + workspace + trimaps) rotate, across calls as well: a submitted call only enqueues
 // work, so the copy-in of call n+1 overlaps the kernels of call n and the host<->device link
 // stays busy (one call alone pays the fill and drain of the pipeline).
-static int host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H,
+static int host_submit(gg_handle h, const uint8_t* bgr_host, const void* labels_host_v, int B, int H,
                        int W, const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
                        int32_t* n_edges_host, int* ticket, size_t chunk_input_bytes) {
-  GG_REQUIRE(h && bgr_host && labels_host && cfg && trimap_host && ticket, "gg_trimap_path_host: null argument");
+  GG_REQUIRE(h && bgr_host && labels_host_v && cfg && trimap_host && ticket, "gg_trimap_path_host: null argument");
   GG_REQUIRE(B > 0 && H >= 2 && W >= 2, "gg_trimap_path_host: bad shape");
+  GG_REQUIRE(cfg->label_bytes == 0 || cfg->label_bytes == 4 || cfg->label_bytes == 2,
+             "gg_trimap_path_host: label_bytes must be 4 (int32) or 2 (uint16)");
+  const size_t lbytes = cfg->label_bytes == 2 ? 2 : 4;
+  const char* labels_host = reinterpret_cast<const char*>(labels_host_v);
   GG_CUDA_OK(cudaSetDevice(h->device));
   if (!h->net.loaded) { set_error("gg_trimap_path_host_submit: call gg_load_weights first"); return GG_ERR_STATE; }
   if (h->tickets_open >= gg_context::MAX_TICKETS) {
@@ -422,12 +442,12 @@ static int host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labe
     return GG_ERR_STATE;
   }
   const size_t npx = (size_t)H * W;
-  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)(chunk_input_bytes / (npx * 7) + 1)));
+  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)(chunk_input_bytes / (npx * (3 + lbytes)) + 1)));
   chunk = std::min(chunk, B);
   const int n_chunks = (B + chunk - 1) / chunk;
   const int n_slots = 3;
   const size_t in_bytes = Arena::padded((size_t)chunk * npx * 3, 1) + Arena::padded((size_t)chunk * npx, 4) +
-                          Arena::padded((size_t)chunk * npx, 1);
+                          Arena::padded((size_t)chunk * npx, 1) + (lbytes == 2 ? Arena::padded((size_t)chunk * npx, 2) : 0);
   const size_t slot_bytes = in_bytes + path_workspace_bytes(h, chunk, H, W, *cfg) + 4096;
   if (slot_bytes != h->slot_bytes) {
     // a different chunk geometry: let the calls in flight finish, then lay the slots out anew
@@ -450,19 +470,25 @@ static int host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labe
     uint8_t* d_bgr = ar.take<uint8_t>((size_t)chunk * npx * 3);
     int32_t* d_lab = ar.take<int32_t>((size_t)chunk * npx);
     uint8_t* d_tri = ar.take<uint8_t>((size_t)chunk * npx);
+    uint16_t* d_lab16 = lbytes == 2 ? ar.take<uint16_t>((size_t)chunk * npx) : nullptr;
     // the slot is free again once its previous trimaps have been copied out
     if (h->slot_used[s]) GG_CUDA_OK(cudaStreamWaitEvent(h->s_in, ev_out[s], 0));
     h->slot_used[s] = true;
     GG_CUDA_OK(cudaMemcpyAsync(d_bgr, bgr_host + (size_t)b0 * npx * 3, (size_t)nb * npx * 3, cudaMemcpyHostToDevice, h->s_in));
-    GG_CUDA_OK(cudaMemcpyAsync(d_lab, labels_host + (size_t)b0 * npx, (size_t)nb * npx * 4, cudaMemcpyHostToDevice, h->s_in));
+    GG_CUDA_OK(cudaMemcpyAsync(lbytes == 2 ? (void*)d_lab16 : (void*)d_lab, labels_host + (size_t)b0 * npx * lbytes,
+                               (size_t)nb * npx * lbytes, cudaMemcpyHostToDevice, h->s_in));
     GG_CUDA_OK(cudaEventRecord(ev_in[s], h->s_in));
     cudaStream_t rs = par ? h->s_sub[3] : h->s_run;
     GG_CUDA_OK(cudaStreamWaitEvent(rs, ev_in[s], 0));
+    if (lbytes == 2)
+      GG_LAUNCH(h, k_widen_labels, ceil_div((long long)nb * npx, 256 * 8), 256, 0, rs, d_lab16, d_lab, (size_t)nb * npx);
     h->status_word = h->d_status + 2 + par;
+    h->rs_direct = lbytes == 2 ? 1 : 0;      // 7 B/px in: copy-bound, keep the L2 atomics low (see build_graphs)
     int st = run_path(h, ar, d_bgr, d_lab, nb, H, W, *cfg, d_tri, nullptr, nullptr,
                       n_nodes_host ? n_nodes_host + b0 : nullptr, n_edges_host ? n_edges_host + b0 : nullptr,
                       rs);
     h->status_word = h->d_status;
+    h->rs_direct = 1;
     if (st != GG_OK) { cudaDeviceSynchronize(); return st; }
     // accumulate the per-chunk device status into the sticky word
     GG_LAUNCH(h, k_status_or, 1, 1, 0, rs, h->d_status + 2 + par, h->d_status + 1);
@@ -505,14 +531,14 @@ int gg_trimap_path_host_wait(gg_handle h, int ticket) {
 // Default chunk sizes (cfg->chunk == 0), measured on B200 at 320x480: a streamed call keeps the
 // pipeline full across calls and prefers large chunks (kernel efficiency: ~128 images, 138 MB of
 // input); a single synchronous call pays the fill and drain itself and prefers ~64 images.
-int gg_trimap_path_host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H,
+int gg_trimap_path_host_submit(gg_handle h, const uint8_t* bgr_host, const void* labels_host, int B, int H,
                                int W, const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
                                int32_t* n_edges_host, int* ticket) {
   return host_submit(h, bgr_host, labels_host, B, H, W, cfg, trimap_host, n_nodes_host, n_edges_host, ticket,
                      (size_t)137 << 20);
 }
 
-int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B, int H, int W,
+int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const void* labels_host, int B, int H, int W,
                         const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
                         int32_t* n_edges_host) {
   int ticket = -1;

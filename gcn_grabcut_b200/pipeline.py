@@ -136,7 +136,7 @@ class TrimapPath:
         self.pc = nat.PathConfig(
             nat.GraphConfig(int(self.cfg.connectivity), int(self.cfg.n_nonlocal), self.node_cap, pair_cap),
             int(filter_radius), float(eps), float(threshold_fg), float(threshold_bg), int(bool(edge_aware)),
-            int(chunk), float(seed_frac))
+            int(chunk), 4, 0, float(seed_frac))
 
     def _ensure_weights(self):
         if self.h.weights_token is not self:
@@ -161,27 +161,38 @@ class TrimapPath:
         import torch
         self._ensure_weights()
         img = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
-        lab = labels if torch.is_tensor(labels) else torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32))
+        if torch.is_tensor(labels):
+            lab = labels
+        elif isinstance(labels, np.ndarray) and labels.dtype == np.uint16:
+            lab = torch.from_numpy(np.ascontiguousarray(labels))     # compact transport, see below
+        else:
+            lab = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32))
         if img.is_cuda or lab.is_cuda:
             raise ValueError("TrimapPath.__call__ takes host buffers; use run_device for CUDA tensors")
         if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[-1] != 3:
             raise ValueError("images must be uint8 (B,H,W,3)")
-        if lab.dtype != torch.int32 or tuple(lab.shape) != tuple(img.shape[:3]):
-            raise ValueError("labels must be int32 (B,H,W) matching images")
+        # int32 label maps are the reference layout (graph_builder.py:188); uint16 maps (labels
+        # < 65536) are accepted as a compact transport: 5 instead of 7 bytes per pixel over PCIe
+        if lab.dtype not in (torch.int32, torch.uint16) or tuple(lab.shape) != tuple(img.shape[:3]):
+            raise ValueError("labels must be int32 (or uint16) (B,H,W) matching images")
         B, H, W = int(img.shape[0]), int(img.shape[1]), int(img.shape[2])
         tri = out if out is not None else torch.empty((B, H, W), dtype=torch.uint8)
         tri_t = tri if torch.is_tensor(tri) else torch.from_numpy(tri)
         nn_ = torch.empty(B, dtype=torch.int32) if return_counts else None
         ne_ = torch.empty(B, dtype=torch.int32) if return_counts else None
         img, lab = img.contiguous(), lab.contiguous()
+        pc = self.pc
+        if lab.dtype == torch.uint16:
+            pc = nat.PathConfig.from_buffer_copy(self.pc)
+            pc.label_bytes = 2
         ticket = C.c_int(-1)
         with torch.cuda.device(self.dev):
             if _sync:
                 nat.check(nat.lib().gg_trimap_path_host(self.h.ptr, nat.ptr(img), nat.ptr(lab), B, H, W,
-                                                        C.byref(self.pc), nat.ptr(tri_t), nat.ptr(nn_), nat.ptr(ne_)))
+                                                        C.byref(pc), nat.ptr(tri_t), nat.ptr(nn_), nat.ptr(ne_)))
                 return PendingTrimaps(self, -1, None, tri_t, torch.is_tensor(out), nn_, ne_)
             nat.check(nat.lib().gg_trimap_path_host_submit(self.h.ptr, nat.ptr(img), nat.ptr(lab), B, H, W,
-                                                           C.byref(self.pc), nat.ptr(tri_t), nat.ptr(nn_),
+                                                           C.byref(pc), nat.ptr(tri_t), nat.ptr(nn_),
                                                            nat.ptr(ne_), C.byref(ticket)))
         return PendingTrimaps(self, ticket.value, (img, lab), tri_t, torch.is_tensor(out), nn_, ne_)
 

@@ -227,11 +227,15 @@ typedef struct gg_path_config {
   float thr_bg;
   int32_t edge_aware;  /* 1: refine_trimap, 0: predict_trimap (pipeline.py:312-321) */
   int32_t chunk;       /* images per pipelined chunk; 0 = choose */
+  int32_t label_bytes; /* host entry points only: 4 (or 0) = int32 label maps as the reference holds them
+                          (graph_builder.py:188); 2 = uint16 label maps -- a compact transport for
+                          PCIe-bound streaming (5 instead of 7 bytes per pixel), widened on the device */
+  int32_t reserved;
   double seed_frac;    /* > 0: repair one-sided trimaps like _seed_from_prior (pipeline.py:149-186,
                           called by segment() with 0.1); 0 = leave the trimap as predicted */
 } gg_path_config;
 
-int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host, int B,
+int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const void* labels_host /*int32 or uint16 [B,H,W]*/, int B,
                         int H, int W, const gg_path_config* cfg, uint8_t* trimap_host /*[B,H,W]*/,
                         int32_t* n_nodes_host /*optional [B]*/, int32_t* n_edges_host /*optional [B]*/);
 
@@ -242,7 +246,7 @@ int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const int32_t* lab
  * batch n+1 overlaps the kernels of batch n.  gg_trimap_path_host == _submit + _wait.
  * The device status is sticky over the calls in flight: _wait reports GG_ERR_CAPACITY if any
  * batch submitted so far overflowed. */
-int gg_trimap_path_host_submit(gg_handle h, const uint8_t* bgr_host, const int32_t* labels_host,
+int gg_trimap_path_host_submit(gg_handle h, const uint8_t* bgr_host, const void* labels_host,
                                int B, int H, int W, const gg_path_config* cfg,
                                uint8_t* trimap_host, int32_t* n_nodes_host,
                                int32_t* n_edges_host, int* ticket);

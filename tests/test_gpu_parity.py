@@ -511,3 +511,19 @@ def test_trimap_path_with_seeding(gg):
     for b in range(B):
         want = trimap_port.seed_from_prior(t_b[b], graphs[b].prior_features, labs[b], graphs[b].n_nodes, 0.1)
         assert np.array_equal(t_a[b], want)
+
+
+def test_trimap_path_uint16_label_transport(gg):
+    """uint16 label maps on the host entry points (gg_path_config.label_bytes = 2) give the
+    same trimaps and counts as the int32 maps of the reference layout."""
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import model_port
+    B, H, W = 9, 131, 150          # odd sizes: the widening kernel's tail path
+    imgs, labs = make_batch(B, H, W, 50, seed0=500)
+    state = model_port.random_state_dict(32, 2, seed=6)
+    path = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=int(labs.max()) + 1, chunk=4)
+    t32, n32, e32 = path(imgs, labs, return_counts=True)
+    t16, n16, e16 = path(imgs, labs.astype(np.uint16), return_counts=True)
+    assert np.array_equal(t32, t16) and np.array_equal(n32, n16) and np.array_equal(e32, e16)
+    p = path.submit(imgs, labs.astype(np.uint16))
+    assert np.array_equal(p.result(), t32)
