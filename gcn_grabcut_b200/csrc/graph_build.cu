@@ -1025,10 +1025,9 @@ k_prior_contrast(const float* __restrict__ st_all, const int* __restrict__ label
   const float* pcy = st + (size_t)ST_PCY * node_cap;
   const float* pcx = st + (size_t)ST_PCX * node_cap;
   const float* cnt = st + (size_t)ST_COUNT * node_cap;
-  // counts.sum() is exact in float32 (integers < 2^24); recompute it per warp
-  float tot = 0.0f;
-  for (int j = lane; j < n; j += 32) tot += cnt[j];
-  tot = fmaxf(warp_sum(tot), 1.0f);
+  // area_w = counts / counts.sum() (graph_builder.py:409): every pixel carries a label, so
+  // counts.sum() is H*W (exact in float32) and area_w is the area ratio k_finalize_regions stored
+  const float* area = st + (size_t)ST_AREA * node_cap;
   const float two_sig2 = (float)(2 * 0.40 * 0.40);   // 2*contrast_sigma**2 as float32
   const float li = mL[i], ai = mA[i], bi = mB[i], yi = pcy[i], xi = pcx[i];
   double s = 0.0;
@@ -1039,8 +1038,7 @@ k_prior_contrast(const float* __restrict__ st_all, const int* __restrict__ label
     const float dy = __fsub_rn(yi, pcy[j]), dx = __fsub_rn(xi, pcx[j]);
     const float sd = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
     const float sw = expf(__fdiv_rn(-__fmul_rn(sd, sd), two_sig2));
-    const float aw = __fdiv_rn(cnt[j], tot);
-    s += (double)__fmul_rn(__fmul_rn(cd, sw), aw);
+    s += (double)__fmul_rn(__fmul_rn(cd, sw), area[j]);
   }
   s = warp_sum(s);
   if (lane == 0) contrast_all[(size_t)b * node_cap + i] = (float)s;

@@ -455,10 +455,33 @@ k_graph_context(const float* __restrict__ z, const int64_t* __restrict__ graph_o
   tot = block_reduce<float>(tot, 0.0f, OpAdd(), sred);
   const float inv = 1.0f / (n_graphs > 1 ? tot + 1e-12f : tot);
   __syncthreads();
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float a = 0.0f;
-    for (int v = v0; v < v1; ++v) a = fmaf(score[v] * inv, z[(size_t)v * D + c], a);
-    s_g[c] = a;
+  // g = sum_v a_v z_v: the nodes are split over the warps (a lane owns channels lane, lane+32,
+  // ...); the per-warp partial sums are combined in a fixed order (deterministic)
+  {
+    __shared__ float s_part[8][256];             // blockDim.x == 256 -> 8 warps, D <= 256
+    float part[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[j] = 0.0f;
+    for (int v = v0 + wid; v < v1; v += nw) {
+      const float a = score[v] * inv;
+      const float* zr = z + (size_t)v * D;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        if (c < D) part[j] = fmaf(a, zr[c], part[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      if (c < D) s_part[wid][c] = part[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float a = 0.0f;
+      for (int w = 0; w < nw; ++w) a += s_part[w][c];
+      s_g[c] = a;
+    }
   }
   __syncthreads();
   for (int u = wid; u < Dh; u += nw) {
