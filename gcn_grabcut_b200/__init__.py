@@ -20,6 +20,7 @@ try:  # torch-dependent names (same guard as the reference's __init__)
     )
     from .pipeline import (guided_filter, refine_trimap, seed_from_prior, TrimapPath, PendingTrimaps,  # noqa: F401
                            shard_range)  # noqa: F401
+    from .dataset import derive_trimap_labels, prepare_sample, prepare_samples  # noqa: F401
     _MODELS_AVAILABLE = True
 except ImportError:  # pragma: no cover
     _MODELS_AVAILABLE = False

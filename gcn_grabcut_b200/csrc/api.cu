@@ -390,6 +390,17 @@ int gg_project_trimap(gg_handle h, const int32_t* labels_dev, const float* probs
                         (cudaStream_t)stream);
 }
 
+int gg_region_labels(gg_handle h, const int32_t* labels_dev, const uint8_t* gt_mask_dev,
+                     const int64_t* node_off_dev, int B, int H, int W, int64_t node_cap_total,
+                     double fg_threshold, double bg_threshold, float* fg_ratio_dev, int64_t* y_dev, void* stream) {
+  GG_REQUIRE(h && labels_dev && gt_mask_dev && node_off_dev && (fg_ratio_dev || y_dev), "gg_region_labels: null argument");
+  GG_REQUIRE(B > 0 && H > 0 && W > 0 && node_cap_total > 0, "gg_region_labels: bad sizes");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_TRY(h->arena.reserve(2 * Arena::padded((size_t)node_cap_total, 4) + 1024));
+  return region_labels(h, h->arena, labels_dev, gt_mask_dev, node_off_dev, B, H, W, node_cap_total, fg_threshold,
+                       bg_threshold, fg_ratio_dev, reinterpret_cast<long long*>(y_dev), (cudaStream_t)stream);
+}
+
 int gg_seed_from_prior(gg_handle h, uint8_t* trimap_dev, const int32_t* labels_dev, const float* x_dev,
                        const int64_t* node_off_dev, int B, int H, int W, int64_t node_cap_total,
                        double seed_frac, void* stream) {

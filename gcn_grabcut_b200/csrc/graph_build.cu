@@ -14,6 +14,8 @@
 // that, given identical region sums, every feature is bit-identical to numpy's.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "pixel_math.cuh"
 #include "graph_build.cuh"
@@ -1315,6 +1317,71 @@ __global__ void k_pixel_planes(const uint8_t* __restrict__ bgr, const double* __
                    (G(y - 1, x - 1) + 2 * G(y - 1, x) + G(y - 1, x + 1));
     o_grad[o] = fsqrt_int((float)(gx * gx + gy * gy));
   }
+}
+
+// ============================================================================ training labels
+// derive_trimap_labels and the fg_ratio of prepare_sample (dataset.py:175-205, 239-249):
+// per region, pixels and ground-truth-foreground pixels are counted exactly (integers; one
+// MATCH.ANY per 32 pixels aggregates equal labels before the atomics), the ratio is formed in
+// float64 like numpy does and thresholded.
+__global__ void __launch_bounds__(256)
+k_mask_counts(const int32_t* __restrict__ labels, const uint8_t* __restrict__ mask,
+              const int64_t* __restrict__ node_off, int HW, int* __restrict__ cnt,
+              int* __restrict__ fg, int* __restrict__ status) {
+  const int b = blockIdx.y;
+  const int64_t n0 = node_off[b];
+  const int n = (int)(node_off[b + 1] - n0);
+  const int lane = threadIdx.x & 31;
+  const int32_t* l = labels + (size_t)b * HW;
+  const uint8_t* m = mask + (size_t)b * HW;
+  for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < HW; i0 += gridDim.x * blockDim.x) {
+    const int i = i0 + lane;
+    const bool in = i < HW;
+    const int lab = in ? l[i] : -1;
+    const bool ok = in && lab >= 0 && lab < n;
+    if (in && !ok) atomicOr(status, ST_LABEL_RANGE);
+    const unsigned act = __ballot_sync(0xffffffffu, ok);
+    const unsigned fgm = __ballot_sync(0xffffffffu, ok && m[i] > 0);
+    if (ok) {
+      const unsigned grp = __match_any_sync(act, lab);
+      if (lane == __ffs(grp) - 1) {
+        atomicAdd(&cnt[n0 + lab], __popc(grp));
+        const int f = __popc(grp & fgm);
+        if (f) atomicAdd(&fg[n0 + lab], f);
+      }
+    }
+  }
+}
+
+__global__ void k_region_labels(const int* __restrict__ cnt, const int* __restrict__ fg,
+                                const int64_t* __restrict__ node_off, int n_graphs, double fg_thr,
+                                double bg_cut, float* __restrict__ fg_ratio, long long* __restrict__ y) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= node_off[n_graphs]) return;
+  const double c = (double)cnt[v];
+  const double ratio = (double)fg[v] / fmax(c, 1.0);
+  long long lab = 1;                       // CLASS_UNK
+  if (ratio >= fg_thr) lab = 2;            // CLASS_FG
+  if (ratio <= bg_cut) lab = 0;            // CLASS_BG (assigned second in the reference: wins)
+  if (cnt[v] == 0) lab = 1;
+  if (fg_ratio) fg_ratio[v] = (float)ratio;
+  if (y) y[v] = lab;
+}
+
+int region_labels(gg_context* ctx, Arena& ar, const int32_t* labels, const uint8_t* mask,
+                  const int64_t* node_off, int B, int H, int W, long long node_cap_total,
+                  double fg_thr, double bg_thr, float* fg_ratio, long long* y, cudaStream_t st) {
+  const int HW = H * W;
+  int* cnt = ar.take<int>((size_t)node_cap_total);
+  int* fg = ar.take<int>((size_t)node_cap_total);
+  GG_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)node_cap_total * sizeof(int), st));
+  GG_CUDA_OK(cudaMemsetAsync(fg, 0, (size_t)node_cap_total * sizeof(int), st));
+  GG_CUDA_OK(cudaMemsetAsync(ctx->status_word, 0, sizeof(int), st));
+  dim3 grid(std::min(ceil_div(HW, 256), 148), B);
+  GG_LAUNCH(ctx, k_mask_counts, grid, 256, 0, st, labels, mask, node_off, HW, cnt, fg, ctx->status_word);
+  GG_LAUNCH(ctx, k_region_labels, ceil_div(node_cap_total, 256), 256, 0, st, cnt, fg, node_off, B, fg_thr,
+            1.0 - bg_thr, fg_ratio, y);
+  return GG_OK;
 }
 
 // ============================================================================ self test

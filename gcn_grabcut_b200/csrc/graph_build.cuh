@@ -26,6 +26,11 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
 int pixel_planes(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, int W, float* lab,
                  float* hsv, float* gray, float* grad, cudaStream_t st);
 
+// derive_trimap_labels / fg_ratio (dataset.py:175-205, 239-249) for a batch of label maps + masks
+int region_labels(gg_context* ctx, Arena& ar, const int32_t* labels, const uint8_t* mask,
+                  const int64_t* node_off, int B, int H, int W, long long node_cap_total,
+                  double fg_thr, double bg_thr, float* fg_ratio, long long* y, cudaStream_t st);
+
 // float32 fast paths of pixel_math.cuh vs the IEEE intrinsics; mismatches[4] (see k_selftest_math)
 int selftest_math(gg_context* ctx, Arena& ar, long long* mismatches, cudaStream_t st);
 

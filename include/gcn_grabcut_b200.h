@@ -200,6 +200,19 @@ int gg_project_trimap(gg_handle h, const int32_t* labels_dev, const float* probs
                       const int64_t* node_off_dev, int B, int H, int W, float thr_fg,
                       float thr_bg, uint8_t* trimap_dev, void* stream);
 
+/* ------------------------------------------------------------------ training-data labels
+ * derive_trimap_labels(segments, gt_mask, fg_threshold, bg_threshold) and the fg_ratio tensor of
+ * prepare_sample (dataset.py:175-205, 239-249), batched: gt_mask_dev uint8 [B,H,W] (> 0 =
+ * foreground).  Per node (rows as gg_graph_out.x, image b at node_off[b]):
+ *   fg_ratio = #foreground pixels / max(#pixels, 1)   (float64 quotient, stored as float32)
+ *   y        = 2 (FG) if fg_ratio >= fg_threshold; 0 (BG) if fg_ratio <= 1 - bg_threshold (BG is
+ *              assigned second and wins); 1 (UNK) otherwise and for regions without pixels.
+ * Either output may be NULL.  A label outside [0, n_nodes[b]) sets the device status word. */
+int gg_region_labels(gg_handle h, const int32_t* labels_dev, const uint8_t* gt_mask_dev,
+                     const int64_t* node_off_dev, int B, int H, int W, int64_t node_cap_total,
+                     double fg_threshold, double bg_threshold, float* fg_ratio_dev /*[SN]*/,
+                     int64_t* y_dev /*[SN]*/, void* stream);
+
 /* _seed_from_prior(trimap, graph, seed_frac) (pipeline.py:149-186), batched and in place: an image
  * whose trimap has no foreground label (1, 3) gets its max(1, round(seed_frac * n_nodes)) regions
  * with the largest foreground prior (node_input column 16) set to GC_PR_FGD; likewise the

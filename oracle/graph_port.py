@@ -299,3 +299,20 @@ def build_graph(bgr: np.ndarray, seg: np.ndarray, connectivity: int = 4,
         edge_attr=edge_attr, n_nodes=n, n_edges=edge_index.shape[1],
         node_centroids=st["centroids"], prior_features=prior,
         node_areas=st["area_ratio"], stages=stages)
+
+
+# ----------------------------------------------------------------------------- training labels
+def derive_trimap_labels(segments: np.ndarray, gt_mask: np.ndarray, fg_threshold: float = 0.75,
+                         bg_threshold: float = 0.75):
+    """dataset.py:175-205 (labels) and :239-249 (fg_ratio of prepare_sample): per-region foreground
+    coverage by exact counts; returns (labels int64 (N,), fg_ratio float32 (N,))."""
+    n_nodes = int(segments.max()) + 1
+    flat = segments.ravel()
+    counts = np.bincount(flat, minlength=n_nodes).astype(np.float64)
+    fg_sum = np.bincount(flat, weights=(gt_mask.ravel() > 0).astype(np.float64), minlength=n_nodes)
+    fg_ratio = fg_sum / np.maximum(counts, 1.0)
+    labels = np.full(n_nodes, 1, dtype=np.int64)
+    labels[fg_ratio >= fg_threshold] = 2
+    labels[fg_ratio <= 1 - bg_threshold] = 0
+    labels[counts == 0] = 1
+    return labels, fg_ratio.astype(np.float32)

@@ -527,3 +527,42 @@ def test_trimap_path_uint16_label_transport(gg):
     assert np.array_equal(t32, t16) and np.array_equal(n32, n16) and np.array_equal(e32, e16)
     p = path.submit(imgs, labs.astype(np.uint16))
     assert np.array_equal(p.result(), t32)
+
+
+# ----------------------------------------------------------------------------- training-data labels
+def test_region_labels_vs_reference_golden(gg):
+    """derive_trimap_labels / prepare_samples (gg_region_labels) against the reference's own
+    dataset.py outputs (tests/golden/handoff/region_labels.npz): labels, fg_ratio and edge lists
+    bit-exact, features within the feature tolerance; batched == per image."""
+    import os
+    from gcn_grabcut_b200.synthetic import geometric_sample, slic_like_labels
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "handoff", "region_labels.npz"))
+    cases = sorted({k.split("/")[0] for k in z.files})
+    for name in cases:
+        H, W, seed, nseg = (int(v) for v in z[f"{name}/meta"])
+        img, mask = geometric_sample(H, W, seed)
+        seg = slic_like_labels(H, W, nseg, seed)
+        for key in [k for k in z.files if k.startswith(f"{name}/labels/")]:
+            fg_thr, bg_thr = (float(v) for v in key.split("/")[-1].split("_"))
+            got = gg.derive_trimap_labels(seg, mask, fg_thr, bg_thr)
+            assert got.dtype == np.int64 and np.array_equal(got, z[key]), key
+        data, y, segments = gg.prepare_sample({"image": img, "gt_mask": mask},
+                                              gg.SuperpixelGraphConfig(n_segments=nseg), segments=seg)
+        assert np.array_equal(segments, seg) and y is data.y
+        assert data.y.dtype == torch.int64 and np.array_equal(data.y.numpy(), z[f"{name}/y"])
+        assert data.fg_ratio.dtype == torch.float32 and np.array_equal(data.fg_ratio.numpy(), z[f"{name}/fg_ratio"])
+        assert np.array_equal(data.edge_index.numpy(), z[f"{name}/edge_index"])
+        np.testing.assert_allclose(data.x.numpy(), z[f"{name}/x"], rtol=FEAT_RTOL, atol=FEAT_ATOL)
+        np.testing.assert_allclose(data.node_area.numpy(), z[f"{name}/node_area"], rtol=1e-6)
+    # batched form, images of one shape: against the oracle per image
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import graph_port
+    B, H, W, nseg = 7, 144, 176, 60
+    imgs, labs = make_batch(B, H, W, nseg, seed0=900)
+    masks = np.stack([geometric_sample(H, W, 900 + b)[1] for b in range(B)])
+    res = gg.prepare_samples(imgs, masks, labs, gg.SuperpixelGraphConfig(n_segments=nseg))
+    assert len(res) == B
+    for b, (data, y, segm) in enumerate(res):
+        want_y, want_r = graph_port.derive_trimap_labels(labs[b], masks[b], 0.70, 0.70)
+        assert np.array_equal(y.numpy(), want_y) and np.array_equal(data.fg_ratio.numpy(), want_r)
+        assert data.x.shape == (len(want_y), 19) and np.array_equal(segm, labs[b])

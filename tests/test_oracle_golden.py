@@ -152,3 +152,24 @@ def test_seed_from_prior_port_matches_reference():
                     assert not np.array_equal(got, tri)
                 n_checked += 1
     assert n_checked == 30
+
+
+def test_region_labels_port_matches_reference():
+    """oracle.graph_port.derive_trimap_labels against the reference's derive_trimap_labels and
+    prepare_sample outputs (tests/golden/make_golden_labels.py): labels and fg_ratio bit-exact."""
+    import os
+    from gcn_grabcut_b200.synthetic import geometric_sample, slic_like_labels
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "handoff", "region_labels.npz"))
+    cases = sorted({k.split("/")[0] for k in z.files})
+    assert len(cases) == 3
+    for name in cases:
+        H, W, seed, nseg = (int(v) for v in z[f"{name}/meta"])
+        mask = geometric_sample(H, W, seed)[1]
+        seg = slic_like_labels(H, W, nseg, seed)
+        for key in [k for k in z.files if k.startswith(f"{name}/labels/")]:
+            fg_thr, bg_thr = (float(v) for v in key.split("/")[-1].split("_"))
+            labels, _ = graph_port.derive_trimap_labels(seg, mask, fg_thr, bg_thr)
+            assert labels.dtype == np.int64 and np.array_equal(labels, z[key]), key
+        labels, ratio = graph_port.derive_trimap_labels(seg, mask, 0.70, 0.70)
+        assert np.array_equal(labels, z[f"{name}/y"]) and np.array_equal(ratio, z[f"{name}/fg_ratio"])
+        assert set(np.unique(labels)) <= {0, 1, 2} and len(np.unique(labels)) >= 2
