@@ -1435,6 +1435,20 @@ int selftest_math(gg_context* ctx, Arena& ar, long long* mismatches, cudaStream_
 }
 
 // ============================================================================ host driver
+// Slots of the per-image adjacency hash table.  Only ADJACENCY pairs live in it (the non-local
+// pairs are produced later, sorted, without a table): a 4-connected label map is a planar graph
+// (< 3 N pairs), the diagonals of 8-connectivity add at most one crossing pair per pixel corner,
+// far below 8 N in practice -- so the table is sized for the adjacency share of pair_cap, not for
+// a multiple of the full pair capacity (which grows with n_nonlocal).  An overflow is reported (ST_PAIR_TABLE).
+static int next_pow2(int v);
+static int adjacency_table_slots(int node_cap, int pair_cap, int k_nonlocal) {
+  // what the caller's pair capacity leaves for adjacency once every node has its k non-local
+  // pairs, but at least 8 N (a caller with unusual label maps raises pair_cap)
+  const long long adj_cap = std::min<long long>(
+      pair_cap, std::max<long long>(8ll * node_cap, (long long)pair_cap - (long long)node_cap * k_nonlocal));
+  return next_pow2((int)std::max<long long>(2 * adj_cap, 64));
+}
+
 // strip height of k_region_stats: the image is cut into equal strips of about 107 rows (every
 // strip boundary costs one hand-over per column; shorter strips give more warps)
 static int rs_rows(int H) {
@@ -1450,7 +1464,7 @@ static int next_pow2(int v) {
 }
 
 size_t graph_workspace_bytes(int B, int H, int W, const gg_graph_config& cfg) {
-  const int nc = cfg.node_cap, pc = cfg.pair_cap, tc = next_pow2(4 * pc);
+  const int nc = cfg.node_cap, pc = cfg.pair_cap, tc = adjacency_table_slots(nc, pc, cfg.n_nonlocal);
   const int k = cfg.n_nonlocal > 0 ? cfg.n_nonlocal : 1;
   size_t s = 0;
   s += Arena::padded((size_t)B * H * W, 1);                 // gray
@@ -1492,7 +1506,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
              "build_graphs: a mandatory output pointer is NULL");
   GG_REQUIRE((long long)B * 2 * cfg.pair_cap < (1ll << 31) && (long long)B * cfg.node_cap < (1ll << 31),
              "build_graphs: batch too large for 32-bit CSR ids");
-  const int nc = cfg.node_cap, pc = cfg.pair_cap, tc = next_pow2(4 * pc);
+  const int nc = cfg.node_cap, pc = cfg.pair_cap, tc = adjacency_table_slots(nc, pc, cfg.n_nonlocal);
   const int k = cfg.n_nonlocal;
 
   // coordinate tables: a function of (H, W) alone, kept in the handle between calls.  A change of
