@@ -835,6 +835,93 @@ k_knn_sel(const float* __restrict__ st_all, const int* __restrict__ label_max,
     for (; r < k; ++r) out[r] = -1;
 }
 
+// The same selection for images with up to 2048 regions (T = 32 or 64 distances per lane): the
+// distances live in shared memory (one padded row per lane), every lane keeps only its current
+// minimum in registers, and after a round only the WINNER's minimum is recomputed -- by the whole
+// warp, from the winner's row -- instead of every lane rescanning its T registers.  Rounds cost
+// ~60 instructions instead of ~5 T.  Same result as k_knn_sel / k_knn.
+template <int T>
+__global__ void __launch_bounds__(256)
+k_knn_sel_smem(const float* __restrict__ st_all, const int* __restrict__ label_max,
+               const int2* __restrict__ pairs_all, const int* __restrict__ start_all,
+               int* __restrict__ picks_all, int node_cap, int pair_cap, int k) {
+  static_assert(T % 32 == 0, "T is a multiple of the warp size");
+  extern __shared__ float knn_smem[];
+  constexpr int LD = T + 1;                               // odd row length: conflict-free both ways
+  const int b = blockIdx.y;
+  const int n = min(label_max[b] + 1, node_cap);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (i >= n) return;
+  float* rows = knn_smem + (size_t)wid * 32 * LD;         // rows[lane][t]: distance to region lane + 32 t
+  float* mine = rows + lane * LD;
+  const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
+  const float* mL = st + (size_t)ST_MEAN_L * node_cap;
+  const float* mA = mL + node_cap;
+  const float* mB = mA + node_cap;
+  const int2* pairs = pairs_all + (size_t)b * pair_cap;
+  const int* start = start_all + (size_t)b * (node_cap + 1);
+  const float INF = __int_as_float(0x7f800000);
+  const float li = mL[i], ai = mA[i], bi = mB[i];
+  float md = INF;
+  int mt = 0;
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    const int j = lane + 32 * t;
+    float d = INF;
+    if (j < n && j != i) {
+      const float dx = __fsub_rn(li, mL[j]), dy = __fsub_rn(ai, mA[j]), dz = __fsub_rn(bi, mB[j]);
+      d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      if (!(d < INF)) d = INF;      // inf / nan never selected (np.isfinite filter, …:346)
+    }
+    mine[t] = d;
+    if (d < md) { md = d; mt = t; }   // strict '<': lowest index among equal distances
+  }
+  __syncwarp();
+  int* out = picks_all + ((size_t)b * node_cap + i) * k;
+  int r = 0;
+  while (r < k) {
+    float d = md;
+    int j = md < INF ? lane + 32 * mt : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+      if (knn_less(od, oj, d, j)) { d = od; j = oj; }
+    }
+    if (!(d < INF)) break;          // fewer than k finite candidates
+    const int wl = j & 31;
+    if (lane == wl) mine[j >> 5] = INF;                  // retire the winner
+    __syncwarp();
+    {
+      // the winner's new minimum, computed by the whole warp from the winner's row
+      const float* wrow = rows + wl * LD;
+      float cd = INF;
+      int ct = 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < T / 32; ++u) {
+        const float v = wrow[lane + 32 * u];
+        if (v < cd) { cd = v; ct = lane + 32 * u; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, cd, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, ct, o);
+        if (knn_less(od, ot, cd, ct)) { cd = od; ct = ot; }
+      }
+      if (lane == wl) { md = cd; mt = cd < INF ? ct : 0; }
+    }
+    const int lo = min(i, j), hi = max(i, j);
+    bool found = false;
+    for (int q = start[lo] + lane; q < start[lo + 1]; q += 32) found |= pairs[q].y == hi;
+    if (__any_sync(0xffffffffu, found)) continue;        // spatially adjacent: excluded
+    if (lane == 0) out[r] = j;
+    ++r;
+  }
+  if (lane == 0)
+    for (; r < k; ++r) out[r] = -1;
+}
+
 // ============================================================================ S4
 // Symmetrise the picks into sorted unique (lo,hi) pairs (graph_builder.py:348-350).
 __global__ void __launch_bounds__(512)
@@ -1596,8 +1683,14 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     if (!knn_legacy && nc <= 2048) {
       if (nc <= 320) GG_LAUNCH(ctx, k_knn_sel<10>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
       else if (nc <= 512) GG_LAUNCH(ctx, k_knn_sel<16>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
-      else if (nc <= 1024) GG_LAUNCH(ctx, k_knn_sel<32>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
-      else GG_LAUNCH(ctx, k_knn_sel<64>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
+      else if (nc <= 1024) {
+        const size_t smem = (size_t)8 * 32 * (32 + 1) * sizeof(float);
+        GG_LAUNCH(ctx, k_knn_sel_smem<32>, grid, 256, smem, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
+      } else {
+        const size_t smem = (size_t)8 * 32 * (64 + 1) * sizeof(float);
+        GG_SMEM_ATTR_ONCE(ctx, 41, k_knn_sel_smem<64>, smem);
+        GG_LAUNCH(ctx, k_knn_sel_smem<64>, grid, 256, smem, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
+      }
     } else if (k <= 4) GG_TRY(launch_knn<4>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
     else if (k <= 8) GG_TRY(launch_knn<8>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));
     else if (k <= 16) GG_TRY(launch_knn<16>(ctx, st, grid, stats, label_max, pairs, start_adj, picks, nc, pc, k));

@@ -120,7 +120,7 @@ def test_graph_builder_vs_golden(gg, name):
 
 @pytest.mark.parametrize("conn,k,H,W,nseg", [(4, 4, 320, 480, 300), (8, 4, 200, 264, 120),
                                              (4, 8, 240, 320, 200), (4, 0, 128, 160, 60),
-                                             (4, 16, 161, 203, 90)])
+                                             (4, 16, 161, 203, 90), (4, 8, 300, 420, 700)])
 def test_graph_batch_vs_oracle(gg, conn, k, H, W, nseg):
     from gcn_grabcut_b200.synthetic import make_batch
     B = 6
