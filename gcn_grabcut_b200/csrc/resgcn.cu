@@ -499,6 +499,103 @@ k_graph_context(const float* __restrict__ z, const int64_t* __restrict__ graph_o
   }
 }
 
+// The same readout for large graphs, split over many blocks (a graph of 10^4 regions on one
+// block leaves the GPU idle): scores + per-graph maximum (ordered-int atomicMax), then partial
+// softmax sums per (graph, block) written to scratch, then one block per graph adds the partials
+// in a fixed order (deterministic) and applies the two small linear layers.
+GG_D int float_to_ordered(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+GG_D float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void __launch_bounds__(256)
+k_ctx_scores(const float* __restrict__ z, const int* __restrict__ node_graph, const float* __restrict__ wb,
+             NetOffsets o, const int* __restrict__ sizes, float* __restrict__ score, int* __restrict__ gmax) {
+  const int D = o.D, lane = threadIdx.x & 31;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (v >= sizes[0]) return;
+  float s = 0.0f;
+  for (int c = lane; c < D; c += 32) s = fmaf(wb[o.attn_w + c], z[(size_t)v * D + c], s);
+  s = warp_sum(s) + wb[o.attn_b];
+  if (lane == 0) {
+    score[v] = s;
+    atomicMax(&gmax[node_graph[v]], float_to_ordered(s));
+  }
+}
+
+constexpr int CTX_PARTS = 32;     // blocks per graph in the partial-sum pass
+
+__global__ void __launch_bounds__(256)
+k_ctx_partial(const float* __restrict__ z, const int64_t* __restrict__ graph_off, const float* __restrict__ score,
+              const int* __restrict__ gmax, int D, float* __restrict__ part /*[G][PARTS][D+1]*/) {
+  __shared__ float s_part[8][257];
+  const int g = blockIdx.y, pb = blockIdx.x;
+  const int v0 = (int)graph_off[g], v1 = (int)graph_off[g + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const float mx = ordered_to_float(gmax[g]);
+  float acc[8], tot = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  // node v of the graph belongs to part (v - v0) / span, warp (v - v0) % 8 within the part
+  const int span = (v1 - v0 + CTX_PARTS - 1) / CTX_PARTS;
+  const int lo = v0 + pb * span, hi = min(v1, lo + span);
+  for (int v = lo + wid; v < hi; v += 8) {
+    const float e = expf(score[v] - mx);
+    tot += e;
+    const float* zr = z + (size_t)v * D;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      if (c < D) acc[j] = fmaf(e, zr[c], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane + 32 * j;
+    if (c < D) s_part[wid][c] = acc[j];
+  }
+  if (lane == 0) s_part[wid][256] = tot;
+  __syncthreads();
+  float* out = part + ((size_t)g * CTX_PARTS + pb) * (D + 1);
+  for (int c = threadIdx.x; c <= D; c += blockDim.x) {
+    const int col = c < D ? c : 256;
+    float a = 0.0f;
+    for (int w = 0; w < 8; ++w) a += s_part[w][col];
+    out[c] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_ctx_finish(const float* __restrict__ part, const float* __restrict__ wb, NetOffsets o, int n_graphs,
+             float* __restrict__ gvec) {
+  extern __shared__ float sm[];
+  const int D = o.D, Dh = D / 2;
+  float* s_g = sm;            // [D]
+  float* s_c = sm + D;        // [Dh]
+  __shared__ float s_tot;
+  const int g = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* pg = part + (size_t)g * CTX_PARTS * (D + 1);
+  for (int c = threadIdx.x; c <= D; c += blockDim.x) {
+    float a = 0.0f;
+    for (int pb = 0; pb < CTX_PARTS; ++pb) a += pg[(size_t)pb * (D + 1) + c];
+    if (c < D) s_g[c] = a; else s_tot = a;
+  }
+  __syncthreads();
+  const float inv = 1.0f / (n_graphs > 1 ? s_tot + 1e-12f : s_tot);
+  for (int u = wid; u < Dh; u += nw) {
+    float s = 0.0f;
+    for (int c = lane; c < D; c += 32) s = fmaf(wb[o.cmp_w + (size_t)u * D + c], s_g[c] * inv, s);
+    s = warp_sum(s);
+    if (lane == 0) s_c[u] = fmaxf(s + wb[o.cmp_b + u], 0.0f);
+  }
+  __syncthreads();
+  for (int c = wid; c < D; c += nw) {
+    float s = 0.0f;
+    for (int u = lane; u < Dh; u += 32) s = fmaf(wb[o.exp_w + (size_t)c * Dh + u], s_c[u], s);
+    s = warp_sum(s);
+    if (lane == 0) gvec[(size_t)g * D + c] = sigmoidf(s + wb[o.exp_b + c]);
+  }
+}
+
 // ------------------------------------------------------------------ head
 // logits = W_h f + b_h; probs = softmax(logits)   (model.py:536, 543-546); warp per node
 __global__ void __launch_bounds__(256)
@@ -710,6 +807,7 @@ size_t resgcn_workspace_bytes(const NetWeights& nw, long long node_cap, long lon
   s += Arena::padded((size_t)node_cap * c, 4);          // ctx
   s += Arena::padded((size_t)node_cap, 4) * 3;          // node_graph, dinv, score
   s += Arena::padded((size_t)n_graphs * D, 4);          // gvec
+  s += Arena::padded((size_t)n_graphs, 4) + Arena::padded((size_t)n_graphs * 32 * (D + 1), 4);   // split readout
   s += 4096;
   return s;
 }
@@ -753,6 +851,8 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   float* dinv = ar.take<float>((size_t)node_cap);
   float* score = ar.take<float>((size_t)node_cap);
   float* gvec = ar.take<float>((size_t)n_graphs * D);
+  int* ctx_gmax = ar.take<int>((size_t)n_graphs);
+  float* ctx_part = ar.take<float>((size_t)n_graphs * CTX_PARTS * (D + 1));
   int* sizes = ar.take<int>(64);
   const int* n_nodes_p = sizes;
   const int* n_edges_p = sizes + 1;
@@ -831,7 +931,16 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   // ---- global context, fuse, head
   {
     const size_t smem = (size_t)(D + D / 2) * sizeof(float);
-    GG_LAUNCH(ctx, k_graph_context, n_graphs, 256, smem, st, z, graph_off, wb, o, n_graphs, score, gvec);
+    if (ceil_div(node_cap, n_graphs) <= 1024) {
+      GG_LAUNCH(ctx, k_graph_context, n_graphs, 256, smem, st, z, graph_off, wb, o, n_graphs, score, gvec);
+    } else {
+      // large graphs: the readout is split over CTX_PARTS blocks per graph
+      GG_CUDA_OK(cudaMemsetAsync(ctx_gmax, 0x80, (size_t)n_graphs * sizeof(int), st));   // ordered(-huge)
+      GG_LAUNCH(ctx, k_ctx_scores, warp_blocks, 256, 0, st, z, node_graph, wb, o, sizes, score, ctx_gmax);
+      dim3 grid(CTX_PARTS, n_graphs);
+      GG_LAUNCH(ctx, k_ctx_partial, grid, 256, 0, st, z, graph_off, score, ctx_gmax, D, ctx_part);
+      GG_LAUNCH(ctx, k_ctx_finish, n_graphs, 256, smem, st, ctx_part, wb, o, n_graphs, gvec);
+    }
   }
   if (use_tc && gemm_tc_supported(ctx, GEMM_FUSE, D, D) && D == 128) {
     TcPrologue pro;                                     // z * gvec[graph] -> LayerNorm fused into the A producer
