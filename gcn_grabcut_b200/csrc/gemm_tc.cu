@@ -125,8 +125,8 @@ GG_HD uint32_t sw128_offset(int r, int k, int rows) {
 template <int ACT, int PRO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const float* __restrict__ bias,
-          float* __restrict__ C, const int* __restrict__ m_ptr, int N, int K, int accumulate,
-          const TcPrologue pro) {
+          float* __restrict__ C, const int* __restrict__ m_ptr, int N, int K, int lda, int ldc,
+          int accumulate, const TcPrologue pro) {
   extern __shared__ unsigned char tc_smem_raw[];
   const int M = *m_ptr;
   const int n_tiles = (M + TC_BM - 1) / TC_BM;
@@ -226,7 +226,7 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (i < n_pass) {
             const int row = row0 + warp * RPW + i * rpp + sub;
-            if (row < M) v[i] = __ldg(reinterpret_cast<const float4*>(A + (size_t)row * K) + ch);
+            if (row < M) v[i] = __ldg(reinterpret_cast<const float4*>(A + (size_t)row * lda) + ch);
           }
         }
         if (PRO == 1) {
@@ -333,7 +333,7 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
           if (lane == 0) mbar_arrive(bar_free0 + 8 * s_);
         }
         if (row < M) {
-          float* crow = C + (size_t)row * N + col0;
+          float* crow = C + (size_t)row * ldc + col0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 o;
@@ -367,11 +367,12 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
 // ----------------------------------------------------------------------------- host side
 static size_t tc_image_bytes(int N, int K) { return (size_t)3 * (K / 64) * N * 128; }
 
-static void pack_weight(const float* W, int N, int K, uint8_t* img) {
+// image of the N x K block of W (row stride ldw) that starts at W
+static void pack_weight(const float* W, int ldw, int N, int K, uint8_t* img) {
   const size_t split = (size_t)(K / 64) * N * 128;
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
-      float r = W[(size_t)n * K + k];
+      float r = W[(size_t)n * ldw + k];
       const uint32_t off = sw128_offset(n, k, N);
       for (int s = 0; s < 3; ++s) {
         uint32_t u;
@@ -386,9 +387,12 @@ static void pack_weight(const float* W, int N, int K, uint8_t* img) {
     }
 }
 
+// Widths of 256 are handled as 2 x 2 blocks of 128 (one launch per block, the second K block
+// accumulates into C): the kernel itself sees N, K in {64, 128} and row strides lda / ldc.
 static bool tc_shape_ok(int N, int K) {
-  return (K == 64 || K == 128) && (N == 64 || N == 128);
+  return (K == 64 || K == 128 || K == 256) && (N == 64 || N == 128 || N == 256);
 }
+static int tc_chunk(int dim) { return dim > 128 ? 128 : dim; }
 
 int gemm_tc_prepare_weights(gg_context* ctx, const std::vector<float>& blob) {
   NetWeights& nw = ctx->net;
@@ -403,11 +407,22 @@ int gemm_tc_prepare_weights(gg_context* ctx, const std::vector<float>& blob) {
   for (int l = 0; l < nw.n_layers; ++l) items.push_back({GEMM_GCN0 + l, nw.gcn_w[l], D, D});
   size_t total = 0;
   for (auto& it : items)
-    if (tc_shape_ok(it.N, it.K)) { nw.tc_off[it.which] = total; total += (tc_image_bytes(it.N, it.K) + 1023) & ~size_t(1023); }
+    if (tc_shape_ok(it.N, it.K)) {
+      const int Nc = tc_chunk(it.N), Kc = tc_chunk(it.K);
+      nw.tc_off[it.which] = total;
+      total += (size_t)(it.N / Nc) * (it.K / Kc) * ((tc_image_bytes(Nc, Kc) + 1023) & ~size_t(1023));
+    }
   if (total == 0) return GG_OK;
   std::vector<uint8_t> host(total, 0);
   for (auto& it : items)
-    if (tc_shape_ok(it.N, it.K)) pack_weight(blob.data() + it.w_off, it.N, it.K, host.data() + nw.tc_off[it.which]);
+    if (tc_shape_ok(it.N, it.K)) {
+      const int Nc = tc_chunk(it.N), Kc = tc_chunk(it.K), nK = it.K / Kc;
+      const size_t one = (tc_image_bytes(Nc, Kc) + 1023) & ~size_t(1023);
+      for (int nb = 0; nb < it.N / Nc; ++nb)
+        for (int kb = 0; kb < nK; ++kb)
+          pack_weight(blob.data() + it.w_off + (size_t)nb * Nc * it.K + (size_t)kb * Kc, it.K, Nc, Kc,
+                      host.data() + nw.tc_off[it.which] + (size_t)(nb * nK + kb) * one);
+    }
   GG_CUDA_OK(cudaMalloc(&nw.tc_blob, total));
   GG_CUDA_OK(cudaMemcpy(nw.tc_blob, host.data(), total, cudaMemcpyHostToDevice));
   nw.tc_bytes = total;
@@ -420,24 +435,18 @@ bool gemm_tc_supported(const gg_context* ctx, int which, int N, int K) {
          nw.tc_off[which] != (size_t)-1 && tc_shape_ok(N, K);
 }
 
-int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* bias, float* C,
-            const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate,
-            const TcPrologue* prologue) {
-  const NetWeights& nw = ctx->net;
-  const uint8_t* img = reinterpret_cast<const uint8_t*>(nw.tc_blob) + nw.tc_off[which];
+static int gemm_tc_block(gg_context* ctx, cudaStream_t st, const uint8_t* img, const float* A, const float* bias,
+                         float* C, const int* m_ptr, long long m_cap, int N, int K, int lda, int ldc, int act,
+                         int accumulate, const TcPrologue& pro) {
   const size_t smem = (size_t)3 * (K / 64) * TC_BM * 128 + tc_image_bytes(N, K) + 64 + 512 + 1024;
   const size_t smem_max = (size_t)3 * 2 * TC_BM * 128 + tc_image_bytes(128, 128) + 64 + 512 + 1024;   // K = N = 128
   const int tiles_cap = ceil_div(m_cap, TC_BM);
   const int grid = tiles_cap < ctx->sm_count ? tiles_cap : ctx->sm_count;
-  TcPrologue pro{};
-  if (prologue) pro = *prologue;
-  GG_REQUIRE(pro.mode == 0 || (pro.mode == 1 && K == 128) || (pro.mode == 2 && K == 64),
-             "gemm_tc: unsupported prologue for K=%d", K);
 #define GG_TC_CASE(ACT_, PRO_, BIT_)                                                               \
   if (act == ACT_ && pro.mode == PRO_) {                                                          \
     GG_SMEM_ATTR_ONCE(ctx, BIT_, (k_tc_gemm<ACT_, PRO_>), smem_max);                              \
     GG_LAUNCH(ctx, (k_tc_gemm<ACT_, PRO_>), grid, TC_THREADS, smem, st, A, img, bias, C, m_ptr, N, \
-              K, accumulate, pro);                                                                \
+              K, lda, ldc, accumulate, pro);                                                      \
     return GG_OK;                                                                                 \
   }
   GG_TC_CASE(0, 0, 16) GG_TC_CASE(1, 0, 17) GG_TC_CASE(2, 0, 18)
@@ -445,6 +454,29 @@ int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const f
 #undef GG_TC_CASE
   set_error("gemm_tc: unsupported act/prologue combination %d/%d", act, pro.mode);
   return GG_ERR_INVALID;
+}
+
+int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* bias, float* C,
+            const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate,
+            const TcPrologue* prologue) {
+  const NetWeights& nw = ctx->net;
+  const uint8_t* img0 = reinterpret_cast<const uint8_t*>(nw.tc_blob) + nw.tc_off[which];
+  TcPrologue pro{};
+  if (prologue) pro = *prologue;
+  const int Nc = tc_chunk(N), Kc = tc_chunk(K), nN = N / Nc, nK = K / Kc;
+  GG_REQUIRE(pro.mode == 0 || (pro.mode == 1 && K == 128) || (pro.mode == 2 && K == 64),
+             "gemm_tc: unsupported prologue for K=%d", K);
+  const size_t one = (tc_image_bytes(Nc, Kc) + 1023) & ~size_t(1023);
+  const int lda = pro.mode == 2 ? 5 : K;
+  for (int nb = 0; nb < nN; ++nb)
+    for (int kb = 0; kb < nK; ++kb) {
+      const bool last = kb == nK - 1;
+      // bias and activation belong to the finished sum: the last K block applies them
+      GG_TRY(gemm_tc_block(ctx, st, img0 + (size_t)(nb * nK + kb) * one, A + (size_t)kb * Kc,
+                           last && bias ? bias + (size_t)nb * Nc : nullptr, C + (size_t)nb * Nc, m_ptr, m_cap, Nc,
+                           Kc, lda, N, last ? act : 0, (kb > 0 || accumulate) ? 1 : 0, pro));
+    }
+  return GG_OK;
 }
 
 }  // namespace gg

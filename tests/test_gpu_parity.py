@@ -566,3 +566,37 @@ def test_region_labels_vs_reference_golden(gg):
         want_y, want_r = graph_port.derive_trimap_labels(labs[b], masks[b], 0.70, 0.70)
         assert np.array_equal(y.numpy(), want_y) and np.array_equal(data.fg_ratio.numpy(), want_r)
         assert data.x.shape == (len(want_y), 19) and np.array_equal(segm, labs[b])
+
+
+@pytest.mark.parametrize("D", [64, 256])
+def test_resgcn_other_widths_tc_vs_simt_vs_oracle(gg, D):
+    """Hidden widths other than 128: D = 256 runs the tcgen05 transforms as 2 x 2 blocks of 128
+    (strided launches, the second K block accumulates), D = 64 as single 64-wide blocks; both
+    against the SIMT fp32 transforms and the oracle."""
+    from gcn_grabcut_b200 import _native as nat
+    from oracle import model_port
+    state = model_port.random_state_dict(D, 3, seed=8)
+    net = gg.ResGCNNet(hidden_channels=D, n_layers=3)
+    net.load_state_dict(state)
+    net = net.to("cuda").eval()
+    gen = torch.Generator().manual_seed(11)
+    N = 700                                      # several 128-row tiles, a ragged last one
+    x = torch.randn(N, 19, generator=gen)
+    s = torch.randint(0, N, (4 * N,), generator=gen)
+    d = torch.randint(0, N, (4 * N,), generator=gen)
+    keep = s != d
+    pairs = torch.unique(torch.stack([torch.minimum(s, d)[keep], torch.maximum(s, d)[keep]]), dim=1)
+    ei = torch.cat([pairs, pairs.flip(0)], 1)
+    ea = torch.rand(pairs.size(1), 5, generator=gen).repeat(2, 1)
+    out = {}
+    for impl in ("simt", "tc"):
+        nat.handle(0).set_option("gemm_impl", 0 if impl == "simt" else 1)
+        try:
+            out[impl] = net(gg.Data(x=x, edge_index=ei, edge_attr=ea).to("cuda")).cpu()
+        finally:
+            nat.handle(0).set_option("gemm_impl", 1)
+    ref = model_port.resgcn_forward(state, x, ei, ea, None)
+    print(f"D={D}: tc-simt {float((out['tc'] - out['simt']).abs().max()):.3g}  tc-oracle "
+          f"{float((out['tc'] - ref).abs().max()):.3g}")
+    assert torch.allclose(out["tc"], out["simt"], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(out["tc"], ref, atol=5e-4, rtol=1e-4)
