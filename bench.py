@@ -135,7 +135,7 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = a.cpu_sample or max(32, 2 * cores)
+    sample = a.cpu_sample or max(64, 8 * cores)
     cpu = CpuPath(a, cores)
     imgs, labs = make_inputs(sample, a.height, a.width, a.segments, pool=cpu.pool)
     for _ in range(max(a.warmup, 1)):
@@ -295,7 +295,7 @@ def run_ours(a):
     imgs, labs = make_inputs(a.batch, a.height, a.width, a.segments, seed0=1000 * rank, pool=gen_pool)
     gen_pool.close(); gen_pool.join()
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        sample = a.cpu_sample or max(32, 2 * cores)
+        sample = a.cpu_sample or max(64, 8 * cores)
         sample = min(sample, a.batch)
         cpu = CpuPath(a, cores)
         cpu.run(imgs[:min(cores, sample)], labs[:min(cores, sample)])            # warm-up (imports, page-in)

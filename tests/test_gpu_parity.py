@@ -600,3 +600,33 @@ def test_resgcn_other_widths_tc_vs_simt_vs_oracle(gg, D):
           f"{float((out['tc'] - ref).abs().max()):.3g}")
     assert torch.allclose(out["tc"], out["simt"], atol=2e-4, rtol=1e-4)
     assert torch.allclose(out["tc"], ref, atol=5e-4, rtol=1e-4)
+
+
+def test_streaming_sweep_is_chunking_invariant(gg):
+    """Size-independent properties on a longer sweep (BASELINE config D in miniature: many
+    batches streamed back to back): the trimap of an image does not depend on the batch it
+    travels in, on its position in the batch, on the chunk size or on the number of batches in
+    flight -- every reduction of the path is per image."""
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import model_port
+    H, W, nseg, n_img = 96 + 64, 128 + 64, 40, 96
+    imgs, labs = make_batch(n_img, H, W, nseg, seed0=4000)
+    state = model_port.random_state_dict(32, 2, seed=9)
+    cap = int(labs.max()) + 1
+    ref_path = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=cap, chunk=0)
+    want = ref_path(imgs, labs)                                     # one call, default chunking
+    rng = np.random.RandomState(0)
+    perm = rng.permutation(n_img)
+    path = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=cap, chunk=5)
+    got = np.empty_like(want)
+    pending, pos = [], 0
+    for bs in (7, 1, 32, 13, 20, 23):                                # ragged batches of a shuffled order
+        idx = perm[pos:pos + bs]
+        pos += bs
+        pending.append((idx, path.submit(imgs[idx], labs[idx])))
+        if len(pending) > 3:
+            i0, p0 = pending.pop(0)
+            got[i0] = p0.result()
+    for i0, p0 in pending:
+        got[i0] = p0.result()
+    assert pos == n_img and np.array_equal(got, want)
