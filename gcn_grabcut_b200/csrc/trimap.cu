@@ -34,9 +34,10 @@ struct GuidedParams {
   // plane mode
   const float* guide;       // [B,H,W]
   const float* src;         // [B,H,W]
-  // stage-1 outputs / stage-2 inputs: NSRC * 2 planes of [B,H,W] float32 (a_0, b_0, a_1, b_1)
+  // stage-1 outputs / stage-2 inputs, interleaved per pixel: [B,H,W][a_0, b_0(, a_1, b_1)]
+  // float32 -- one 16-byte (trimap mode) / 8-byte (plane mode) access per pixel
   float* ab;
-  size_t plane_stride;      // B*H*W
+  size_t plane_stride;      // B*H*W (pixels)
   // stage-2 outputs
   uint8_t* trimap;
   float* q0;                // optional filtered planes (p_bg / out)
@@ -251,15 +252,17 @@ k_guided_ab(const GuidedParams p) {
       const float var = __fsub_rn(mgg, __fmul_rn(mg, mg));
       const float den = __fadd_rn(var, p.eps);
       const size_t op = img_off + (size_t)y * W + x;
+      float abv[2 * NS];
 #pragma unroll
       for (int c = 0; c < NS; ++c) {
         const float ms = m[(2 + 2 * c) * NT], mgs = m[(3 + 2 * c) * NT];
         const float cov = __fsub_rn(mgs, __fmul_rn(mg, ms));
         const float a = fdiv_zero_guard(cov, den);
-        const float bb = __fsub_rn(ms, __fmul_rn(a, mg));
-        p.ab[(size_t)(2 * c) * p.plane_stride + op] = a;
-        p.ab[(size_t)(2 * c + 1) * p.plane_stride + op] = bb;
+        abv[2 * c] = a;
+        abv[2 * c + 1] = __fsub_rn(ms, __fmul_rn(a, mg));
       }
+      if (NS == 2) *reinterpret_cast<float4*>(p.ab + op * 4) = make_float4(abv[0], abv[1], abv[2 * NS - 2], abv[2 * NS - 1]);
+      else *reinterpret_cast<float2*>(p.ab + op * 2) = make_float2(abv[0], abv[1]);
     }
     cn = nn_;
     co = no_;
@@ -282,7 +285,7 @@ k_guided_out(const GuidedParams p) {
   const int xs = reflect101(x0 - r + t, W);
   const size_t img_off = (size_t)b * H * W;
   const double scale = 1.0 / ((double)(2 * r + 1) * (double)(2 * r + 1));
-  const float* col = p.ab + img_off + xs;
+  const float* col = p.ab + (img_off + xs) * NP;          // NP interleaved values per pixel
   fill_row_table(sRow, y_begin, y_end, r, H, W);
   if (kTrimap)
     for (int i = t; i < 256; i += NT) sLut[i] = __fdiv_rn((float)i, 255.0f);
@@ -292,9 +295,14 @@ k_guided_out(const GuidedParams p) {
 #pragma unroll
   for (int q = 0; q < NP; ++q) vs[q] = 0.0;
   auto load_row = [&](int yy, float (&v)[NP]) {
-    const float* rp = col + rowtab[yy];
-#pragma unroll
-    for (int q = 0; q < NP; ++q) v[q] = __ldg(rp + (size_t)q * p.plane_stride);
+    const float* rp = col + (size_t)rowtab[yy] * NP;
+    if (NP == 4) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(rp));
+      v[0] = t4.x; v[1] = t4.y; v[NP - 2] = t4.z; v[NP - 1] = t4.w;
+    } else {
+      const float2 t2 = __ldg(reinterpret_cast<const float2*>(rp));
+      v[0] = t2.x; v[1] = t2.y;
+    }
   };
   for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
     float v[NP];
