@@ -313,7 +313,7 @@ struct ChanVec {
 };
 
 template <int CPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_gcn_aggregate(const float* __restrict__ xw, const int32_t* __restrict__ rowptr,
                 const int32_t* __restrict__ src, const float* __restrict__ dinv,
                 const float* __restrict__ bias, const float* __restrict__ gate, float jkw,
@@ -915,9 +915,10 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
       });
       GG_TRY(gemm(ctx, st, GEMM_GCN0 + l, t0, wb + nw.gcn_w[l], nullptr, t1, n_nodes_p, node_cap, D, D, 0, 0));
     }
+    static const int agg_threads = getenv("GG_AGG_THREADS") ? atoi(getenv("GG_AGG_THREADS")) : 256;
     GG_CPL_SWITCH(D, {
-      GG_LAUNCH(ctx, k_gcn_aggregate<CPL>, warp_blocks, 256, 0, st, t1, rowptr, src, dinv,
-                wb + nw.gcn_b[l], gate, nw.h_jk[l + 1], sizes, h, z);
+      GG_LAUNCH(ctx, k_gcn_aggregate<CPL>, ceil_div(node_cap, agg_threads / 32), agg_threads, 0, st, t1, rowptr, src,
+                dinv, wb + nw.gcn_b[l], gate, nw.h_jk[l + 1], sizes, h, z);
     });
   }
   // ---- SAGE branch
