@@ -1,14 +1,15 @@
 // Graph construction: label map + BGR image -> attributed region graph (batched).
 //
 // Replaces graph_builder.py:142-154, 190-350, 357-454 of the reference.  Stages:
-//   k_gray_gradmax     grey plane (uint8) + per-image max of the squared Sobel magnitude
-//   k_coord_tables     y/H, x/W in the two precisions the reference uses
-//   k_region_stats     ONE pass over pixels: per-region sums (fp64) + adjacency transitions
-//   k_finalize_regions region sums -> means / std / centroids ...
-//   k_adj_sort         adjacency hash table -> (lo,hi)-sorted pair list + shared lengths
-//   k_knn / k_nl_pairs non-local colour edges
-//   k_offsets          ragged offsets (prefix sums over the batch)
+//   k_gray_gradmax(_v4) grey plane (uint8) + per-image max of the squared Sobel magnitude
+//   k_coord_tables      y/H, x/W in the two precisions the reference uses (+ prefix sums), cached
+//   k_region_stats      ONE pass over pixels: per-region sums (fp64) + adjacency transitions
+//   k_finalize_regions  region sums -> means / std / centroids ...
+//   k_adj_sort          adjacency hash table -> (lo,hi)-sorted pair list + shared lengths
+//   k_knn_sel(_smem) / k_knn / k_nl_pairs   non-local colour edges
+//   k_offsets           ragged offsets (prefix sums over the batch)
 //   k_node_features, k_prior_contrast, k_prior_finish, k_edge_attrs, k_csr
+//   k_mask_counts, k_region_labels          training labels (dataset.py), k_selftest_math
 //
 // Float32 epilogues use explicit round-to-nearest intrinsics (never contracted to FMA) so
 // that, given identical region sums, every feature is bit-identical to numpy's.
