@@ -21,7 +21,6 @@ net = gg.ResGCNNet(hidden_channels=128, n_layers=6)
 net.load_state_dict(state)
 net = net.to("cuda").eval()
 cfg = gg.SuperpixelGraphConfig(n_segments=nseg)
-path = gg.TrimapPath(state, cfg, node_cap=int(labs.max()) + 1, seed_frac=0.1)
 
 
 def per_image(i):
@@ -44,6 +43,8 @@ ts = np.array([per_image(i % 4)[1] for i in range(40)]) * 1e3
 print(f"drop-in per-image API (numpy in/out): graph_build {np.median(ts[:, 0]):.2f} ms, gcn_inference "
       f"{np.median(ts[:, 1]):.2f} ms, refine+seed {np.median(ts[:, 2]):.2f} ms, total {np.median(ts.sum(1)):.2f} ms")
 tri_a = per_image(0)[0]
+# one device handle holds one set of weights: the batched path is created after the per-image model is done
+path = gg.TrimapPath(state, cfg, node_cap=int(labs.max()) + 1, seed_frac=0.1)
 for _ in range(4):
     path(imgs[:1], labs[:1])
 t = []
