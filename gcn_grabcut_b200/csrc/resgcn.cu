@@ -777,7 +777,11 @@ int load_weights(gg_context* ctx, const gg_resgcn_weights* w) {
   nw.head_b = push(blob, w->head_bias, 3);
 
   GG_CUDA_OK(cudaSetDevice(ctx->device));
-  if (nw.blob) { cudaFree(nw.blob); nw.blob = nullptr; }
+  if (nw.blob) {
+    GG_CUDA_OK(cudaDeviceSynchronize());     // queued work may still read the old weights
+    cudaFree(nw.blob);
+    nw.blob = nullptr;
+  }
   GG_CUDA_OK(cudaMalloc(&nw.blob, blob.size() * sizeof(float)));
   GG_CUDA_OK(cudaMemcpy(nw.blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   nw.blob_floats = blob.size();

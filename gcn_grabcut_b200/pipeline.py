@@ -129,7 +129,8 @@ class TrimapPath:
         self.dev = nat.device_index(device if device is not None else "cuda")
         self.h = nat.handle(self.dev)
         state = model.state_dict() if hasattr(model, "state_dict") else model
-        nat.load_state_dict(self.h, state)
+        self._state = {k: v.detach().clone() if hasattr(v, "detach") else v for k, v in state.items()}
+        nat.load_state_dict(self.h, self._state)
         self.h.weights_token = self
         self.node_cap = int(node_cap)
         pair_cap = int(pair_cap) if pair_cap else self.node_cap * max(6, 3 + self.cfg.n_nonlocal)
@@ -139,9 +140,12 @@ class TrimapPath:
             int(chunk), 4, 0, float(seed_frac))
 
     def _ensure_weights(self):
+        # one device handle holds one set of weights: if another model (a ResGCNNet, another
+        # TrimapPath) used the handle in between, this path's weights are loaded again (the
+        # library waits for queued work before it replaces them)
         if self.h.weights_token is not self:
-            raise nat.NativeError(nat.GG_ERR_STATE, "another model was loaded on this device handle; "
-                                                    "create a new TrimapPath")
+            nat.load_state_dict(self.h, self._state)
+            self.h.weights_token = self
 
     def __call__(self, images, labels, out: Optional[np.ndarray] = None,
                  return_counts: bool = False):

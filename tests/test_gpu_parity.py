@@ -630,3 +630,27 @@ def test_streaming_sweep_is_chunking_invariant(gg):
     for i0, p0 in pending:
         got[i0] = p0.result()
     assert pos == n_img and np.array_equal(got, want)
+
+
+def test_models_share_the_device_handle(gg):
+    """One device handle holds one set of weights: a ResGCNNet and two TrimapPaths with different
+    weights can be used alternately, each reloads its own weights when another one used the handle."""
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import model_port
+    imgs, labs = make_batch(3, 128, 160, 40, seed0=77)
+    cap = int(labs.max()) + 1
+    s1, s2 = model_port.random_state_dict(32, 2, seed=1), model_port.random_state_dict(64, 3, seed=2)
+    p1 = gg.TrimapPath(s1, gg.SuperpixelGraphConfig(), node_cap=cap)
+    t1 = p1(imgs, labs)
+    p2 = gg.TrimapPath(s2, gg.SuperpixelGraphConfig(), node_cap=cap)
+    t2 = p2(imgs, labs)
+    net = gg.ResGCNNet(hidden_channels=32, n_layers=2)
+    net.load_state_dict(s1)
+    net = net.to("cuda").eval()
+    g = gg.GraphBuilder(imgs[0], gg.SuperpixelGraphConfig(), segments=labs[0]).build()
+    data = gg.Data(x=torch.tensor(g.node_input()), edge_index=torch.tensor(g.edge_index),
+                   edge_attr=torch.tensor(g.edge_attr)).to("cuda")
+    probs = net.predict_probs(data)
+    assert np.array_equal(p1(imgs, labs), t1) and np.array_equal(p2(imgs, labs), t2)
+    assert np.array_equal(net.predict_probs(data), probs)
+    assert np.array_equal(gg.refine_trimap(probs, labs[0], imgs[0]), t1[0])
