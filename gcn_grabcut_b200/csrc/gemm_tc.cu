@@ -233,6 +233,17 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
           // fused LayerNorm (K == 128: one float4 per lane covers the row, rpp == 1)
           const float4 g4 = __ldg(reinterpret_cast<const float4*>(pro.ln_g) + lane);
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(pro.ln_b) + lane);
+          if (pro.row_stats != nullptr && pro.gvec == nullptr) {
+            // row statistics were written by the kernel that produced A: no reductions here
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+              const int row = row0 + warp * RPW + i;
+              const float2 ms = row < M ? __ldg(pro.row_stats + row) : make_float2(0.f, 0.f);
+              const float4 x4 = v[i];
+              v[i] = make_float4((x4.x - ms.x) * ms.y * g4.x + b4.x, (x4.y - ms.x) * ms.y * g4.y + b4.y,
+                                 (x4.z - ms.x) * ms.y * g4.z + b4.z, (x4.w - ms.x) * ms.y * g4.w + b4.w);
+            }
+          } else {
 #pragma unroll
           for (int i = 0; i < RPW; ++i) {
             const int row = row0 + warp * RPW + i;
@@ -252,6 +263,7 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
             const float rstd = 1.0f / sqrtf(sq / (float)K + 1e-5f);
             v[i] = make_float4(dx * rstd * g4.x + b4.x, dy * rstd * g4.y + b4.y,
                                dz * rstd * g4.z + b4.z, dw * rstd * g4.w + b4.w);
+          }
           }
         }
       }

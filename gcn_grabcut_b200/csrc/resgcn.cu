@@ -59,7 +59,8 @@ __global__ void k_node_meta(const int64_t* __restrict__ graph_off, int n_graphs,
 template <int CPL>   // channels per lane = D/32
 __global__ void __launch_bounds__(256)
 k_input_stage(const float* __restrict__ x, const float* __restrict__ wb, NetOffsets o,
-              const int* __restrict__ sizes, float* __restrict__ h, float* __restrict__ z) {
+              const int* __restrict__ sizes, float* __restrict__ h, float* __restrict__ z,
+              float2* __restrict__ row_stats) {
   extern __shared__ float sw[];
   const int D = CPL * 32, q = o.q;
   float* s_win = sw;                    // [D][19]
@@ -114,6 +115,7 @@ k_input_stage(const float* __restrict__ x, const float* __restrict__ wb, NetOffs
         for (int j = 0; j < CPL; ++j) boost[j] = fmaf(s_pb2[(u0 + s) * D + lane + 32 * j], hs, boost[j]);
       }
     }
+    float hsum = 0.0f, hvv[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       const int c = lane + 32 * j;
@@ -121,7 +123,16 @@ k_input_stage(const float* __restrict__ x, const float* __restrict__ wb, NetOffs
       const float hv = gelu_erf(ln) * (1.0f + sigmoidf(boost[j]));
       h[(size_t)v * D + c] = hv;
       z[(size_t)v * D + c] = jk0 * hv;
+      hvv[j] = hv;
+      hsum += hv;
     }
+    // mean / rstd of the new row for the next layer's LayerNorm (consumed by the GEMM producers)
+    const float hmean = warp_sum(hsum) / (float)D;
+    float hsq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { const float d = hvv[j] - hmean; hsq += d * d; }
+    const float hrstd = 1.0f / sqrtf(warp_sum(hsq) / (float)D + 1e-5f);
+    if (lane == 0) row_stats[v] = make_float2(hmean, hrstd);
   }
 }
 
@@ -317,7 +328,8 @@ __global__ void __launch_bounds__(1024)
 k_gcn_aggregate(const float* __restrict__ xw, const int32_t* __restrict__ rowptr,
                 const int32_t* __restrict__ src, const float* __restrict__ dinv,
                 const float* __restrict__ bias, const float* __restrict__ gate, float jkw,
-                const int* __restrict__ sizes, float* __restrict__ h, float* __restrict__ z) {
+                const int* __restrict__ sizes, float* __restrict__ h, float* __restrict__ z,
+                float2* __restrict__ row_stats) {
   constexpr int D = CPL * 32;
   const int lane = threadIdx.x & 31;
   const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -358,6 +370,17 @@ k_gcn_aggregate(const float* __restrict__ xw, const int32_t* __restrict__ rowptr
   }
   hv.store(h + (size_t)v * D, lane);
   zv.store(z + (size_t)v * D, lane);
+  // mean / rstd of the new row for the next layer's LayerNorm (the GEMM producers then skip their
+  // own reductions); the same two-pass formula the producers use
+  float sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) sum += hv.v[j];
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.0f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { const float d = hv.v[j] - mean; sq += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + 1e-5f);
+  if (lane == 0) row_stats[v] = make_float2(mean, rstd);
 }
 
 // SAGE mean aggregation: m_v = mean_{j -> v} h_j (self loops kept, empty -> 0)
@@ -810,6 +833,7 @@ size_t resgcn_workspace_bytes(const NetWeights& nw, long long node_cap, long lon
   s += Arena::padded((size_t)std::max<long long>(std::max<long long>(edge_cap, node_cap), 1) * c, 4) * 2;   // e1, enc
   s += Arena::padded((size_t)node_cap * c, 4);          // ctx
   s += Arena::padded((size_t)node_cap, 4) * 3;          // node_graph, dinv, score
+  s += Arena::padded((size_t)node_cap, 8);              // row_stats
   s += Arena::padded((size_t)n_graphs * D, 4);          // gvec
   s += Arena::padded((size_t)n_graphs, 4) + Arena::padded((size_t)n_graphs * 32 * (D + 1), 4);   // split readout
   s += 4096;
@@ -855,6 +879,7 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   float* dinv = ar.take<float>((size_t)node_cap);
   float* score = ar.take<float>((size_t)node_cap);
   float* gvec = ar.take<float>((size_t)n_graphs * D);
+  float2* row_stats = ar.take<float2>((size_t)node_cap);
   int* ctx_gmax = ar.take<int>((size_t)n_graphs);
   float* ctx_part = ar.take<float>((size_t)n_graphs * CTX_PARTS * (D + 1));
   int* sizes = ar.take<int>(64);
@@ -872,7 +897,7 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
     const int blocks = min(warp_blocks, ctx->sm_count * 8);
     GG_CPL_SWITCH(D, {
       GG_SMEM_ATTR_ONCE(ctx, 1 + CPL, k_input_stage<CPL>, smem);
-      GG_LAUNCH(ctx, k_input_stage<CPL>, blocks, 256, smem, st, x, wb, o, sizes, h, z);
+      GG_LAUNCH(ctx, k_input_stage<CPL>, blocks, 256, smem, st, x, wb, o, sizes, h, z, row_stats);
     });
   }
   // ---- edge context -> gate
@@ -911,6 +936,7 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
     if (use_tc && gemm_tc_supported(ctx, GEMM_GCN0 + l, D, D) && D == 128) {
       TcPrologue pro;                                   // LayerNorm fused into the A producer
       pro.mode = 1; pro.ln_g = wb + nw.norm_g[l]; pro.ln_b = wb + nw.norm_b[l];
+      pro.row_stats = row_stats;                        // written by the kernel that produced h
       GG_TRY(gemm_tc(ctx, st, GEMM_GCN0 + l, h, nullptr, t1, n_nodes_p, node_cap, D, D, 0, 0, &pro));
     } else {
       GG_CPL_SWITCH(D, {
@@ -922,7 +948,7 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
     static const int agg_threads = getenv("GG_AGG_THREADS") ? atoi(getenv("GG_AGG_THREADS")) : 256;
     GG_CPL_SWITCH(D, {
       GG_LAUNCH(ctx, k_gcn_aggregate<CPL>, ceil_div(node_cap, agg_threads / 32), agg_threads, 0, st, t1, rowptr, src,
-                dinv, wb + nw.gcn_b[l], gate, nw.h_jk[l + 1], sizes, h, z);
+                dinv, wb + nw.gcn_b[l], gate, nw.h_jk[l + 1], sizes, h, z, row_stats);
     });
   }
   // ---- SAGE branch

@@ -39,6 +39,7 @@ struct TcPrologue {
   const float* ln_b = nullptr;
   const float* gvec = nullptr;       // [n_graphs, K] optional per-graph row scale (mode 1)
   const int* node_graph = nullptr;   // [M]
+  const float2* row_stats = nullptr; // [M] optional (mean, rstd) of every row, precomputed by the producer of A (mode 1, no gvec)
   const float* w0 = nullptr;         // [K,5]  (mode 2)
   const float* b0 = nullptr;         // [K]
 };
