@@ -95,7 +95,7 @@ def _cpu_init(hidden, layers):
     import torch
     cv2.setNumThreads(1)
     torch.set_num_threads(1)
-    from oracle.model_port import random_state_dict
+    from gcn_grabcut_b200.synthetic import random_state_dict
     _STATE = random_state_dict(hidden, layers, seed=0)
 
 
@@ -309,7 +309,7 @@ def run_ours(a):
     import torch.distributed as dist
     import gcn_grabcut_b200 as gg
     from gcn_grabcut_b200 import _native as nat
-    from oracle.model_port import random_state_dict        # weights only: a seeded random state-dict
+    from gcn_grabcut_b200.synthetic import random_state_dict
 
     torch.cuda.set_device(local)
     if world > 1:

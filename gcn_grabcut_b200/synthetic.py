@@ -125,3 +125,66 @@ def make_batch(n_images: int, height: int, width: int, n_segments: int,
         imgs[i], _ = geometric_sample(height, width, seed0 + i, scale)
         labs[i] = slic_like_labels(height, width, n_segments, seed0 + i)
     return imgs, labs
+
+
+# ----------------------------------------------------------------------------- weights
+N_PRIOR_FEATS = 3
+
+
+def random_state_dict(hidden: int = 128, n_layers: int = 6, seed: int = 0,
+                      in_channels: int = 19, edge_channels: int = 5, n_classes: int = 3,
+                      randomize_norms: bool = True) -> dict:
+    """
+    A random-init ResGCNNet state-dict with the reference's keys and shapes
+    (model.py:449-499).  nn.Linear layers: kaiming-normal(relu) weights (model.py:501-506);
+    biases, LayerNorm/BatchNorm affine terms and running statistics are drawn non-trivially
+    (``randomize_norms``) so that every term of the forward pass is exercised -- a freshly
+    constructed reference model has zero biases and identity norms.
+    """
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    D, q, c = hidden, max(hidden // 4, 8), max(hidden // 2, 8)
+
+    def lin(o, i):
+        return torch.randn(o, i, generator=g) * math.sqrt(2.0 / i)
+
+    def vec(n, scale=0.1, shift=0.0):
+        if not randomize_norms:
+            return torch.full((n,), float(shift))
+        return torch.randn(n, generator=g) * scale + shift
+
+    s = {}
+    s["jk_logits"] = vec(n_layers + 2, 0.5)
+    s["in_norm.norm.weight"] = vec(in_channels, 0.1, 1.0)
+    s["in_norm.norm.bias"] = vec(in_channels)
+    s["in_norm.norm.running_mean"] = vec(in_channels, 0.2, 0.3)
+    s["in_norm.norm.running_var"] = (vec(in_channels, 0.1, 0.5).abs() + 0.05)
+    s["in_norm.norm.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    s["input_proj.0.weight"], s["input_proj.0.bias"] = lin(D, in_channels), vec(D)
+    s["input_proj.1.weight"], s["input_proj.1.bias"] = vec(D, 0.1, 1.0), vec(D)
+    s["prior_booster.0.weight"], s["prior_booster.0.bias"] = lin(q, N_PRIOR_FEATS), vec(q)
+    s["prior_booster.2.weight"], s["prior_booster.2.bias"] = lin(D, q), vec(D)
+    s["edge_ctx.encode.0.weight"], s["edge_ctx.encode.0.bias"] = lin(c, edge_channels), vec(c)
+    s["edge_ctx.encode.2.weight"], s["edge_ctx.encode.2.bias"] = lin(c, c), vec(c)
+    s["edge_ctx.to_gate.0.weight"], s["edge_ctx.to_gate.0.bias"] = vec(c, 0.1, 1.0), vec(c)
+    s["edge_ctx.to_gate.1.weight"], s["edge_ctx.to_gate.1.bias"] = lin(D, c), vec(D)
+    a = math.sqrt(6.0 / (D + D))
+    for i in range(n_layers):
+        s[f"gcn_layers.{i}.bias"] = vec(D)
+        s[f"gcn_layers.{i}.lin.weight"] = (torch.rand(D, D, generator=g) * 2 - 1) * a
+        s[f"norms.{i}.weight"], s[f"norms.{i}.bias"] = vec(D, 0.1, 1.0), vec(D)
+    b = 1.0 / math.sqrt(D)
+    s["sage.lin_l.weight"] = (torch.rand(D, D, generator=g) * 2 - 1) * b
+    s["sage.lin_l.bias"] = (torch.rand(D, generator=g) * 2 - 1) * b
+    s["sage.lin_r.weight"] = (torch.rand(D, D, generator=g) * 2 - 1) * b
+    s["sage_norm.weight"], s["sage_norm.bias"] = vec(D, 0.1, 1.0), vec(D)
+    s["ctx.attn.weight"], s["ctx.attn.bias"] = lin(1, D), vec(1)
+    s["ctx.compress.weight"], s["ctx.compress.bias"] = lin(D // 2, D), vec(D // 2)
+    s["ctx.expand.weight"], s["ctx.expand.bias"] = lin(D, D // 2), vec(D)
+    s["fuse.0.weight"], s["fuse.0.bias"] = vec(D, 0.1, 1.0), vec(D)
+    s["fuse.1.weight"], s["fuse.1.bias"] = lin(D, D), vec(D)
+    s["head.weight"], s["head.bias"] = lin(n_classes, D), vec(n_classes)
+    return {k: v.contiguous() for k, v in s.items()}
+
+

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """
-Stage-by-stage GPU-vs-oracle diagnostics (development aid; run on the B200 box):
+Stage-by-stage GPU-vs-oracle diagnostics (TEST TOOLING like tests/: a development aid that uses
+the oracle as the checker; run on the B200 box):
 
     python tools/gpu_diag.py > gpurun_out/diag.log 2>&1
 
@@ -16,7 +17,7 @@ import traceback
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 import gcn_grabcut_b200 as gg                                   # noqa: E402
 from gcn_grabcut_b200 import _native as nat                     # noqa: E402

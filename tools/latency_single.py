@@ -12,7 +12,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gcn_grabcut_b200 as gg                                   # noqa: E402
 from gcn_grabcut_b200.synthetic import make_batch               # noqa: E402
-from oracle.model_port import random_state_dict                # noqa: E402  (seeded weights only)
+from gcn_grabcut_b200.synthetic import random_state_dict          # noqa: E402
 
 H, W, nseg = 320, 480, 300
 imgs, labs = make_batch(4, H, W, nseg, seed0=0)
