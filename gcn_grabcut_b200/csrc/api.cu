@@ -453,8 +453,11 @@ static int host_submit(gg_handle h, const uint8_t* bgr_host, const void* labels_
     return GG_ERR_STATE;
   }
   const size_t npx = (size_t)H * W;
-  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)(chunk_input_bytes / (npx * (3 + lbytes)) + 1)));
+  // default chunk: sized by pixels (7 B/px whatever the label transport: the kernels, not the copy,
+  // set the efficient size), then balanced so that all chunks of the call are equal
+  int chunk = cfg->chunk > 0 ? cfg->chunk : std::max(1, std::min(B, (int)(chunk_input_bytes / (npx * 7) + 1)));
   chunk = std::min(chunk, B);
+  if (cfg->chunk <= 0) chunk = (B + (B + chunk - 1) / chunk - 1) / ((B + chunk - 1) / chunk);
   const int n_chunks = (B + chunk - 1) / chunk;
   const int n_slots = 3;
   const size_t in_bytes = Arena::padded((size_t)chunk * npx * 3, 1) + Arena::padded((size_t)chunk * npx, 4) +
