@@ -654,3 +654,45 @@ def test_models_share_the_device_handle(gg):
     assert np.array_equal(p1(imgs, labs), t1) and np.array_equal(p2(imgs, labs), t2)
     assert np.array_equal(net.predict_probs(data), probs)
     assert np.array_equal(gg.refine_trimap(probs, labs[0], imgs[0]), t1[0])
+
+
+def test_abi_error_paths(gg):
+    """Misuse is reported through the status code and gg_last_error, never by a crash or a silent
+    fallback: forward before gg_load_weights, bad shapes, a bad label width, NULL pointers,
+    an unknown option, an unknown ticket."""
+    import ctypes as C
+    from gcn_grabcut_b200 import _native as nat
+    L = nat.lib()
+    hp = C.c_void_p()
+    assert L.gg_create(C.byref(hp), 0) == 0
+    try:
+        img = torch.zeros((1, 16, 16, 3), dtype=torch.uint8)
+        lab = torch.zeros((1, 16, 16), dtype=torch.int32)
+        tri = torch.zeros((1, 16, 16), dtype=torch.uint8)
+        pc = nat.PathConfig(nat.GraphConfig(4, 4, 8, 0), 8, 1e-3, 0.55, 0.55, 1, 0, 4, 0, 0.0)
+        rc = L.gg_trimap_path_host(hp, nat.ptr(img), nat.ptr(lab), 1, 16, 16, C.byref(pc), nat.ptr(tri), None, None)
+        assert rc == nat.GG_ERR_STATE and b"gg_load_weights" in L.gg_last_error()
+        assert L.gg_set_option(hp, b"no_such_option", 1) == nat.GG_ERR_INVALID
+        assert L.gg_trimap_path_host_wait(hp, 3) == nat.GG_ERR_INVALID
+        assert L.gg_trimap_path_host(hp, None, nat.ptr(lab), 1, 16, 16, C.byref(pc), nat.ptr(tri), None, None) == nat.GG_ERR_INVALID
+        out = (C.c_int64 * 4)()
+        assert L.gg_selftest_math(hp, None) == nat.GG_ERR_INVALID and L.gg_selftest_math(hp, out) == 0
+    finally:
+        L.gg_destroy(hp)
+    # through the Python mirror: shape / dtype mistakes raise ValueError like the reference's checks
+    from oracle import model_port
+    path = gg.TrimapPath(model_port.random_state_dict(32, 2, seed=0), gg.SuperpixelGraphConfig(), node_cap=8)
+    with pytest.raises(ValueError):
+        path(np.zeros((1, 16, 16), np.uint8), np.zeros((1, 16, 16), np.int32))
+    with pytest.raises(ValueError):
+        path(np.zeros((1, 16, 16, 3), np.uint8), np.zeros((1, 8, 16), np.int32))
+    pc_bad = nat.PathConfig.from_buffer_copy(path.pc)
+    pc_bad.label_bytes = 3
+    img = torch.zeros((1, 16, 16, 3), dtype=torch.uint8)
+    lab = torch.zeros((1, 16, 16), dtype=torch.int32)
+    tri = torch.zeros((1, 16, 16), dtype=torch.uint8)
+    assert nat.lib().gg_trimap_path_host(path.h.ptr, nat.ptr(img), nat.ptr(lab), 1, 16, 16, C.byref(pc_bad),
+                                         nat.ptr(tri), None, None) == nat.GG_ERR_INVALID
+    with pytest.raises(nat.NativeError):          # a label >= node_cap is a capacity error, not a wrong answer
+        path(np.zeros((1, 16, 16, 3), np.uint8), np.full((1, 16, 16), 9, np.int32))
+    assert path(np.zeros((2, 16, 16, 3), np.uint8), np.zeros((2, 16, 16), np.int32)).shape == (2, 16, 16)
