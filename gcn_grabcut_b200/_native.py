@@ -15,7 +15,7 @@ from typing import Dict, Optional
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libgcn_grabcut_b200.so")
+LIB_PATH = os.environ.get("GG_LIB") or os.path.join(_PKG, "libgcn_grabcut_b200.so")   # GG_LIB: A/B builds
 
 GG_OK, GG_ERR_INVALID, GG_ERR_CUDA, GG_ERR_CAPACITY, GG_ERR_STATE = 0, -1, -2, -3, -4
 
