@@ -20,6 +20,15 @@ One step = graph build + GCN forward + guided-filter trimap for the whole batch.
 Multi-GPU: one process per GPU (torchrun), images shard with no exchange step; every rank
 runs its own 256-image batch per step ("weak" scaling); the only collectives are the timing
 barrier / max-reduction.
+
+Beside the headline (config B) the same JSON line carries
+  other_configs.A   single-image latency of the drop-in per-image API next to the reference's own
+                    pipeline.segment() timing dict (incl. cv2.grabCut) on this box's host
+  other_configs.C   64 x 1080x1920, ~2000 regions, k=16 non-local edges      (N=1 runs only)
+  other_configs.E   8 x 2160x3840, ~10^4 regions, ResGCNNet(D=256, n=8)       (N=1 runs only)
+  config_D          ONE fixed 8192-image 320x480 sweep split over the ranks by shard_range
+                    ("strong" scaling: 8192/N images per GPU), device-resident and end to end,
+                    with a final all-gather of the per-rank image counts and trimap checksums.
 """
 from __future__ import annotations
 
@@ -59,9 +68,24 @@ def parse():
     return ap.parse_args()
 
 
+def config_letter(batch, height, width):
+    """BASELINE.json config letter of a workload shape (A: one image, B: 256 x 320x480, C: 1080x1920,
+    E: 2160x3840; D is the 8192-image sweep of B-shaped images, see config_D)."""
+    if (height, width) == (320, 480):
+        return "A" if batch == 1 else "B"
+    if (height, width) == (1080, 1920):
+        return "C"
+    if (height, width) == (2160, 3840):
+        return "E"
+    return "custom"
+
+
 def workload_config(a):
+    """The workload keys only -- identical for the `ours` and `reference` arms (everything that
+    describes the run rather than the workload lives in the sibling key "run")."""
+    letter = config_letter(a.batch, a.height, a.width)
     return {
-        "workload": f"B: batch of {a.batch} synthetic {a.height}x{a.width} images per GPU per step, "
+        "workload": f"{letter}: batch of {a.batch} synthetic {a.height}x{a.width} images per GPU per step, "
                     f"~{a.segments} regions, graph build + ResGCNNet(D={a.hidden}, n={a.layers}) + "
                     f"guided-filter trimap (r={a.radius})",
         "batch_per_gpu": a.batch, "height": a.height, "width": a.width, "n_segments": a.segments,
@@ -74,7 +98,8 @@ def workload_config(a):
 def _gen_one(args):
     from gcn_grabcut_b200.synthetic import geometric_sample, slic_like_labels
     i, H, W, nseg = args
-    return geometric_sample(H, W, i)[0], slic_like_labels(H, W, nseg, i)
+    scale = min(H, W) / 320.0 if min(H, W) > 320 else 1.0      # configs C / E: the object keeps its relative size
+    return geometric_sample(H, W, i, scale)[0], slic_like_labels(H, W, nseg, i)
 
 
 def make_inputs(B, H, W, nseg, seed0=0, pool=None):
@@ -85,25 +110,56 @@ def make_inputs(B, H, W, nseg, seed0=0, pool=None):
     return imgs, labs
 
 
-# ----------------------------------------------------------------------------- CPU path (oracle port)
+# ----------------------------------------------------------------------------- CPU path
+# kind "reference": the reference's OWN files (oracle/_ref, written by oracle/make_ref.py; or
+# /root/reference) -- GraphBuilder(image, cfg).build(), ResGCNNet.predict_probs, refine_trimap,
+# exactly the calls pipeline.segment() makes (pipeline.py:298-317) -- over the third-party shims
+# (scikit-image / PyG are not installable here); kind "port": the oracle's restatement, used only
+# when the reference files are not present.  Label-map generation (SLIC) is excluded on both.
 _STATE = None
+_REF = None
+
+
+def cpu_kind():
+    from oracle import ref_loader
+    return "reference" if ref_loader.available() and not os.environ.get("GG_CPU_PORT") else "port"
 
 
 def _cpu_init(hidden, layers):
-    global _STATE
+    global _STATE, _REF
     import cv2
     import torch
     cv2.setNumThreads(1)
     torch.set_num_threads(1)
     from gcn_grabcut_b200.synthetic import random_state_dict
     _STATE = random_state_dict(hidden, layers, seed=0)
+    if cpu_kind() == "reference":
+        from oracle import ref_loader
+        ref = ref_loader.load()
+        model = ref.model.ResGCNNet(hidden_channels=hidden, n_layers=layers)
+        model.load_state_dict(_STATE)
+        model.eval()
+        from skimage import segmentation as slic_shim          # the shim: slic() returns the queued label map
+        _REF = (ref, model, slic_shim)
 
 
 def _cpu_one(job):
     """The reference's per-image hot path, label-map generation excluded."""
     import torch
-    from oracle import graph_port, model_port, trimap_port
     img, seg, k, radius = job
+    if _REF is not None:
+        ref, model, slic_shim = _REF
+        from torch_geometric.data import Data as PyGData
+        slic_shim.set_next_labels(seg)
+        cfg = ref.graph_builder.SuperpixelGraphConfig(n_segments=int(seg.max()) + 1, n_nonlocal=k)
+        graph = ref.graph_builder.GraphBuilder(img, cfg).build()
+        data = PyGData(x=torch.tensor(graph.node_input(), dtype=torch.float32),
+                       edge_index=torch.tensor(graph.edge_index, dtype=torch.long),
+                       edge_attr=torch.tensor(graph.edge_attr, dtype=torch.float32))
+        probs = model.predict_probs(data)
+        tri = ref.pipeline.refine_trimap(probs, graph.segments, img, 0.55, 0.55, radius=radius)
+        return int(tri.sum())
+    from oracle import graph_port, model_port, trimap_port
     g = graph_port.build_graph(img, seg, 4, k, keep_stages=False)
     probs = model_port.predict_probs(_STATE, torch.from_numpy(g.node_input()),
                                      torch.from_numpy(g.edge_index), torch.from_numpy(g.edge_attr))
@@ -115,6 +171,7 @@ class CpuPath:
     def __init__(self, a, cores):
         import multiprocessing as mp
         self.cores = cores
+        self.kind = cpu_kind()
         self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(a.hidden, a.layers))
         self.a = a
 
@@ -129,8 +186,40 @@ class CpuPath:
         self.pool.join()
 
 
+def reference_segment_timing(hidden, layers, n_images=3):
+    """Config A, CPU side: the reference's own GCNGrabCutPipeline.segment() (unmodified file) on
+    320x480 synthetic images with ~300 regions and a random-init ResGCNNet -- its timing dict,
+    cv2.grabCut included (pipeline.py:294-342), median over `n_images` images, all host threads
+    (the reference's default: numpy / OpenCV / torch thread pools as they come up)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return None
+    import cv2
+    import torch
+    from gcn_grabcut_b200.synthetic import geometric_sample, random_state_dict, slic_like_labels
+    ref = ref_loader.load()
+    from skimage import segmentation as slic_shim
+    model = ref.model.ResGCNNet(hidden_channels=hidden, n_layers=layers)
+    model.load_state_dict(random_state_dict(hidden, layers, seed=0))
+    model.eval()
+    pipe = ref.pipeline.GCNGrabCutPipeline(model, ref.graph_builder.SuperpixelGraphConfig(n_segments=300), device="cpu")
+    rows = []
+    for i in range(n_images + 1):
+        img = geometric_sample(320, 480, i)[0]
+        slic_shim.set_next_labels(slic_like_labels(320, 480, 300, i))
+        res = pipe.segment(img)
+        if i:                                   # the first image pays imports and page-in
+            rows.append(res.timing)
+    med = {k: 1e3 * float(np.median([r[k] for r in rows])) for k in rows[0]}
+    med["trimap_path_ms"] = med["graph_build"] + med["data_prep"] + med["gcn_inference"]
+    return {"timing_ms": med, "images": n_images, "threads": {"torch": torch.get_num_threads(), "cv2": cv2.getNumThreads(),
+                                                               "cpu_count": os.cpu_count()},
+            "what": "reference pipeline.segment() timing dict, medians; SLIC replaced by the supplied label map "
+                    "(scikit-image is not installable here), so graph_build excludes SLIC"}
+
+
 def run_reference(a):
-    """--impl reference: the CPU implementation of the path on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -146,13 +235,15 @@ def run_reference(a):
     cpu.close()
     val = sample * a.steps / total
     sample_txt = (f"{sample} images of the workload per step (label maps supplied, SLIC excluded), "
-                  f"one process per core, 1 thread each")
+                  f"one process per core, 1 thread each; "
+                  + ("the reference's own GraphBuilder / ResGCNNet.predict_probs / refine_trimap (oracle/_ref) over "
+                     "the third-party shims" if cpu.kind == "reference" else "oracle port (reference files not present)"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (fp64 region/window sums)", "data": "synthetic", "config": workload_config(a),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_txt},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": cpu.kind, "sample": sample_txt},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -276,6 +367,217 @@ def bind_to_gpu_numa(local):
     return None
 
 
+def roofline_record(rows, steps, B, H, W, N_avg, E_avg, with_traffic=True):
+    """The dominant kernel of a CUDA-event profile (rows = [(kernel, launches, total_ms)] over
+    `steps` steps of B images) against the measured HBM peak."""
+    total_prof_ms = sum(r[2] for r in rows)
+    top = rows[0]
+    per_img, what = algorithmic_bytes_per_image(top[0], H * W, N_avg, E_avg)
+    launches_per_step = top[1] / steps
+    avg_launch_ms = top[2] / top[1]
+    alg_bytes_per_launch = per_img * B / launches_per_step
+    achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic, traffic_src = None, None
+    if with_traffic and (H, W) == (320, 480):                # the ncu captures are of config B
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(REPO, "profiles", name)
+            if not os.path.exists(tpath):
+                continue
+            ent = json.load(open(tpath))["kernels"].get(top[0].split("<")[0])
+            if ent:
+                traffic = ent["bytes_per_image_per_launch"] * B / launches_per_step
+                traffic_src = "profiles/" + ent["source"]
+                break
+    # whole-step view: algorithmic bytes of all three stages over the profiled step time
+    step_bytes = (7 * H * W + 80 * N_avg + 40 * E_avg) + (92 * N_avg + 24 * E_avg) + (8 * H * W + 12 * N_avg)
+    step_ms = total_prof_ms / steps
+    return {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes_per_launch, "algorithmic_model": what,
+            "avg_launch_ms": avg_launch_ms, "share_of_step": top[2] / total_prof_ms,
+            "kernels_ms_per_step": {r[0]: round(r[2] / steps, 4) for r in rows[:40]},
+            "profiled_step_ms": step_ms,
+            "whole_step": {"algorithmic_bytes_per_image": step_bytes,
+                           "achieved": step_bytes * B / (step_ms * 1e-3) / 1e9,
+                           "frac": step_bytes * B / (step_ms * 1e-3) / 1e9 / peak}}
+
+
+def measure_device(path, h, img_d, lab_d, tri_d, steps, warmup, stream, profile=True):
+    """`steps` device-resident passes of the path over the batch: CUDA events on the launching
+    stream, then (optionally) the same steps again with per-kernel events, one sub-batch at a
+    time so that kernel durations do not overlap."""
+    import torch
+    for _ in range(warmup):
+        path.run_device(img_d, lab_d, tri_d)
+    path.check_status()              # a silent overflow (clamped labels) must not produce a number
+    torch.cuda.synchronize()
+    l0 = h.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        path.run_device(img_d, lab_d, tri_d)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = h.launches() - l0
+    path.check_status()
+    rows = None
+    if profile:
+        n_sub = int(os.environ.get("GG_SUBBATCH", "2"))
+        h.set_option("n_sub", 1)
+        h.profile(True)
+        for _ in range(steps):
+            path.run_device(img_d, lab_d, tri_d)
+        rows = [(name.rstrip(")"), n, t) for name, n, t in h.profile_report()]
+        h.profile(False)
+        h.set_option("n_sub", n_sub)
+    return ms, launches, rows
+
+
+def run_other_config(gg, nat, dev, letter, B, H, W, nseg, k, hidden, layers, radius, steps, warmup, cores):
+    """One more BASELINE config on this GPU (device-resident): value, ms_per_step, roofline."""
+    import multiprocessing as mp
+    import torch
+    from gcn_grabcut_b200.synthetic import random_state_dict
+    t0 = time.perf_counter()
+    pool = mp.get_context("fork").Pool(max(1, min(cores, B, 32)))
+    imgs, labs = make_inputs(B, H, W, nseg, seed0=7000, pool=pool)
+    pool.close(); pool.join()
+    gen_s = time.perf_counter() - t0
+    node_cap = int(labs.max()) + 1
+    cfg = gg.SuperpixelGraphConfig(n_segments=nseg, n_nonlocal=k)
+    path = gg.TrimapPath(random_state_dict(hidden, layers, seed=0), cfg, node_cap=node_cap, filter_radius=radius,
+                         device=dev)
+    img_d, lab_d = torch.from_numpy(imgs).to(dev), torch.from_numpy(labs).to(dev)
+    tri_d = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    ms, launches, rows = measure_device(path, path.h, img_d, lab_d, tri_d, steps, warmup, None)
+    g = gg.build_graph_batch(img_d[:2], lab_d[:2], cfg, node_cap=node_cap)
+    N_avg, E_avg = float(g.node_off[-1].item()) / 2, float(g.edge_off[-1].item()) / 2
+    rec = {"workload": f"{letter}: batch of {B} synthetic {H}x{W} images, ~{nseg} regions, k={k} non-local edges, "
+                       f"ResGCNNet(D={hidden}, n={layers}), guided-filter trimap (r={radius})",
+           "value": B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "avg_nodes_per_image": N_avg, "avg_directed_edges_per_image": E_avg, "gpu_launches": int(launches),
+           "input_generation_s": round(gen_s, 1),
+           "roofline": roofline_record(rows, steps, B, H, W, N_avg, E_avg, with_traffic=False),
+           "inputs": f"device-resident, {(imgs.nbytes + labs.nbytes) / 1e6:.0f} MB per step > 126 MB L2"
+                     if imgs.nbytes + labs.nbytes > 126e6 else
+                     f"device-resident, {(imgs.nbytes + labs.nbytes) / 1e6:.0f} MB per step"}
+    del path, img_d, lab_d, tri_d
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_config_a(gg, nat, dev, hidden, layers):
+    """Config A: one 320x480 image through the drop-in per-image API (the three calls
+    pipeline.segment() makes, numpy in / numpy out) and through TrimapPath with B = 1."""
+    import torch
+    from gcn_grabcut_b200.synthetic import make_batch, random_state_dict
+    imgs, labs = make_batch(4, 320, 480, 300, seed0=0)
+    state = random_state_dict(hidden, layers, seed=0)
+    net = gg.ResGCNNet(hidden_channels=hidden, n_layers=layers)
+    net.load_state_dict(state)
+    net = net.to(dev).eval()
+    cfg = gg.SuperpixelGraphConfig(n_segments=300)
+
+    def per_image(i):
+        t0 = time.perf_counter()
+        graph = gg.GraphBuilder(imgs[i], cfg, segments=labs[i]).build()
+        t1 = time.perf_counter()
+        data = gg.Data(x=torch.tensor(graph.node_input()), edge_index=torch.tensor(graph.edge_index),
+                       edge_attr=torch.tensor(graph.edge_attr)).to(dev)
+        probs = net.predict_probs(data)
+        tri = gg.refine_trimap(probs, graph.segments, imgs[i], 0.55, 0.55, radius=8)
+        t2 = time.perf_counter()
+        return (t1 - t0, t2 - t1)
+
+    for i in range(4):
+        per_image(i)
+    ts = np.array([per_image(i % 4) for i in range(24)]) * 1e3
+    path = gg.TrimapPath(state, cfg, node_cap=int(labs.max()) + 1, device=dev)
+    for _ in range(4):
+        path(imgs[:1], labs[:1])
+    t = []
+    for _ in range(24):
+        t0 = time.perf_counter()
+        path(imgs[:1], labs[:1])
+        t.append(time.perf_counter() - t0)
+    return {"per_image_api_ms": {"graph_build": float(np.median(ts[:, 0])), "gcn_inference": float(np.median(ts[:, 1])),
+                                 "trimap_path_ms": float(np.median(ts.sum(1)))},
+            "trimap_path_b1_host_call_ms": float(np.median(t) * 1e3),
+            "what": "GraphBuilder(image, cfg, segments).build() / predict_probs + refine_trimap with numpy in/out "
+                    "(wall clock, host<->device copies and syncs included), and TrimapPath(B=1) host call"}
+
+
+def run_config_d(a, gg, nat, dist, dev, path, img_pin, lab_pin, img_d, lab_d, rank, world, barrier, max_over_ranks):
+    """Config D: ONE fixed sweep of 8192 images of 320x480, split over the ranks by shard_range
+    (strong scaling).  Every rank cycles through its resident 256-image pool to cover its share
+    (the cost of the path does not depend on the image content; generating 8192 distinct images
+    on the host would only time the generator)."""
+    import torch
+    total = int(os.environ.get("GG_SWEEP_IMAGES", "8192"))
+    B = int(img_d.shape[0])
+    lo, hi = path.shard(total, rank, world)
+    mine = hi - lo
+    sizes = [B] * (mine // B) + ([mine % B] if mine % B else [])
+    tri_d = torch.empty((B,) + tuple(img_d.shape[1:3]), dtype=torch.uint8, device=dev)
+    # device-resident
+    for _ in range(2):
+        path.run_device(img_d, lab_d, tri_d)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    checksum = torch.zeros((), dtype=torch.int64, device=dev)
+    for n in sizes:
+        path.run_device(img_d[:n], lab_d[:n], tri_d[:n])
+        checksum += tri_d[:n].sum(dtype=torch.int64)
+    e1.record()
+    barrier()
+    path.check_status()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    # end to end (pinned host buffers, streaming submit / result)
+    depth = 2
+    tri_pins = [torch.empty((B,) + tuple(img_d.shape[1:3]), dtype=torch.uint8).pin_memory() for _ in range(depth + 1)]
+    pend = [path.submit(img_pin, lab_pin, out=tri_pins[0])]
+    pend.pop(0).result()
+    barrier()
+    t0 = time.perf_counter()
+    pend = []
+    for i, n in enumerate(sizes):
+        pend.append(path.submit(img_pin[:n], lab_pin[:n], out=tri_pins[i % (depth + 1)][:n]))
+        if len(pend) > depth:
+            pend.pop(0).result()
+    for p_ in pend:
+        p_.result()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # final gather of the per-rank results (the only collective of the sweep, after the timed region)
+    mine_t = torch.tensor([mine, int(checksum.item())], dtype=torch.int64, device=dev)
+    if world > 1:
+        parts = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(parts, mine_t)
+    else:
+        parts = [mine_t]
+    counts = [int(p_[0].item()) for p_ in parts]
+    assert sum(counts) == total, (counts, total)
+    return {"workload": f"D: one sweep of {total} synthetic 320x480 images (~300 regions) sharded per image over "
+                        f"{world} GPU(s) by shard_range, batches of {B}",
+            "scaling": "strong", "images": total, "images_per_rank": counts,
+            "trimap_checksums_per_rank": [int(p_[1].item()) for p_ in parts],
+            "value": total / (ms * 1e-3), "unit": UNIT, "sweep_ms": ms,
+            "e2e": {"value": total / e2e_s, "unit": UNIT, "sweep_ms": 1e3 * e2e_s,
+                    "h2d_bytes": int(7 * total * img_d.shape[1] * img_d.shape[2]),
+                    "d2h_bytes": int(total * img_d.shape[1] * img_d.shape[2])},
+            "data": f"synthetic; each rank cycles its resident pool of {B} images to cover its shard",
+            "gather": "dist.all_gather of (images processed, trimap checksum) per rank after the timed region"
+                      if world > 1 else "single rank"}
+
+
 def run_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -286,9 +588,11 @@ def run_ours(a):
     os.dup2(2, 1)
     numa_cpus = bind_to_gpu_numa(local) if world > 1 else None
     cores = len(os.sched_getaffinity(0)) if numa_cpus else (os.cpu_count() or 1)
+    extras = rank == 0 and world == 1 and not os.environ.get("GG_BENCH_NO_EXTRAS")
 
     # ---- CPU baseline first (fork pool before CUDA is initialised), rank 0 at N=1 only
     cpu_baseline = None
+    ref_a = None
     pool_cores = max(1, min(cores, 16)) if numa_cpus else max(1, min(cores, 64) // max(world, 1))
     import multiprocessing as mp
     gen_pool = mp.get_context("fork").Pool(pool_cores)
@@ -301,9 +605,16 @@ def run_ours(a):
         cpu.run(imgs[:min(cores, sample)], labs[:min(cores, sample)])            # warm-up (imports, page-in)
         dt = cpu.run(imgs[:sample], labs[:sample])
         cpu.close()
-        cpu_baseline = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu_baseline = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": cpu.kind,
                         "sample": f"{sample} images of the same batch in {dt:.2f} s wall, one process per core "
-                                  f"(1 BLAS/OpenCV thread each), label maps supplied (SLIC excluded)"}
+                                  f"(1 BLAS/OpenCV thread each), label maps supplied (SLIC excluded); "
+                                  + ("the reference's own files (oracle/_ref) over the third-party shims"
+                                     if cpu.kind == "reference" else "oracle port")}
+        if extras:
+            try:
+                ref_a = reference_segment_timing(a.hidden, a.layers)
+            except Exception as e:      # the CPU side of config A is a report, never a reason to lose the line
+                ref_a = {"error": repr(e)}
 
     import torch
     import torch.distributed as dist
@@ -347,7 +658,7 @@ def run_ours(a):
     # ---- device-resident throughput
     for _ in range(a.warmup):
         path.run_device(img_d, lab_d, tri_d)
-    h.check_status(nat.current_stream(local))
+    path.check_status()
     barrier()
     l0 = h.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -359,53 +670,22 @@ def run_ours(a):
     barrier()
     t_wall1 = time.perf_counter()
     launches = h.launches() - l0
+    path.check_status()              # a silent overflow (clamped labels) must not produce a headline number
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * a.steps / (ms * 1e-3)
     clocks = sampler.window(t_wall0, t_wall1) if sampler else None
 
     # ---- per-kernel CUDA-event timing of the same steps (events on the launching stream)
     n_sub = int(os.environ.get("GG_SUBBATCH", "2"))
-    h.set_option("n_sub", 1)            # one batch at a time, so that kernel durations do not overlap
-    h.profile(True)
-    for _ in range(a.steps):
-        path.run_device(img_d, lab_d, tri_d)
-    rows = [(name.rstrip(")"), n, ms) for name, n, ms in h.profile_report()]
-    h.profile(False)
-    h.set_option("n_sub", n_sub)
+    _, _, rows = measure_device(path, h, img_d, lab_d, tri_d, a.steps, 0, None)
     tri_host_check = tri_d[:2].cpu().numpy()
     assert set(np.unique(tri_host_check)).issubset({0, 1, 2, 3})
-    total_prof_ms = sum(r[2] for r in rows)
-    top = rows[0]
     # average directed edges per image from the builder (second pass, cheap)
     g = gg.build_graph_batch(img_d[:8], lab_d[:8], gg.SuperpixelGraphConfig(n_segments=a.segments,
                                                                            n_nonlocal=a.nonlocal_k), node_cap=node_cap)
     E_avg = float(g.edge_off[-1].item()) / 8
     N_avg = float(g.node_off[-1].item()) / 8
-    per_img, what = algorithmic_bytes_per_image(top[0], H * W, N_avg, E_avg)
-    launches_per_step = top[1] / a.steps
-    avg_launch_ms = top[2] / top[1]
-    alg_bytes_per_launch = per_img * B / launches_per_step
-    achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
-    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic, traffic_src = None, None
-    tpath = os.path.join(REPO, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and (H, W) == (320, 480):       # the capture is of this workload
-        base = top[0].split("<")[0]
-        ent = json.load(open(tpath))["kernels"].get(base)
-        if ent:
-            traffic = ent["bytes_per_image_per_launch"] * B / launches_per_step
-            traffic_src = "profiles/" + ent["source"]
-    roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "algorithmic_model": what,
-                "avg_launch_ms": avg_launch_ms, "share_of_step": top[2] / total_prof_ms,
-                "kernels_ms_per_step": {r[0]: round(r[2] / a.steps, 4) for r in rows[:40]},
-                "profiled_step_ms": total_prof_ms / a.steps}
+    roofline = roofline_record(rows, a.steps, B, H, W, N_avg, E_avg)
 
     # ---- end to end through the host-buffer entry point.  Every step copies its 256 images and
     # label maps from pinned host memory and its trimaps back.  Two figures: one synchronous call
@@ -463,21 +743,43 @@ def run_ours(a):
     if sampler:
         sampler.stop()
 
+    # ---- config D: the fixed 8192-image sweep, strong scaling, final gather (every N)
+    config_d = None
+    if (H, W) == (320, 480) and not os.environ.get("GG_BENCH_NO_SWEEP"):
+        config_d = run_config_d(a, gg, nat, dist, dev, path, img_pin, lab_pin, img_d, lab_d, rank, world, barrier,
+                                max_over_ranks)
+
+    # ---- the other BASELINE configs on this GPU (N = 1 runs only; bounded: a few seconds each)
+    other = {}
+    if extras and (H, W) == (320, 480):
+        del img_d, lab_d, tri_d
+        torch.cuda.empty_cache()
+        try:
+            other["A"] = {"gpu": run_config_a(gg, nat, dev, a.hidden, a.layers), "cpu_reference_segment": ref_a,
+                          "workload": "A: one 320x480 synthetic image, ~300 regions, random-init ResGCNNet(D=128, n=6)"}
+            other["C"] = run_other_config(gg, nat, dev, "C", 64, 1080, 1920, 2000, 16, 128, 6, a.radius, 10, 3, cores)
+            other["E"] = run_other_config(gg, nat, dev, "E", 8, 2160, 3840, 10000, 4, 256, 8, a.radius, 10, 3, cores)
+        except Exception as e:      # the headline line must survive a failure of an extra record
+            other["error"] = repr(e)
+
     if rank == 0:
-        cfg = workload_config(a)
-        cfg.update({"parallelism": f"{world} x 1 GPU, images sharded, no data-path collective"
-                                   + (f", each rank bound to its GPU's {numa_cpus} local cores" if numa_cpus else ""),
-                    "l2": f"inputs per step {(img_pin.numel() + lab_pin.numel() * 4) / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
-                    "avg_nodes_per_image": N_avg, "avg_directed_edges_per_image": E_avg,
-                    "gemm_impl": "tcgen05" if os.environ.get("GG_GEMM_IMPL", "tc") != "simt" else "simt",
-                    "concurrent_sub_batches": n_sub})
+        run = {"parallelism": f"{world} x 1 GPU, images sharded, no data-path collective"
+                              + (f", each rank bound to its GPU's {numa_cpus} local cores" if numa_cpus else ""),
+               "l2": f"inputs per step {(img_pin.numel() + lab_pin.numel() * 4) / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+               "avg_nodes_per_image": N_avg, "avg_directed_edges_per_image": E_avg,
+               "gemm_impl": "tcgen05" if os.environ.get("GG_GEMM_IMPL", "tc") != "simt" else "simt",
+               "concurrent_sub_batches": n_sub}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32 (fp64 region/window sums)", "data": "synthetic",
-               "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+               "config": workload_config(a), "run": run, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                "roofline": roofline}
         if cpu_baseline:
             out["cpu_baseline"] = cpu_baseline
+        if config_d:
+            out["config_D"] = config_d
+        if other:
+            out["other_configs"] = other
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

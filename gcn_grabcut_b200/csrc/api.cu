@@ -23,6 +23,7 @@ void set_error(const char* fmt, ...) {
 
 int Arena::reserve(size_t bytes) {
   off = 0;
+  overflowed = false;
   if (bytes <= cap) return GG_OK;
   if (base) {
     GG_CUDA_OK(cudaDeviceSynchronize());   // the old buffer may still be in use by queued work
@@ -40,6 +41,17 @@ void Arena::release() {
   if (base) cudaFree(base);
   base = nullptr;
   cap = off = 0;
+}
+
+// an entry point whose kernels were handed workspace past the reservation fails (the estimate in
+// *_workspace_bytes disagrees with the takes: a bug, reported instead of corrupting memory)
+static int arena_checked(Arena& ar, int rc, const char* what) {
+  if (ar.overflowed) {
+    ar.overflowed = false;
+    set_error("%s: internal workspace overflow (reserved %zu bytes)", what, ar.cap);
+    return GG_ERR_INVALID;
+  }
+  return rc;
 }
 
 static cudaEvent_t prof_event(gg_context* ctx) {
@@ -188,7 +200,6 @@ static int run_path_multi(gg_context* ctx, Arena& ar, const uint8_t* bgr, const 
   const int per = (B + S - 1) / S;
   const size_t slice = path_workspace_bytes(ctx, per, H, W, pc);
   cudaEvent_t ev_fork = ctx->ev[12];
-  GG_CUDA_OK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));
   GG_CUDA_OK(cudaEventRecord(ev_fork, st));
   int rc = GG_OK;
   for (int s = 0; s < S && rc == GG_OK; ++s) {
@@ -206,6 +217,7 @@ static int run_path_multi(gg_context* ctx, Arena& ar, const uint8_t* bgr, const 
     rc = run_path(ctx, sub, bgr + (size_t)b0 * npx * 3, labels + (size_t)b0 * npx, nb, H, W, pc,
                   trimap + (size_t)b0 * npx, nullptr, nullptr, n_nodes_out ? n_nodes_out + b0 : nullptr,
                   n_edges_out ? n_edges_out + b0 : nullptr, ss, ctx->ev[17 + s]);
+    if (sub.overflowed) ar.overflowed = true;
     if (rc == GG_OK) {
       GG_LAUNCH(ctx, k_status_or, 1, 1, 0, ss, ctx->d_status + 8 + s, ctx->d_status);
       GG_CUDA_OK(cudaEventRecord(ctx->ev[13 + s], ss));
@@ -258,6 +270,8 @@ int gg_create(gg_handle* out, int device) {
   c->cc_minor = prop.minor;
   GG_CUDA_OK(cudaMalloc((void**)&c->d_status, 64));
   GG_CUDA_OK(cudaMemset(c->d_status, 0, 64));
+  GG_CUDA_OK(cudaHostAlloc((void**)&c->h_ticket_status, gg_context::MAX_TICKETS * sizeof(int), cudaHostAllocDefault));
+  memset(c->h_ticket_status, 0, gg_context::MAX_TICKETS * sizeof(int));
   c->status_word = c->d_status;
   double lin[256];
   for (int v = 0; v < 256; ++v) lin[v] = srgb_linear(v);
@@ -288,6 +302,7 @@ void gg_destroy(gg_handle h) {
   if (h->net.blob) cudaFree(h->net.blob);
   if (h->net.tc_blob) cudaFree(h->net.tc_blob);
   if (h->d_status) cudaFree(h->d_status);
+  if (h->h_ticket_status) cudaFreeHost(h->h_ticket_status);
   if (h->d_lin) cudaFree(h->d_lin);
   if (h->d_coord) cudaFree(h->d_coord);
   for (auto& ev : h->ev) cudaEventDestroy(ev);
@@ -312,6 +327,7 @@ int gg_check_device_status(gg_handle h, void* stream, int* status_bits) {
   GG_REQUIRE(h && status_bits, "gg_check_device_status: null");
   GG_CUDA_OK(cudaSetDevice(h->device));
   GG_CUDA_OK(cudaMemcpyAsync(status_bits, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  GG_CUDA_OK(cudaMemsetAsync(h->d_status, 0, sizeof(int), (cudaStream_t)stream));   // read-and-clear
   GG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
   if (*status_bits) {
     set_error("device status 0x%x:%s%s%s", *status_bits,
@@ -330,7 +346,8 @@ int gg_build_graphs(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_d
   const gg_graph_config c = norm_cfg(*cfg);
   GG_REQUIRE(c.node_cap > 0 && B > 0 && H > 0 && W > 0, "gg_build_graphs: bad sizes");
   GG_TRY(h->arena.reserve(graph_workspace_bytes(B, H, W, c)));
-  return build_graphs(h, h->arena, bgr_dev, labels_dev, B, H, W, c, *out, (cudaStream_t)stream, nullptr);
+  return arena_checked(h->arena, build_graphs(h, h->arena, bgr_dev, labels_dev, B, H, W, c, *out, (cudaStream_t)stream, nullptr),
+                       "gg_build_graphs");
 }
 
 int gg_pixel_planes(gg_handle h, const uint8_t* bgr_dev, int B, int H, int W, float* lab_dev,
@@ -352,8 +369,8 @@ int gg_coo_to_csr(gg_handle h, const int64_t* edge_index_dev, int64_t n_edges, i
              "gg_coo_to_csr: null argument");
   GG_CUDA_OK(cudaSetDevice(h->device));
   GG_TRY(h->arena.reserve(Arena::padded((size_t)n_nodes, 4) + 4096));
-  return coo_to_csr(h, h->arena, edge_index_dev, n_edges, n_nodes, csr_rowptr_dev, csr_src_dev, csr_eid_dev,
-                    (cudaStream_t)stream);
+  return arena_checked(h->arena, coo_to_csr(h, h->arena, edge_index_dev, n_edges, n_nodes, csr_rowptr_dev, csr_src_dev,
+                                            csr_eid_dev, (cudaStream_t)stream), "gg_coo_to_csr");
 }
 
 int gg_resgcn_forward(gg_handle h, const float* x_dev, const int32_t* csr_rowptr_dev,
@@ -365,10 +382,9 @@ int gg_resgcn_forward(gg_handle h, const float* x_dev, const int32_t* csr_rowptr
   GG_CUDA_OK(cudaSetDevice(h->device));
   if (!h->net.loaded) { set_error("gg_resgcn_forward: call gg_load_weights first"); return GG_ERR_STATE; }
   GG_TRY(h->arena.reserve(resgcn_workspace_bytes(h->net, node_cap_total, edge_cap_total, n_graphs)));
-  GG_CUDA_OK(cudaMemsetAsync(h->d_status, 0, sizeof(int), (cudaStream_t)stream));
-  return resgcn_forward(h, h->arena, x_dev, csr_rowptr_dev, csr_src_dev, csr_eid_dev, edge_attr_dev,
-                        graph_off_dev, n_graphs, node_cap_total, edge_cap_total, logits_dev, probs_dev,
-                        (cudaStream_t)stream);
+  return arena_checked(h->arena, resgcn_forward(h, h->arena, x_dev, csr_rowptr_dev, csr_src_dev, csr_eid_dev, edge_attr_dev,
+                                                graph_off_dev, n_graphs, node_cap_total, edge_cap_total, logits_dev,
+                                                probs_dev, (cudaStream_t)stream), "gg_resgcn_forward");
 }
 
 int gg_refine_trimap(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, const float* probs_dev,
@@ -377,8 +393,9 @@ int gg_refine_trimap(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_
   GG_REQUIRE(h && bgr_dev && labels_dev && probs_dev && node_off_dev && trimap_dev, "gg_refine_trimap: null argument");
   GG_CUDA_OK(cudaSetDevice(h->device));
   GG_TRY(h->arena.reserve(trimap_workspace_bytes(B, H, W, true)));
-  return refine_trimap(h, h->arena, bgr_dev, nullptr, labels_dev, probs_dev, node_off_dev, B, H, W, radius, eps,
-                       thr_fg, thr_bg, trimap_dev, p_bg_dev, p_fg_dev, (cudaStream_t)stream);
+  return arena_checked(h->arena, refine_trimap(h, h->arena, bgr_dev, nullptr, labels_dev, probs_dev, node_off_dev, B, H, W,
+                                               radius, eps, thr_fg, thr_bg, trimap_dev, p_bg_dev, p_fg_dev,
+                                               (cudaStream_t)stream), "gg_refine_trimap");
 }
 
 int gg_project_trimap(gg_handle h, const int32_t* labels_dev, const float* probs_dev,
@@ -397,8 +414,10 @@ int gg_region_labels(gg_handle h, const int32_t* labels_dev, const uint8_t* gt_m
   GG_REQUIRE(B > 0 && H > 0 && W > 0 && node_cap_total > 0, "gg_region_labels: bad sizes");
   GG_CUDA_OK(cudaSetDevice(h->device));
   GG_TRY(h->arena.reserve(2 * Arena::padded((size_t)node_cap_total, 4) + 1024));
-  return region_labels(h, h->arena, labels_dev, gt_mask_dev, node_off_dev, B, H, W, node_cap_total, fg_threshold,
-                       bg_threshold, fg_ratio_dev, reinterpret_cast<long long*>(y_dev), (cudaStream_t)stream);
+  return arena_checked(h->arena, region_labels(h, h->arena, labels_dev, gt_mask_dev, node_off_dev, B, H, W, node_cap_total,
+                                               fg_threshold, bg_threshold, fg_ratio_dev,
+                                               reinterpret_cast<long long*>(y_dev), (cudaStream_t)stream),
+                       "gg_region_labels");
 }
 
 int gg_seed_from_prior(gg_handle h, uint8_t* trimap_dev, const int32_t* labels_dev, const float* x_dev,
@@ -408,8 +427,8 @@ int gg_seed_from_prior(gg_handle h, uint8_t* trimap_dev, const int32_t* labels_d
   GG_REQUIRE(B > 0 && H > 0 && W > 0 && node_cap_total > 0, "gg_seed_from_prior: bad sizes");
   GG_CUDA_OK(cudaSetDevice(h->device));
   GG_TRY(h->arena.reserve(seed_workspace_bytes(B, node_cap_total)));
-  return seed_from_prior(h, h->arena, trimap_dev, labels_dev, x_dev, node_off_dev, B, H, W, node_cap_total,
-                         seed_frac, (cudaStream_t)stream);
+  return arena_checked(h->arena, seed_from_prior(h, h->arena, trimap_dev, labels_dev, x_dev, node_off_dev, B, H, W,
+                                                 node_cap_total, seed_frac, (cudaStream_t)stream), "gg_seed_from_prior");
 }
 
 int gg_guided_filter(gg_handle h, const float* guide_dev, const float* src_dev, int H, int W, int radius,
@@ -417,7 +436,8 @@ int gg_guided_filter(gg_handle h, const float* guide_dev, const float* src_dev, 
   GG_REQUIRE(h && guide_dev && src_dev && out_dev, "gg_guided_filter: null argument");
   GG_CUDA_OK(cudaSetDevice(h->device));
   GG_TRY(h->arena.reserve(Arena::padded((size_t)H * W * 2, 4) + 4096));
-  return guided_filter_plane(h, h->arena, guide_dev, src_dev, H, W, radius, eps, out_dev, (cudaStream_t)stream);
+  return arena_checked(h->arena, guided_filter_plane(h, h->arena, guide_dev, src_dev, H, W, radius, eps, out_dev,
+                                                     (cudaStream_t)stream), "gg_guided_filter");
 }
 
 int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, int B, int H, int W,
@@ -427,8 +447,9 @@ int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* la
   GG_CUDA_OK(cudaSetDevice(h->device));
   if (!h->net.loaded) { set_error("gg_trimap_path_device: call gg_load_weights first"); return GG_ERR_STATE; }
   GG_TRY(h->arena.reserve(path_multi_workspace_bytes(h, B, H, W, *cfg)));
-  return run_path_multi(h, h->arena, bgr_dev, labels_dev, B, H, W, *cfg, trimap_dev, probs_dev, node_off_dev,
-                        nullptr, nullptr, (cudaStream_t)stream);
+  return arena_checked(h->arena, run_path_multi(h, h->arena, bgr_dev, labels_dev, B, H, W, *cfg, trimap_dev, probs_dev,
+                                                node_off_dev, nullptr, nullptr, (cudaStream_t)stream),
+                       "gg_trimap_path_device");
 }
 
 // Host buffers in, host trimaps out.  The batch is cut into chunks; chunk i+1 is copied in
@@ -503,6 +524,7 @@ static int host_submit(gg_handle h, const uint8_t* bgr_host, const void* labels_
                       rs);
     h->status_word = h->d_status;
     h->rs_direct = 1;
+    st = arena_checked(ar, st, "gg_trimap_path_host");
     if (st != GG_OK) { cudaDeviceSynchronize(); return st; }
     // accumulate the per-chunk device status into the sticky word
     GG_LAUNCH(h, k_status_or, 1, 1, 0, rs, h->d_status + 2 + par, h->d_status + 1);
@@ -511,9 +533,12 @@ static int host_submit(gg_handle h, const uint8_t* bgr_host, const void* labels_
     GG_CUDA_OK(cudaMemcpyAsync(trimap_host + (size_t)b0 * npx, d_tri, (size_t)nb * npx, cudaMemcpyDeviceToHost, h->s_out));
     GG_CUDA_OK(cudaEventRecord(ev_out[s], h->s_out));
   }
-  // s_out has waited for the compute of every chunk of this call, in order
+  // s_out has waited for the compute of every chunk of this call, in order: the sticky status
+  // word, as it stands when this call's last chunk is done, travels to the ticket's pinned host
+  // word on s_out -- _wait never has to touch a stream that later calls are queued on
   int t = 0;
   while (h->ticket_open[t]) ++t;
+  GG_CUDA_OK(cudaMemcpyAsync(h->h_ticket_status + t, h->d_status + 1, sizeof(int), cudaMemcpyDeviceToHost, h->s_out));
   GG_CUDA_OK(cudaEventRecord(h->ticket_ev[t], h->s_out));
   h->ticket_open[t] = true;
   h->tickets_open++;
@@ -530,9 +555,7 @@ int gg_trimap_path_host_wait(gg_handle h, int ticket) {
   h->ticket_open[ticket] = false;
   h->tickets_open--;
   GG_CUDA_OK(cudaEventSynchronize(h->ticket_ev[ticket]));
-  int dev_bits = 0;
-  GG_CUDA_OK(cudaMemcpyAsync(&dev_bits, h->d_status + 1, sizeof(int), cudaMemcpyDeviceToHost, h->s_in));
-  GG_CUDA_OK(cudaStreamSynchronize(h->s_in));
+  const int dev_bits = h->h_ticket_status[ticket];
   if (dev_bits) {
     GG_CUDA_OK(cudaDeviceSynchronize());
     GG_CUDA_OK(cudaMemset(h->d_status + 1, 0, sizeof(int)));

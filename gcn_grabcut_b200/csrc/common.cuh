@@ -54,9 +54,14 @@ struct Arena {
   size_t off = 0;
   int reserve(size_t bytes);
   void reset() { off = 0; }
+  bool overflowed = false;   // a take() went past the reservation (workspace-size bug): sticky
   template <typename T>
   T* take(size_t n) {
     size_t b = (n * sizeof(T) + 255) & ~size_t(255);
+    if (off + b > cap) {       // never hand out memory past the reservation; the entry point fails
+      overflowed = true;
+      return reinterpret_cast<T*>(base);
+    }
     T* p = reinterpret_cast<T*>(base + off);
     off += b;
     return p;
@@ -115,6 +120,7 @@ struct gg_context {
   static constexpr int MAX_TICKETS = 8;
   cudaEvent_t ticket_ev[MAX_TICKETS] = {};
   bool ticket_open[MAX_TICKETS] = {};
+  int* h_ticket_status = nullptr;   // pinned [MAX_TICKETS]: sticky device status as of each ticket's completion
   int tickets_open = 0;
   long long chunk_seq = 0;
   size_t slot_bytes = 0;
@@ -140,6 +146,17 @@ struct gg_context {
 namespace gg {
 void prof_begin(gg_context* ctx, const char* name, cudaStream_t st);
 void prof_end(gg_context* ctx, cudaStream_t st);
+// Start of a status epoch for the kernels about to be enqueued.  The per-sub-batch / per-chunk
+// words are cleared here and OR-ed into a sticky word when their work is done; the main word
+// d_status[0] is sticky itself -- only gg_check_device_status reads and clears it, so that a bit
+// set by one call (e.g. gg_coo_to_csr) survives the calls that follow it (gg_resgcn_forward).
+static inline int status_epoch(gg_context* ctx, cudaStream_t st) {
+  if (ctx->status_word != ctx->d_status) {
+    cudaError_t e = cudaMemsetAsync(ctx->status_word, 0, sizeof(int), st);
+    if (e != cudaSuccess) { set_error("status_epoch: %s", cudaGetErrorString(e)); return GG_ERR_CUDA; }
+  }
+  return GG_OK;
+}
 }
 
 #define GG_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)        \

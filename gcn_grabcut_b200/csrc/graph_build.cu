@@ -1464,7 +1464,7 @@ int region_labels(gg_context* ctx, Arena& ar, const int32_t* labels, const uint8
   int* fg = ar.take<int>((size_t)node_cap_total);
   GG_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)node_cap_total * sizeof(int), st));
   GG_CUDA_OK(cudaMemsetAsync(fg, 0, (size_t)node_cap_total * sizeof(int), st));
-  GG_CUDA_OK(cudaMemsetAsync(ctx->status_word, 0, sizeof(int), st));
+  GG_TRY(status_epoch(ctx, st));
   dim3 grid(std::min(ceil_div(HW, 256), 148), B);
   GG_LAUNCH(ctx, k_mask_counts, grid, 256, 0, st, labels, mask, node_off, HW, cnt, fg, ctx->status_word);
   GG_LAUNCH(ctx, k_region_labels, ceil_div(node_cap_total, 256), 256, 0, st, cnt, fg, node_off, B, fg_thr,
@@ -1638,7 +1638,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
   GG_CUDA_OK(cudaMemsetAsync(pcnts, 0, (size_t)B * tc * sizeof(int), st));
   GG_CUDA_OK(cudaMemsetAsync(gradmax, 0, (size_t)B * 4 * sizeof(int), st));
   GG_CUDA_OK(cudaMemsetAsync(label_max, 0xFF, (size_t)B * 4 * sizeof(int), st));
-  GG_CUDA_OK(cudaMemsetAsync(ctx->status_word, 0, sizeof(int), st));
+  GG_TRY(status_epoch(ctx, st));
 
   {
     if (W % 4 == 0 && ((uintptr_t)bgr & 3) == 0 && ((uintptr_t)gray & 3) == 0) {

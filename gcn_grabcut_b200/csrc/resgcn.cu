@@ -1044,7 +1044,7 @@ int coo_to_csr(gg_context* ctx, Arena& ar, const int64_t* ei, long long E, long 
   GG_REQUIRE(N > 0 && E >= 0 && N < (1ll << 31) && E < (1ll << 31), "coo_to_csr: bad sizes");
   int* cnt = ar.take<int>((size_t)N);
   GG_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)N * sizeof(int), st));
-  GG_CUDA_OK(cudaMemsetAsync(ctx->status_word, 0, sizeof(int), st));
+  GG_TRY(status_epoch(ctx, st));
   if (E > 0) GG_LAUNCH(ctx, k_coo_count, ceil_div(E, 256), 256, 0, st, ei, E, N, cnt, ctx->status_word);
   GG_LAUNCH(ctx, k_coo_scan, 1, 1024, 0, st, cnt, rowptr, N);
   if (E > 0) GG_LAUNCH(ctx, k_coo_fill, ceil_div(E, 256), 256, 0, st, ei, E, N, rowptr, cnt, src, eid);

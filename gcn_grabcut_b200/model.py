@@ -147,6 +147,7 @@ if _TORCH:
                         nn.init.zeros_(m.bias)
             self._gg_device: Optional[int] = None
             self._gg_dirty = True
+            self._gg_version = -1
             self.requires_grad_(False)
             self.eval()
 
@@ -173,10 +174,14 @@ if _TORCH:
                 raise nat.NativeError(nat.GG_ERR_CUDA, "ResGCNNet needs a CUDA device (no CPU fallback); "
                                                        "call model.to('cuda')")
             h = nat.handle(device)
-            if self._gg_dirty or h.weights_token is not self:
+            # in-place edits (p.data.copy_, an optimiser step over param_groups(),
+            # vector_to_parameters) bump the tensors' version counters: reload on any change
+            version = sum(int(t._version) for t in self.state_dict().values())
+            if self._gg_dirty or h.weights_token is not self or version != self._gg_version:
                 nat.load_state_dict(h, self.state_dict())
                 h.weights_token = self
                 self._gg_dirty = False
+                self._gg_version = version
             return h
 
         # -- inference

@@ -200,8 +200,19 @@ class TrimapPath:
                                                            nat.ptr(ne_), C.byref(ticket)))
         return PendingTrimaps(self, ticket.value, (img, lab), tri_t, torch.is_tensor(out), nn_, ne_)
 
-    def run_device(self, images_t, labels_t, trimap_t=None, probs_t=None, node_off_t=None):
-        """CUDA tensors in, CUDA trimaps out, on the current stream, no host synchronisation."""
+    def check_status(self) -> None:
+        """Read (and clear) the device status word of the ``run_device`` calls enqueued so far on
+        the current stream; raises ``NativeError`` (GG_ERR_CAPACITY) if any of them saw a label
+        >= ``node_cap`` or overflowed the pair / edge capacity -- such a batch's trimaps are NOT
+        valid (out-of-range labels are clamped on the device).  Synchronises the stream."""
+        import torch
+        with torch.cuda.device(self.dev):
+            self.h.check_status(nat.current_stream(self.dev))
+
+    def run_device(self, images_t, labels_t, trimap_t=None, probs_t=None, node_off_t=None, check: bool = False):
+        """CUDA tensors in, CUDA trimaps out, on the current stream, no host synchronisation
+        (``check=False``).  The device status is sticky: call ``check_status()`` once after a run of
+        calls, or pass ``check=True`` to synchronise and verify this call."""
         import torch
         self._ensure_weights()
         B, H, W = int(images_t.shape[0]), int(images_t.shape[1]), int(images_t.shape[2])
@@ -212,6 +223,8 @@ class TrimapPath:
                 self.h.ptr, nat.ptr(images_t, torch.uint8), nat.ptr(labels_t, torch.int32), B, H, W,
                 C.byref(self.pc), nat.ptr(trimap_t), nat.ptr(probs_t), nat.ptr(node_off_t),
                 C.c_void_p(nat.current_stream(self.dev))))
+        if check:
+            self.check_status()
         return trimap_t
 
     def shard(self, n_items: int, rank: int, world_size: int) -> Tuple[int, int]:

@@ -24,6 +24,12 @@
  *     exactly as in the reference: graph_builder.py:158, :194-195).
  *   - there is no CPU fallback: every entry point fails with GG_ERR_CUDA when no
  *     sm_100 device is usable.
+ *   - threading contract: a handle is SINGLE-THREADED and its device-pointer calls must be
+ *     STREAM-ORDERED -- all of them share one workspace arena, one status word and a few
+ *     events, none of which is locked.  Consecutive calls on one handle must be enqueued on the
+ *     same stream (or on streams the caller has ordered with events); use one handle per host
+ *     thread / per concurrently used stream.  The whole-path entry points fork onto internal
+ *     streams and join back into the caller's stream themselves.
  */
 #ifndef GCN_GRABCUT_B200_H
 #define GCN_GRABCUT_B200_H
@@ -65,9 +71,14 @@ void gg_destroy(gg_handle h);
  * cut a batch into, 1..4 (default 2; env GG_SUBBATCH). */
 int gg_set_option(gg_handle h, const char* key, int value);
 
-/* Device-side status word written by the kernels of the last enqueued call:
- * bit0 label >= node_cap, bit1 adjacency table overflow, bit2 edge capacity overflow.
- * Synchronises the given stream. */
+/* Device-side status word of the device-pointer entry points: bit0 label / edge index out of
+ * range (>= node_cap, >= n_nodes), bit1 adjacency table overflow, bit2 pair / edge capacity
+ * overflow.  The word is STICKY: every kernel ORs into it and only this call reads and clears
+ * it, so one check after a run of calls (gg_coo_to_csr + gg_resgcn_forward, or many
+ * gg_trimap_path_device steps) reports an overflow of any of them.  The device-pointer entry
+ * points never synchronise, so they cannot report these conditions themselves: a batch whose
+ * status is non-zero has clamped labels / dropped edges and its outputs are NOT valid.
+ * Returns GG_ERR_CAPACITY when a bit is set.  Synchronises the given stream. */
 int gg_check_device_status(gg_handle h, void* stream, int* status_bits);
 
 /* ------------------------------------------------------------------ graph construction

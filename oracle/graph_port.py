@@ -148,33 +148,61 @@ def adjacency_pairs(seg: np.ndarray, n: int, connectivity: int = 4):
     return pairs, cnt
 
 
-def nonlocal_pairs(adj: np.ndarray, mean_lab: np.ndarray, n: int, k: int):
+def _adjacency_csr(adj: np.ndarray, n: int):
+    """Symmetric adjacency as CSR (indptr, indices) -- the row-blocked form of the reference's
+    N x N boolean mask (graph_builder.py:337-340)."""
+    a = np.concatenate([adj[:, 0], adj[:, 1]]).astype(np.int64)
+    b = np.concatenate([adj[:, 1], adj[:, 0]]).astype(np.int64)
+    order = np.argsort(a, kind="stable")
+    a, b = a[order], b[order]
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(indptr, a + 1, 1)
+    return np.cumsum(indptr), b
+
+
+def nonlocal_pairs(adj: np.ndarray, mean_lab: np.ndarray, n: int, k: int,
+                   tie_break: str = "argpartition", block: int = 512):
     """
     graph_builder.py:324-350 -- k nearest neighbours in mean-Lab space, spatially adjacent
     pairs excluded, symmetrised.  Returns (pairs, n_ties): ``n_ties`` counts rows whose
     k-th and (k+1)-th candidate distances are equal -- there np.argpartition's choice is
     implementation-defined and a different (valid) selection is possible.
+
+    The reference materialises the N x N distance matrix (400 MB at N = 10^4); every row of
+    it is independent, so the same arithmetic is evaluated here in blocks of ``block`` rows
+    (identical float32 operations per element, identical result).
+
+    ``tie_break``: "argpartition" = the reference's call (whatever numpy's introselect picks
+    among equal distances); "lower_index" = the rule the CUDA path documents (equal
+    distances -> the lower region index first), i.e. a stable sort on (distance, index).
+    Both agree whenever ``n_ties == 0``.
     """
-    diff = mean_lab[:, None, :] - mean_lab[None, :, :]
-    sq = diff * diff
-    d = np.sqrt((sq[:, :, 0] + sq[:, :, 1]) + sq[:, :, 2])     # float32, left-to-right (:334)
-    np.fill_diagonal(d, np.inf)
-    mask = np.zeros((n, n), dtype=bool)
-    mask[adj[:, 0], adj[:, 1]] = True
-    mask[adj[:, 1], adj[:, 0]] = True
-    d[mask] = np.inf
-
+    indptr, indices = _adjacency_csr(adj, n)
     kth = min(k, n - 1) - 1
-    nbrs = np.argpartition(d, kth=kth, axis=1)[:, :k]
-    rows = np.repeat(np.arange(n), k)
-    cols = nbrs.ravel()
-    ok = np.isfinite(d[rows, cols])
-    rows, cols = rows[ok], cols[ok]
-    lo, hi = np.minimum(rows, cols).astype(np.int64), np.maximum(rows, cols).astype(np.int64)
-    codes = np.unique(lo * n + hi)
-
-    srt = np.sort(d, axis=1)
-    n_ties = int(np.sum((srt[:, k - 1] == srt[:, k]) & np.isfinite(srt[:, k - 1]))) if n > k else 0
+    codes, n_ties = [], 0
+    for r0 in range(0, n, block):
+        r1 = min(n, r0 + block)
+        diff = mean_lab[r0:r1, None, :] - mean_lab[None, :, :]
+        sq = diff * diff
+        d = np.sqrt((sq[:, :, 0] + sq[:, :, 1]) + sq[:, :, 2])     # float32, left-to-right (:334)
+        rr = np.arange(r0, r1)
+        d[rr - r0, rr] = np.inf                                     # fill_diagonal
+        reps = indptr[r0 + 1:r1 + 1] - indptr[r0:r1]
+        d[np.repeat(rr - r0, reps), indices[indptr[r0]:indptr[r1]]] = np.inf      # adjacent pairs
+        if tie_break == "lower_index":
+            nbrs = np.argsort(d, axis=1, kind="stable")[:, :k]
+        else:
+            nbrs = np.argpartition(d, kth=kth, axis=1)[:, :k]
+        rows = np.repeat(rr, nbrs.shape[1])
+        cols = nbrs.ravel()
+        ok = np.isfinite(d[rows - r0, cols])
+        rows, cols = rows[ok], cols[ok]
+        lo, hi = np.minimum(rows, cols).astype(np.int64), np.maximum(rows, cols).astype(np.int64)
+        codes.append(lo * n + hi)
+        if n > k:
+            part = np.partition(d, (k - 1, k), axis=1)
+            n_ties += int(np.sum((part[:, k - 1] == part[:, k]) & np.isfinite(part[:, k - 1])))
+    codes = np.unique(np.concatenate(codes)) if codes else np.zeros(0, np.int64)
     return np.stack([codes // n, codes % n], 1), n_ties
 
 
@@ -191,7 +219,7 @@ def pair_features(pairs, st, shared, flag) -> np.ndarray:
     return np.stack([de, dxy, shared, gc, flag], axis=1).astype(F32)
 
 
-def compute_edges(seg, st, n, connectivity=4, n_nonlocal=4):
+def compute_edges(seg, st, n, connectivity=4, n_nonlocal=4, tie_break="argpartition"):
     """graph_builder.py:257-307 -- COO order [adj | nl | adj reversed | nl reversed]."""
     adj, cnt = adjacency_pairs(seg, n, connectivity)
     shared = cnt.astype(F32) / (np.float64(cnt.max()) + 1e-6)   # float64 division (:286)
@@ -199,7 +227,7 @@ def compute_edges(seg, st, n, connectivity=4, n_nonlocal=4):
     pairs, n_ties = adj, 0
     nl = np.zeros((0, 2), dtype=np.int64)
     if n_nonlocal > 0 and n > n_nonlocal + 1:
-        nl, n_ties = nonlocal_pairs(adj, st["mean_lab"], n, int(n_nonlocal))
+        nl, n_ties = nonlocal_pairs(adj, st["mean_lab"], n, int(n_nonlocal), tie_break)
         if len(nl):
             nl_attr = pair_features(nl, st, np.zeros(len(nl), F32), np.ones(len(nl), F32))
             pairs = np.concatenate([adj, nl], 0)
@@ -224,7 +252,7 @@ def _unit_norm(v: np.ndarray) -> np.ndarray:
 
 
 def auto_prior(seg: np.ndarray, lab: np.ndarray, centre_sigma: float = 0.45,
-               contrast_sigma: float = 0.40, return_stages: bool = False):
+               contrast_sigma: float = 0.40, return_stages: bool = False, block: int = 512):
     """graph_builder.py:357-444 -- [fg-ness, bg-ness, ambiguity] per region."""
     H, W = seg.shape
     n = int(seg.max()) + 1
@@ -238,13 +266,19 @@ def auto_prior(seg: np.ndarray, lab: np.ndarray, centre_sigma: float = 0.45,
     cx = np.bincount(flat, weights=(xx.ravel() / W), minlength=n) / safe
     cen = np.stack([cy, cx], axis=1).astype(F32)
 
-    dl = mean_lab[:, None, :] - mean_lab[None, :, :]
-    colour_d = np.sqrt((dl[..., 0] * dl[..., 0] + dl[..., 1] * dl[..., 1]) + dl[..., 2] * dl[..., 2])
-    dc = cen[:, None, :] - cen[None, :, :]
-    spatial_d = np.sqrt(dc[..., 0] * dc[..., 0] + dc[..., 1] * dc[..., 1])
-    spatial_w = np.exp(-(spatial_d ** 2) / F32(2 * contrast_sigma ** 2))
+    # the two N x N matrices of :406-411, evaluated in row blocks (rows are independent; numpy
+    # reduces each row of a C-contiguous float32 block with the same pairwise order whatever
+    # the number of rows, so the blocked sum is bit-identical to the reference's full matrix)
     area_w = counts / F32(max(counts.sum(), 1.0))
-    contrast = (colour_d * spatial_w * area_w[None, :]).sum(axis=1)
+    contrast = np.empty(n, dtype=F32)
+    for r0 in range(0, n, block):
+        r1 = min(n, r0 + block)
+        dl = mean_lab[r0:r1, None, :] - mean_lab[None, :, :]
+        colour_d = np.sqrt((dl[..., 0] * dl[..., 0] + dl[..., 1] * dl[..., 1]) + dl[..., 2] * dl[..., 2])
+        dc = cen[r0:r1, None, :] - cen[None, :, :]
+        spatial_d = np.sqrt(dc[..., 0] * dc[..., 0] + dc[..., 1] * dc[..., 1])
+        spatial_w = np.exp(-(spatial_d ** 2) / F32(2 * contrast_sigma ** 2))
+        contrast[r0:r1] = (colour_d * spatial_w * area_w[None, :]).sum(axis=1)
     contrast = _unit_norm(contrast)
 
     c0 = cen - F32(0.5)
@@ -278,14 +312,16 @@ def auto_prior(seg: np.ndarray, lab: np.ndarray, centre_sigma: float = 0.45,
 # --------------------------------------------------------------------------- driver
 
 def build_graph(bgr: np.ndarray, seg: np.ndarray, connectivity: int = 4,
-                n_nonlocal: int = 4, keep_stages: bool = True) -> RegionGraph:
-    """GraphBuilder(image, cfg).build() with the label map supplied (graph_builder.py:156-175)."""
+                n_nonlocal: int = 4, keep_stages: bool = True,
+                tie_break: str = "argpartition") -> RegionGraph:
+    """GraphBuilder(image, cfg).build() with the label map supplied (graph_builder.py:156-175).
+    ``tie_break``: see nonlocal_pairs."""
     seg = np.ascontiguousarray(seg, dtype=np.int32)
     n = int(seg.max()) + 1
     planes = pixel_planes(bgr)
     st = region_statistics(seg, planes, n)
     feats = node_features(st)
-    edge_index, edge_attr, est = compute_edges(seg, st, n, connectivity, n_nonlocal)
+    edge_index, edge_attr, est = compute_edges(seg, st, n, connectivity, n_nonlocal, tie_break)
     prior, pst = auto_prior(seg, planes["lab"], return_stages=True)
     stages: Dict[str, np.ndarray] = {}
     if keep_stages:

@@ -1,14 +1,15 @@
 """
-Import the UNMODIFIED reference files from /root/reference over the oracle shims.
+Import the UNMODIFIED reference files over the oracle shims.
 
-TEST INFRASTRUCTURE, authoring container only: /root/reference does not exist on the
-GPU box, so nothing in the ``-m gpu`` tests, smoke() or bench.py calls this.  It is
-used by tests/golden/make_golden.py (fixture generation) and by the optional
-``test_port_matches_reference_live`` CPU tests, which skip when the tree is absent.
+TEST INFRASTRUCTURE.  The files come from /root/reference (authoring container) or, where
+that tree does not exist (the GPU box), from ``oracle/_ref/`` -- the verbatim, git-ignored
+copy that ``oracle/make_ref.py`` writes and gpurun ships.  Used by tests/golden/make_golden*.py
+(fixture generation), by the drop-in test that runs the reference's own ``segment()`` over this
+repository's classes, and by the ``reference`` CPU arm of bench.py.
 
 The package ``gcn_grabcut/__init__.py`` imports every submodule (incl. matplotlib-based
 ones, absent here), so the package object is pre-seeded as an empty namespace and the
-needed submodules are imported directly; no reference file is modified or copied.
+needed submodules are imported directly; no reference file is modified.
 """
 from __future__ import annotations
 
@@ -17,8 +18,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("GG_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "shims")
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("GG_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "src", "gcn_grabcut", "graph_builder.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
