@@ -188,12 +188,22 @@ __global__ void k_coord_tables(double* __restrict__ tab, int H, int W) {
 // neighbours are replaced by the pixel's own label, so that "differs from a neighbour" needs no
 // bounds tests.  Labels are only range-checked where they are used as an index (run hand-over,
 // pair emission).
-constexpr int RS_WARPS = 8;
 constexpr int RS_SLOTS = 16;
 constexpr int RS_NF = 18;
 constexpr int RS_STAGE_LD = 19;  // doubles per lane in the staging area (odd: conflict-free)
-constexpr size_t RS_SMEM_BYTES =
-    (256 + 256 + RS_WARPS * RS_SLOTS * RS_NF + RS_WARPS * 32 * RS_STAGE_LD) * sizeof(double);
+// the direct hand-over needs the two look-up tables only; the table variant adds per-warp slots + staging
+constexpr size_t rs_smem_bytes(int warps, bool direct) {
+  return (size_t)(256 + 256 + (direct ? 0 : warps * RS_SLOTS * RS_NF + warps * 32 * RS_STAGE_LD)) * sizeof(double);
+}
+
+// x rounded to float32 precision (24 significant bits), computed in the FP64 pipe: Veltkamp's
+// split with 2^29 + 1.  Same value as (double)(float)x -- round to nearest; an exact tie (the 29
+// dropped bits are 1000...0: probability 2^-29 per value) may resolve differently from the
+// conversion instruction -- without the two quarter-rate F2F conversions on the XU pipe.
+GG_D double round_to_f32(double x) {
+  const double t = __dmul_rn(x, 536870913.0);
+  return __dadd_rn(t, -__dadd_rn(t, -x));
+}
 
 struct RegionStatsParams {
   const uint8_t* bgr;
@@ -240,7 +250,7 @@ __device__ __noinline__ void pair_emit(unsigned long long* keys, int* cnts, int 
 // DIRECT: finished runs go straight to the global accumulators (one RED.F64 per field and run)
 // instead of through the per-warp shared-memory table: ~14x more L2 atomics, ~80 fewer
 // instructions per row.
-template <int MINB, bool DIRECT>
+template <int RS_WARPS, int MINB, bool DIRECT, bool VELT>
 __global__ void __launch_bounds__(RS_WARPS * 32, MINB)
 k_region_stats(const RegionStatsParams p) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -250,13 +260,14 @@ k_region_stats(const RegionStatsParams p) {
   double* s_stage_all = s_vals_all + RS_WARPS * RS_SLOTS * RS_NF;           // [W][32*LD]
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* vals = s_vals_all + wid * RS_SLOTS * RS_NF;
-  double* stage = s_stage_all + wid * 32 * RS_STAGE_LD;
+  double* vals = s_vals_all + (DIRECT ? 0 : wid * RS_SLOTS * RS_NF);
+  double* stage = s_stage_all + (DIRECT ? 0 : wid * 32 * RS_STAGE_LD);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     s_lin[i] = p.lin_lut[i];
     s_vd[i] = (double)__fdiv_rn((float)i, 255.0f);          // HSV value channel: max/255
   }
-  for (int i = lane; i < RS_SLOTS * RS_NF; i += 32) vals[i] = 0.0;
+  if (!DIRECT)
+    for (int i = lane; i < RS_SLOTS * RS_NF; i += 32) vals[i] = 0.0;
   __syncthreads();
 
   const long long task = (long long)blockIdx.x * RS_WARPS + wid;
@@ -298,10 +309,20 @@ k_region_stats(const RegionStatsParams p) {
   // computed one iteration earlier, computes the values of row y+1 (independent instruction
   // chains, interleaved by the scheduler) and issues the loads two rows ahead:
   //   BGR(y+2), labels(y+2), grey(y+3) -- so no load is consumed in the iteration that issues it.
-  struct PixelVals { float L, A, Bv, hh, ss, g, gs; int mx; };
+  // VELT: the Lab values stay in float64 registers, rounded to float32 precision inside the FP64
+  // pipe (round_to_f32) instead of a D2F + F2D round trip through the quarter-rate XU pipe; their
+  // squares (float32 products in the reference) are formed and rounded the same way.
+  struct PixelVals { float L, A, Bv, hh, ss, g, gs; int mx; double Ld, Ad, Bd; };
   auto pixel_math = [&](int b_, int g_, int r_, int hs_a, int hd_a, int hd_b, int hs_c_, int hd_c_) {
     PixelVals v;
-    bgr_to_lab_fast(s_lin, p.lab.m, b_, g_, r_, v.L, v.A, v.Bv);
+    if (VELT) {
+      bgr_to_lab_fast_f64(s_lin, p.lab.m, b_, g_, r_, v.Ld, v.Ad, v.Bd);
+      v.Ld = round_to_f32(v.Ld); v.Ad = round_to_f32(v.Ad); v.Bd = round_to_f32(v.Bd);
+      v.L = v.A = v.Bv = 0.0f;
+    } else {
+      bgr_to_lab_fast(s_lin, p.lab.m, b_, g_, r_, v.L, v.A, v.Bv);
+      v.Ld = v.Ad = v.Bd = 0.0;
+    }
     const int mx = max(r_, max(g_, b_)), mn = min(r_, min(g_, b_));
     hsv_hs_fast(b_, g_, r_, mx, mn, v.hh, v.ss);
     v.mx = mx;
@@ -329,10 +350,10 @@ k_region_stats(const RegionStatsParams p) {
     return (uint32_t)(min(max(r, 0), H - 1) * W + xc);
   };
   auto load_grey = [&](int r, int& gc, int& ge) {
-    const uint32_t o = grey_row_off(r);
-    gc = gry[o];
+    const uint8_t* pgr = gry + grey_row_off(r);
+    gc = pgr[0];
     ge = 0;
-    if (edge_lane) ge = gry[o + gdelta];
+    if (edge_lane) ge = pgr[gdelta];
   };
   const uint32_t off0 = (uint32_t)(y_begin * W + xc);  // pixel offset of (y_begin, xc) in the image
   int hs_m, hd_m, hs_c, hd_c, g2c, g2e;
@@ -344,10 +365,11 @@ k_region_stats(const RegionStatsParams p) {
     load_grey(y_begin, gc, ge);     partials(gc, ge, hs_m, hd_m);
     load_grey(y_begin + 1, gc, ge); partials(gc, ge, hs_p0, hd_p0);
     load_grey(y_begin + 2, g2c, g2e);
-    cv = pixel_math(img[3 * off0], img[3 * off0 + 1], img[3 * off0 + 2], hs_a, hd_a, hd_m, hs_p0, hd_p0);
+    const uint8_t* px0 = img + (size_t)3 * off0;
+    cv = pixel_math(px0[0], px0[1], px0[2], hs_a, hd_a, hd_m, hs_p0, hd_p0);
     hs_c = hs_p0; hd_c = hd_p0;
-    const uint32_t o1 = (uint32_t)(min(y_begin + 1, H - 1) * W + xc);
-    pb = img[3 * o1]; pg = img[3 * o1 + 1]; pr = img[3 * o1 + 2];
+    const uint8_t* px1 = img + (size_t)3 * (size_t)(min(y_begin + 1, H - 1) * W + xc);
+    pb = px1[0]; pg = px1[1]; pr = px1[2];
   }
   int lab_c = valid ? lab[off0] : -1;
   int lab_up = (valid && y_begin > 0) ? lab[off0 - W] : lab_c;
@@ -473,12 +495,16 @@ k_region_stats(const RegionStatsParams p) {
     // ---- loads two rows ahead (row indices are warp-uniform)
     int g3c, g3e;
     load_grey(y + 3, g3c, g3e);
-    const uint32_t ob = (uint32_t)(min(y + 2, H - 1) * W + xc);
-    const int nb_ = img[3 * ob], ng_ = img[3 * ob + 1], nr_ = img[3 * ob + 2];
+    // one address per pixel / label (pointer + constant offsets: 32-bit index arithmetic such as
+    // 3 * ob + 1 may wrap and would cost an address computation per load)
+    const int ob = min(y + 2, H - 1) * W + xc;
+    const uint8_t* px2 = img + (size_t)3 * (size_t)ob;
+    const int nb_ = px2[0], ng_ = px2[1], nr_ = px2[2];
     int lab_dn2 = lab_dn, e_lab_n2 = 0;                 // below the image: the own label
     if (y + 2 < H) {
-      if (valid) lab_dn2 = lab[ob];
-      if (edge_lane) e_lab_n2 = lab[ob + ldelta];
+      const int32_t* pl2 = lab + ob;
+      if (valid) lab_dn2 = pl2[0];
+      if (edge_lane) e_lab_n2 = pl2[ldelta];
     }
     const bool has_dn = y + 1 < H;
 
@@ -501,9 +527,16 @@ k_region_stats(const RegionStatsParams p) {
     const PixelVals nv = pixel_math(pb, pg, pr, hs_m, hd_m, hd_c, hs_p, hd_p);
     // ---- ... while row y is accumulated (all lanes; lanes beyond the image feed a dead run)
     {
-      aL += (double)cv.L; aA += (double)cv.A; aB += (double)cv.Bv;
-      aL2 += (double)__fmul_rn(cv.L, cv.L); aA2 += (double)__fmul_rn(cv.A, cv.A);
-      aB2 += (double)__fmul_rn(cv.Bv, cv.Bv);
+      if (VELT) {
+        aL += cv.Ld; aA += cv.Ad; aB += cv.Bd;
+        // the float32 product of two float32 values = their exact float64 product, rounded once
+        aL2 += round_to_f32(__dmul_rn(cv.Ld, cv.Ld)); aA2 += round_to_f32(__dmul_rn(cv.Ad, cv.Ad));
+        aB2 += round_to_f32(__dmul_rn(cv.Bd, cv.Bd));
+      } else {
+        aL += (double)cv.L; aA += (double)cv.A; aB += (double)cv.Bv;
+        aL2 += (double)__fmul_rn(cv.L, cv.L); aA2 += (double)__fmul_rn(cv.A, cv.A);
+        aB2 += (double)__fmul_rn(cv.Bv, cv.Bv);
+      }
       aH += (double)cv.hh; aS += (double)cv.ss; aV += s_vd[cv.mx];
       aG += (double)cv.g; aGs += (double)cv.gs;
       cnt += 1;
@@ -1663,14 +1696,24 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     // ~14x more L2 atomics slow down a concurrent host-to-device copy: the streaming host path,
     // which is bound by that copy, asks for the table variant (ctx->rs_direct = 0).
     static const int forced = getenv("GG_RS_DIRECT") ? atoi(getenv("GG_RS_DIRECT")) : -1;
+    // launch shape of the direct variant: 0 = 8 warps x 2 blocks/SM (128 registers), 1 = 4 warps x 5
+    // blocks/SM (102 registers), 2 = 4 warps x 4 blocks/SM; +4 = keep the F2F conversions (no Veltkamp)
+    static const int variant = getenv("GG_RS_VARIANT") ? atoi(getenv("GG_RS_VARIANT")) : 1;
     const int direct = forced >= 0 ? forced : ctx->rs_direct;
-    if (direct) {
-      GG_SMEM_ATTR_ONCE(ctx, 0, (k_region_stats<2, true>), RS_SMEM_BYTES);
-      GG_LAUNCH(ctx, (k_region_stats<2, true>), ceil_div(tasks, RS_WARPS), RS_WARPS * 32, RS_SMEM_BYTES, st, p);
-    } else {
-      GG_SMEM_ATTR_ONCE(ctx, 30, (k_region_stats<2, false>), RS_SMEM_BYTES);
-      GG_LAUNCH(ctx, (k_region_stats<2, false>), ceil_div(tasks, RS_WARPS), RS_WARPS * 32, RS_SMEM_BYTES, st, p);
-    }
+#define GG_RS_LAUNCH(BIT, W_, MINB_, DIRECT_, VELT_)                                                              \
+    do {                                                                                                          \
+      GG_SMEM_ATTR_ONCE(ctx, BIT, (k_region_stats<W_, MINB_, DIRECT_, VELT_>), rs_smem_bytes(W_, DIRECT_));        \
+      GG_LAUNCH(ctx, (k_region_stats<W_, MINB_, DIRECT_, VELT_>), ceil_div(tasks, W_), W_ * 32,                    \
+                rs_smem_bytes(W_, DIRECT_), st, p);                                                               \
+    } while (0)
+    if (!direct) GG_RS_LAUNCH(30, 8, 2, false, true);
+    else if (variant == 0) GG_RS_LAUNCH(0, 8, 2, true, true);
+    else if (variant == 1) GG_RS_LAUNCH(42, 4, 5, true, true);
+    else if (variant == 2) GG_RS_LAUNCH(43, 4, 4, true, true);
+    else if (variant == 4) GG_RS_LAUNCH(44, 8, 2, true, false);
+    else if (variant == 5) GG_RS_LAUNCH(45, 4, 5, true, false);
+    else GG_RS_LAUNCH(46, 4, 4, true, false);
+#undef GG_RS_LAUNCH
   }
   {
     dim3 grid(ceil_div(nc, 256), B);

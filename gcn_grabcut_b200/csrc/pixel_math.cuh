@@ -164,9 +164,10 @@ __device__ __forceinline__ double cbrt_unit(double t) {
   return __dmul_rn(__dmul_rn(t, r), r);
 }
 
-// bgr_to_lab with one branch for "some channel above the linear segment" instead of three.
-__device__ __forceinline__ void bgr_to_lab_fast(const double* __restrict__ lin, const double* __restrict__ mat,
-                                                int b, int g, int r, float& L, float& A, float& B) {
+// bgr_to_lab with one branch for "some channel above the linear segment" instead of three;
+// float64 L, a, b before the final rounding to float32.
+__device__ __forceinline__ void bgr_to_lab_fast_f64(const double* __restrict__ lin, const double* __restrict__ mat,
+                                                    int b, int g, int r, double& L, double& A, double& B) {
   const double lr = lin[r], lg = lin[g], lb = lin[b];
   const double x = GG_DFMA(mat[2], lb, GG_DFMA(mat[1], lg, mat[0] * lr));
   const double y = GG_DFMA(mat[5], lb, GG_DFMA(mat[4], lg, mat[3] * lr));
@@ -179,9 +180,18 @@ __device__ __forceinline__ void bgr_to_lab_fast(const double* __restrict__ lin, 
     if (y > 0.008856) fy = cbrt_unit(y);
     if (z > 0.008856) fz = cbrt_unit(z);
   }
-  L = (float)(116.0 * fy - 16.0);
-  A = (float)(500.0 * (fx - fy));
-  B = (float)(200.0 * (fy - fz));
+  L = 116.0 * fy - 16.0;
+  A = 500.0 * (fx - fy);
+  B = 200.0 * (fy - fz);
+}
+
+__device__ __forceinline__ void bgr_to_lab_fast(const double* __restrict__ lin, const double* __restrict__ mat,
+                                                int b, int g, int r, float& L, float& A, float& B) {
+  double Ld, Ad, Bd;
+  bgr_to_lab_fast_f64(lin, mat, b, g, r, Ld, Ad, Bd);
+  L = (float)Ld;
+  A = (float)Ad;
+  B = (float)Bd;
 }
 
 // hue and saturation of bgr_to_hsv, branch-free (d == 0 gives 0 / 1 = 0 for both).

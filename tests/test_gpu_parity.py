@@ -768,7 +768,7 @@ def test_device_status_is_sticky_and_checked(gg):
     moved = net(gg.Data(x=x, edge_index=ei, edge_attr=ea).to("cuda")).cpu()
     assert torch.allclose(moved, good + 1.0, atol=1e-5)
     # (b) whole path on device pointers
-    imgs, labs = make_batch(20, 96, 128, 30, seed0=1)
+    imgs, labs = make_batch(20, 128, 160, 30, seed0=1)
     cap = int(labs.max()) + 1
     path = gg.TrimapPath(state, gg.SuperpixelGraphConfig(), node_cap=cap)
     it, lt = torch.from_numpy(imgs).cuda(), torch.from_numpy(labs).cuda()
