@@ -32,6 +32,7 @@ SOURCES = {
     "trimap.cu": ["-fmad=false"],
     "resgcn.cu": [],
     "gemm_tc.cu": [],
+    "gcn_fused.cu": [],
 }
 
 

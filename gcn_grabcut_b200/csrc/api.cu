@@ -165,7 +165,7 @@ static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_
   GG_TRY(build_graphs(ctx, ar, bgr, labels, B, H, W, cfg, pb.g, st, &gray));
   if (graph_done) GG_CUDA_OK(cudaEventRecord(graph_done, st));
   GG_TRY(resgcn_forward(ctx, ar, pb.g.x, pb.g.csr_rowptr, pb.g.csr_src, pb.g.csr_eid, pb.g.edge_attr,
-                        pb.g.node_off, B, SN, SE, nullptr, pb.probs, st));
+                        pb.g.node_off, B, SN, SE, nullptr, pb.probs, st, cfg.node_cap, 2 * cfg.pair_cap));
   if (pc.edge_aware) {
     GG_TRY(refine_trimap(ctx, ar, bgr, gray, labels, pb.probs, pb.g.node_off, B, H, W, pc.radius,
                          pc.eps, pc.thr_fg, pc.thr_bg, trimap, nullptr, nullptr, st));
@@ -283,6 +283,7 @@ int gg_create(gg_handle* out, int device) {
   for (auto& sst : c->s_sub) GG_CUDA_OK(cudaStreamCreateWithFlags(&sst, cudaStreamNonBlocking));
   if (const char* ns = getenv("GG_SUBBATCH")) c->n_sub = std::max(1, std::min(4, atoi(ns)));
   if (const char* sg = getenv("GG_STAGGER")) c->stagger = atoi(sg) != 0;
+  if (getenv("GG_GCN_UNFUSED")) c->gcn_fused = 0;
   c->ev.resize(24);
   for (auto& ev : c->ev) GG_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : c->ticket_ev) GG_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
@@ -319,6 +320,7 @@ int gg_set_option(gg_handle h, const char* key, int value) {
   GG_REQUIRE(h && key, "gg_set_option: null");
   if (!strcmp(key, "gemm_impl")) { h->gemm_impl = value; return GG_OK; }
   if (!strcmp(key, "n_sub")) { h->n_sub = std::max(1, std::min(4, value)); return GG_OK; }
+  if (!strcmp(key, "gcn_fused")) { h->gcn_fused = value != 0; return GG_OK; }
   set_error("gg_set_option: unknown key %s", key);
   return GG_ERR_INVALID;
 }
@@ -384,7 +386,10 @@ int gg_resgcn_forward(gg_handle h, const float* x_dev, const int32_t* csr_rowptr
   GG_TRY(h->arena.reserve(resgcn_workspace_bytes(h->net, node_cap_total, edge_cap_total, n_graphs)));
   return arena_checked(h->arena, resgcn_forward(h, h->arena, x_dev, csr_rowptr_dev, csr_src_dev, csr_eid_dev, edge_attr_dev,
                                                 graph_off_dev, n_graphs, node_cap_total, edge_cap_total, logits_dev,
-                                                probs_dev, (cudaStream_t)stream), "gg_resgcn_forward");
+                                                probs_dev, (cudaStream_t)stream,
+                                                n_graphs == 1 && node_cap_total <= FUSED_MAX_NODES ? (int)node_cap_total : 0,
+                                                n_graphs == 1 && edge_cap_total < (1 << 18) ? (int)edge_cap_total : 0),
+                       "gg_resgcn_forward");
 }
 
 int gg_refine_trimap(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, const float* probs_dev,

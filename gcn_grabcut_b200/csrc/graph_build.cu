@@ -1698,7 +1698,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     static const int forced = getenv("GG_RS_DIRECT") ? atoi(getenv("GG_RS_DIRECT")) : -1;
     // launch shape of the direct variant: 0 = 8 warps x 2 blocks/SM (128 registers), 1 = 4 warps x 5
     // blocks/SM (102 registers), 2 = 4 warps x 4 blocks/SM; +4 = keep the F2F conversions (no Veltkamp)
-    static const int variant = getenv("GG_RS_VARIANT") ? atoi(getenv("GG_RS_VARIANT")) : 1;
+    static const int variant = getenv("GG_RS_VARIANT") ? atoi(getenv("GG_RS_VARIANT")) : 6;
     const int direct = forced >= 0 ? forced : ctx->rs_direct;
 #define GG_RS_LAUNCH(BIT, W_, MINB_, DIRECT_, VELT_)                                                              \
     do {                                                                                                          \

@@ -857,7 +857,7 @@ size_t resgcn_workspace_bytes(const NetWeights& nw, long long node_cap, long lon
 int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* rowptr,
                    const int32_t* src, const int32_t* eid, const float* edge_attr,
                    const int64_t* graph_off, int n_graphs, long long node_cap, long long edge_cap,
-                   float* logits, float* probs, cudaStream_t st) {
+                   float* logits, float* probs, cudaStream_t st, int graph_node_cap, int graph_edge_cap) {
   NetWeights& nw = ctx->net;
   if (!nw.loaded) { set_error("resgcn_forward: no weights loaded (gg_load_weights)"); return GG_ERR_STATE; }
   GG_REQUIRE(n_graphs > 0 && node_cap > 0 && edge_cap >= 0, "resgcn_forward: bad sizes");
@@ -932,7 +932,11 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   GG_TRY(gemm(ctx, st, GEMM_GATE, ctxv, wb + nw.eg_w, wb + nw.eg_b, gate, n_nodes_p, node_cap, D, c, 2, 0));
 
   // ---- residual GCN blocks
-  for (int l = 0; l < n; ++l) {
+  const bool fused = graph_node_cap > 0 && n > 0 && gcn_fused_supported(ctx, graph_node_cap, graph_edge_cap);
+  if (fused)
+    GG_TRY(gcn_layers_fused(ctx, st, h, z, gate, row_stats, dinv, rowptr, src, graph_off, n_graphs, graph_node_cap,
+                            graph_edge_cap));
+  for (int l = 0; l < n && !fused; ++l) {
     if (use_tc && gemm_tc_supported(ctx, GEMM_GCN0 + l, D, D) && D == 128) {
       TcPrologue pro;                                   // LayerNorm fused into the A producer
       pro.mode = 1; pro.ln_g = wb + nw.norm_g[l]; pro.ln_b = wb + nw.norm_b[l];

@@ -17,10 +17,21 @@ enum : int { GEMM_ENC2 = 0, GEMM_GATE = 1, GEMM_SAGE_L = 2, GEMM_SAGE_R = 3, GEM
 
 int load_weights(gg_context* ctx, const gg_resgcn_weights* w);
 size_t resgcn_workspace_bytes(const NetWeights& nw, long long node_cap, long long edge_cap, int n_graphs);
+// graph_node_cap / graph_edge_cap: upper bounds of the nodes / directed edges of ONE graph when the
+// caller knows them (0 = unknown); they enable the per-graph fused kernels (gcn_fused.cu).
 int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* rowptr,
                    const int32_t* src, const int32_t* eid, const float* edge_attr,
                    const int64_t* graph_off, int n_graphs, long long node_cap, long long edge_cap,
-                   float* logits, float* probs, cudaStream_t st);
+                   float* logits, float* probs, cudaStream_t st, int graph_node_cap = 0,
+                   int graph_edge_cap = 0);
+
+// gcn_fused.cu: all residual GCN blocks in one kernel, one CTA per graph
+constexpr int FUSED_MAX_LAYERS = 16;
+constexpr int FUSED_MAX_NODES = 384;
+bool gcn_fused_supported(const gg_context* ctx, int node_cap, int edge_cap);
+int gcn_layers_fused(gg_context* ctx, cudaStream_t st, float* h, float* z, const float* gate,
+                     const float2* row_stats, const float* dinv, const int32_t* rowptr, const int32_t* src,
+                     const int64_t* graph_off, int n_graphs, int node_cap, int edge_cap);
 int coo_to_csr(gg_context* ctx, Arena& ar, const int64_t* ei, long long E, long long N,
                int32_t* rowptr, int32_t* src, int32_t* eid, cudaStream_t st);
 

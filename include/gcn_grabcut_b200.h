@@ -68,7 +68,10 @@ void gg_destroy(gg_handle h);
 /* Runtime options.  "gemm_impl": 1 = tcgen05 tensor-core transforms (default),
  * 0 = SIMT fp32 transforms (validation of the tensor-core path; same device, same API).
  * "n_sub": number of concurrent sub-batches (internal streams) the whole-path entry points
- * cut a batch into, 1..4 (default 2; env GG_SUBBATCH). */
+ * cut a batch into, 1..4 (default 2; env GG_SUBBATCH).
+ * "gcn_fused": 1 = run the residual GCN blocks as one per-graph kernel (x' on chip) where it
+ * applies (hidden 128, graphs of <= 384 regions, tcgen05 transforms; default), 0 = layer-wise
+ * kernels (validation of the fused kernel; env GG_GCN_UNFUSED). */
 int gg_set_option(gg_handle h, const char* key, int value);
 
 /* Device-side status word of the device-pointer entry points: bit0 label / edge index out of

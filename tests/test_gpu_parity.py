@@ -801,8 +801,8 @@ def test_reference_segment_through_the_drop_in(gg):
     import gcn_grabcut_b200.pipeline as ggp
     from gcn_grabcut_b200.synthetic import geometric_sample, slic_like_labels
     from oracle import model_port, trimap_port
+    ref = ref_loader.load()                                  # also puts the third-party shims on sys.path
     from skimage import segmentation as slic_shim            # the shim: returns the queued label map
-    ref = ref_loader.load()
     pm = ref.pipeline
     H, W, nseg, seed = 200, 264, 120, 21
     img = geometric_sample(H, W, seed)[0]
@@ -812,7 +812,9 @@ def test_reference_segment_through_the_drop_in(gg):
     m_ref = ref.model.ResGCNNet(hidden_channels=64, n_layers=3)
     m_ref.load_state_dict(state)
     m_ref.eval()
+    import cv2
     slic_shim.set_next_labels(seg)
+    cv2.setRNGSeed(7)                      # cv2.grabCut seeds its GMMs with cv::kmeans, which draws from OpenCV's global RNG
     res_ref = pm.GCNGrabCutPipeline(m_ref, ref.graph_builder.SuperpixelGraphConfig(n_segments=nseg),
                                     device="cpu").segment(img)
 
@@ -827,6 +829,7 @@ def test_reference_segment_through_the_drop_in(gg):
         m_gg.load_state_dict(state)
         m_gg.eval()
         slic_shim.set_next_labels(seg)
+        cv2.setRNGSeed(7)
         res_gg = pm.GCNGrabCutPipeline(m_gg, gg.SuperpixelGraphConfig(n_segments=nseg), device="cuda").segment(img)
     finally:
         for k, v in saved.items():
@@ -847,3 +850,63 @@ def test_reference_segment_through_the_drop_in(gg):
     assert bad == 0
     if np.array_equal(res_gg.trimap, res_ref.trimap):
         assert np.array_equal(res_gg.binary_mask, res_ref.binary_mask)
+
+
+def test_fused_gcn_blocks_vs_layerwise_and_oracle(gg):
+    """The per-graph fused residual-GCN kernel (gcn_fused.cu: LN -> tcgen05 transform -> x' kept in
+    TMEM / shared memory -> CSR gather -> bias, gate, GELU, residual, JK, all layers in one launch)
+    against the layer-wise kernels and the oracle: single graphs through forward(data) (N = 37, 128,
+    129, 300, 384: one to three 128-row tiles, ragged and exact), isolated nodes and self loops, and
+    the whole batched path (posteriors of every image)."""
+    from gcn_grabcut_b200 import _native as nat
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import model_port
+    h = nat.handle(0)
+    state = model_port.random_state_dict(128, 6, seed=12)
+    net = gg.ResGCNNet(hidden_channels=128, n_layers=6)
+    net.load_state_dict(state)
+    net = net.to("cuda").eval()
+    gen = torch.Generator().manual_seed(3)
+    for N in (37, 128, 129, 300, 384):
+        x = torch.randn(N, 19, generator=gen)
+        s = torch.randint(0, N, (5 * N,), generator=gen)
+        d = torch.randint(0, N, (5 * N,), generator=gen)
+        keep = (s != d) & (s != 3) & (d != 3)                   # node 3 stays isolated
+        pairs = torch.unique(torch.stack([torch.minimum(s, d)[keep], torch.maximum(s, d)[keep]]), dim=1)
+        ei = torch.cat([pairs, pairs.flip(0), torch.tensor([[5, 9], [5, 9]])], 1)   # two self loops
+        ea = torch.rand(ei.size(1), 5, generator=gen)
+        data = gg.Data(x=x, edge_index=ei, edge_attr=ea).to("cuda")
+        out = {}
+        for fused in (1, 0):
+            h.set_option("gcn_fused", fused)
+            try:
+                l0 = h.launches()
+                out[fused] = net(data).cpu()
+                out[fused, "launches"] = h.launches() - l0
+            finally:
+                h.set_option("gcn_fused", 1)
+        ref = model_port.resgcn_forward(state, x, ei, ea, None)
+        assert out[1, "launches"] < out[0, "launches"], "the fused kernel did not run"
+        print(f"N={N}: fused-layerwise {float((out[1] - out[0]).abs().max()):.3g}, fused-oracle "
+              f"{float((out[1] - ref).abs().max()):.3g}; launches {out[1, 'launches']} vs {out[0, 'launches']}")
+        assert torch.allclose(out[1], out[0], atol=5e-5, rtol=1e-5)
+        assert torch.allclose(out[1], ref, atol=POST_ATOL, rtol=1e-4)
+    # batched path: posteriors of every image
+    imgs, labs = make_batch(12, 160, 192, 60, seed0=33)
+    cap = int(labs.max()) + 1
+    path = gg.TrimapPath(state, gg.SuperpixelGraphConfig(n_segments=60), node_cap=cap)
+    it, lt = torch.from_numpy(imgs).cuda(), torch.from_numpy(labs).cuda()
+    res = {}
+    for fused in (1, 0):
+        h.set_option("gcn_fused", fused)
+        try:
+            probs = torch.zeros(12 * cap, 3, device="cuda")
+            noff = torch.zeros(13, dtype=torch.int64, device="cuda")
+            tri = path.run_device(it, lt, probs_t=probs, node_off_t=noff, check=True)
+            res[fused] = (tri.cpu().numpy(), probs.cpu().numpy(), noff.cpu().numpy())
+        finally:
+            h.set_option("gcn_fused", 1)
+    assert np.array_equal(res[1][2], res[0][2])
+    nt = int(res[1][2][-1])
+    assert np.abs(res[1][1][:nt] - res[0][1][:nt]).max() < 2e-5
+    assert np.mean(res[1][0] != res[0][0]) < 1e-4
