@@ -19,8 +19,8 @@ try:  # torch-dependent names (same guard as the reference's __init__)
         TRIMAP_BG, TRIMAP_FG, TRIMAP_PROB_BG, TRIMAP_PROB_FG, CLASS_BG, CLASS_UNK, CLASS_FG,
     )
     from .pipeline import (guided_filter, refine_trimap, seed_from_prior, TrimapPath, PendingTrimaps,  # noqa: F401
-                           shard_range)  # noqa: F401
-    from .dataset import derive_trimap_labels, prepare_sample, prepare_samples  # noqa: F401
+                           shard_range, grabcut_guards, clean_mask)  # noqa: F401
+    from .dataset import derive_trimap_labels, prepare_sample, prepare_samples, prepare_dataset, cache_key  # noqa: F401
     _MODELS_AVAILABLE = True
 except ImportError:  # pragma: no cover
     _MODELS_AVAILABLE = False

@@ -93,7 +93,7 @@ EXPORTED_SYMBOLS = (
     "gg_abi_version", "gg_last_error", "gg_create", "gg_destroy", "gg_set_option",
     "gg_check_device_status", "gg_build_graphs", "gg_pixel_planes", "gg_load_weights",
     "gg_coo_to_csr", "gg_resgcn_forward", "gg_refine_trimap", "gg_project_trimap",
-    "gg_guided_filter", "gg_region_labels", "gg_seed_from_prior", "gg_trimap_path_host", "gg_trimap_path_host_submit", "gg_trimap_path_host_wait",
+    "gg_guided_filter", "gg_region_labels", "gg_seed_from_prior", "gg_grabcut_guards", "gg_clean_masks", "gg_auto_prior", "gg_trimap_path_host", "gg_trimap_path_host_submit", "gg_trimap_path_host_wait",
     "gg_trimap_path_device", "gg_kernel_launch_count",
     "gg_profile_enable", "gg_profile_report", "gg_selftest_math")
 
@@ -141,6 +141,11 @@ def lib() -> C.CDLL:
                                            C.c_void_p]
             L.gg_seed_from_prior.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                              C.c_int, C.c_int, C.c_int64, C.c_double, C.c_void_p]
+            L.gg_auto_prior.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.gg_grabcut_guards.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+            L.gg_clean_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                         C.c_int, C.c_void_p]
             L.gg_trimap_path_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                               C.c_int, C.POINTER(PathConfig), C.c_void_p, C.c_void_p,
                                               C.c_void_p]

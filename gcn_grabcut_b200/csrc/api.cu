@@ -359,6 +359,17 @@ int gg_pixel_planes(gg_handle h, const uint8_t* bgr_dev, int B, int H, int W, fl
   return pixel_planes(h, h->arena, bgr_dev, B, H, W, lab_dev, hsv_dev, gray_dev, grad_dev, (cudaStream_t)stream);
 }
 
+int gg_auto_prior(gg_handle h, const int32_t* labels_dev, const float* lab_dev, int B, int H, int W, int node_cap,
+                  double centre_sigma, double contrast_sigma, float* prior_dev, int32_t* label_max_dev, void* stream) {
+  GG_REQUIRE(h && labels_dev && lab_dev && prior_dev, "gg_auto_prior: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_REQUIRE(B > 0 && H > 0 && W > 0 && node_cap > 0, "gg_auto_prior: bad sizes");
+  GG_TRY(h->arena.reserve(auto_prior_workspace_bytes(B, node_cap)));
+  return arena_checked(h->arena, auto_prior(h, h->arena, labels_dev, lab_dev, B, H, W, node_cap, centre_sigma,
+                                            contrast_sigma, prior_dev, label_max_dev, (cudaStream_t)stream),
+                       "gg_auto_prior");
+}
+
 int gg_load_weights(gg_handle h, const gg_resgcn_weights* w) {
   GG_REQUIRE(h && w, "gg_load_weights: null argument");
   GG_CUDA_OK(cudaSetDevice(h->device));
@@ -434,6 +445,25 @@ int gg_seed_from_prior(gg_handle h, uint8_t* trimap_dev, const int32_t* labels_d
   GG_TRY(h->arena.reserve(seed_workspace_bytes(B, node_cap_total)));
   return arena_checked(h->arena, seed_from_prior(h, h->arena, trimap_dev, labels_dev, x_dev, node_off_dev, B, H, W,
                                                  node_cap_total, seed_frac, (cudaStream_t)stream), "gg_seed_from_prior");
+}
+
+int gg_grabcut_guards(gg_handle h, uint8_t* trimap_dev, int B, int H, int W, int32_t* degenerate_dev, void* stream) {
+  GG_REQUIRE(h && trimap_dev, "gg_grabcut_guards: null argument");
+  GG_REQUIRE(B > 0 && H > 0 && W > 0, "gg_grabcut_guards: bad sizes");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_TRY(h->arena.reserve(Arena::padded((size_t)B, 4) + 512));
+  return arena_checked(h->arena, grabcut_guards(h, h->arena, trimap_dev, B, H, W, degenerate_dev, (cudaStream_t)stream),
+                       "gg_grabcut_guards");
+}
+
+int gg_clean_masks(gg_handle h, const uint8_t* mask_dev, uint8_t* out_dev, int B, int H, int W, double min_area_ratio,
+                   int keep_largest, void* stream) {
+  GG_REQUIRE(h && mask_dev && out_dev, "gg_clean_masks: null argument");
+  GG_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < (1ll << 31), "gg_clean_masks: bad sizes");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_TRY(h->arena.reserve(clean_workspace_bytes(B, H, W)));
+  return arena_checked(h->arena, clean_masks(h, h->arena, mask_dev, out_dev, B, H, W, min_area_ratio, keep_largest,
+                                             (cudaStream_t)stream), "gg_clean_masks");
 }
 
 int gg_guided_filter(gg_handle h, const float* guide_dev, const float* src_dev, int H, int W, int radius,

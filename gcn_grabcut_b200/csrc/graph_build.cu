@@ -1135,7 +1135,7 @@ k_node_features(const float* __restrict__ st_all, const int* __restrict__ label_
 // Global colour contrast (graph_builder.py:405-412): one warp per region.
 __global__ void __launch_bounds__(256)
 k_prior_contrast(const float* __restrict__ st_all, const int* __restrict__ label_max,
-                 float* __restrict__ contrast_all, int node_cap, float inv_unused) {
+                 float* __restrict__ contrast_all, int node_cap, float two_sig2 /* float32(2*contrast_sigma**2) */) {
   const int b = blockIdx.y;
   const int n = min(label_max[b] + 1, node_cap);
   const int lane = threadIdx.x & 31;
@@ -1151,7 +1151,6 @@ k_prior_contrast(const float* __restrict__ st_all, const int* __restrict__ label
   // area_w = counts / counts.sum() (graph_builder.py:409): every pixel carries a label, so
   // counts.sum() is H*W (exact in float32) and area_w is the area ratio k_finalize_regions stored
   const float* area = st + (size_t)ST_AREA * node_cap;
-  const float two_sig2 = (float)(2 * 0.40 * 0.40);   // 2*contrast_sigma**2 as float32
   const float li = mL[i], ai = mA[i], bi = mB[i], yi = pcy[i], xi = pcx[i];
   double s = 0.0;
   for (int j = lane; j < n; j += 32) {
@@ -1190,7 +1189,8 @@ GG_D float unit_norm_apply(float v, float mn, float mx) {
 __global__ void __launch_bounds__(256)
 k_prior_finish(const float* __restrict__ st_all, const int* __restrict__ label_max,
                const float* __restrict__ contrast_all, float* __restrict__ tmp_all,
-               const int64_t* __restrict__ node_off, float* __restrict__ x, int node_cap) {
+               const int64_t* __restrict__ node_off, float* __restrict__ x, int node_cap,
+               float two_c2 /* float32(2*centre_sigma**2) */, int out_stride, int out_col) {
   __shared__ float sred[32];
   __shared__ double sredd[32];
   const int b = blockIdx.x;
@@ -1200,8 +1200,7 @@ k_prior_finish(const float* __restrict__ st_all, const int* __restrict__ label_m
   const float* contrast = contrast_all + (size_t)b * node_cap;
   float* fgv = tmp_all + (size_t)b * 2 * node_cap;   // fg-ness then bg-ness scratch
   float* bgv = fgv + node_cap;
-  const int64_t no = node_off[b];
-  const float two_c2 = (float)(2 * 0.45 * 0.45);
+  const int64_t no = node_off ? node_off[b] : (int64_t)b * node_cap;     // dense rows when there are no offsets
 
   float cmn, cmx;
   block_minmax(n, [&](int i) { return contrast[i]; }, sred, cmn, cmx);
@@ -1268,7 +1267,7 @@ k_prior_finish(const float* __restrict__ st_all, const int* __restrict__ label_m
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float fg = unit_norm_apply(fgv[i], fmn, fmx);
     const float bg = unit_norm_apply(bgv[i], bmn, bmx);
-    float* f = x + (size_t)(no + i) * GG_N_NODE_FEATS + GG_N_IMAGE_FEATS;
+    float* f = x + (size_t)(no + i) * out_stride + out_col;
     f[0] = nan_to_num(fg);
     f[1] = nan_to_num(bg);
     f[2] = nan_to_num(__fsub_rn(1.0f, fabsf(__fsub_rn(fg, bg))));
@@ -1748,10 +1747,10 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
             out.centroids, out.areas, nc);
   {
     dim3 grid(ceil_div(nc, 8), B);
-    GG_LAUNCH(ctx, k_prior_contrast, grid, 256, 0, st, stats, label_max, contrast, nc, 0.0f);
+    GG_LAUNCH(ctx, k_prior_contrast, grid, 256, 0, st, stats, label_max, contrast, nc, (float)(2 * 0.40 * 0.40));
   }
   GG_LAUNCH(ctx, k_prior_finish, B, 256, 0, st, stats, label_max, contrast, tmp2, out.node_off,
-            out.x, nc);
+            out.x, nc, (float)(2 * 0.45 * 0.45), GG_N_NODE_FEATS, GG_N_IMAGE_FEATS);
   GG_LAUNCH(ctx, k_edge_attrs, B, 256, 0, st, stats, pairs, shared, n_adj, n_nl, max_shared,
             out.edge_off, out.edge_index, (int64_t)2 * B * pc, out.edge_attr, nc, pc);
   GG_LAUNCH(ctx, k_csr, B, 512, 0, st, pairs, n_adj, n_nl, label_max, out.node_off, out.edge_off,
@@ -1759,6 +1758,93 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
   if (out.shared_cnt)
     GG_CUDA_OK(cudaMemcpyAsync(out.shared_cnt, shared, (size_t)B * pc * sizeof(int),
                                cudaMemcpyDeviceToDevice, st));
+  return GG_OK;
+}
+
+// ============================================================================ standalone prior
+// compute_auto_prior(segments, lab, centre_sigma, contrast_sigma) (graph_builder.py:357-444) with a
+// caller-supplied float32 Lab plane: the region sums it needs (count, Lab, float64 centroids, frame
+// pixels) in the accumulator layout of k_region_stats, equal labels of a warp aggregated first.
+__global__ void __launch_bounds__(256)
+k_lab_plane_sums(const int32_t* __restrict__ labels, const float* __restrict__ lab, int H, int W, int node_cap,
+                 double* __restrict__ acc_all, int* __restrict__ label_max, int* __restrict__ status) {
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  const int lane = threadIdx.x & 31;
+  const int32_t* l = labels + (size_t)b * HW;
+  const float* p = lab + (size_t)b * HW * 3;
+  double* acc = acc_all + (size_t)b * node_cap * RS_NF;
+  int lmax = -1;
+  for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; i0 < HW; i0 += gridDim.x * blockDim.x) {
+    const int i = i0 + lane;
+    const bool in = i < HW;
+    const int v = in ? l[i] : -1;
+    const bool ok = in && v >= 0 && v < node_cap;
+    if (in && !ok) atomicOr(status, ST_LABEL_RANGE);
+    lmax = max(lmax, ok ? v : -1);
+    const unsigned act = __ballot_sync(0xffffffffu, ok);
+    if (!ok) continue;
+    const int y = i / W, x = i - y * W;
+    double f[8] = {(double)p[3 * (size_t)i], (double)p[3 * (size_t)i + 1], (double)p[3 * (size_t)i + 2],
+                   (double)y / (double)H, (double)x / (double)W, 1.0,
+                   (double)((y == 0) + (y == H - 1) + (x == 0) + (x == W - 1)), 0.0};
+    const unsigned grp = __match_any_sync(act, v);
+    const int leader = __ffs(grp) - 1;
+    // sum the group's values into its leader (sequential over the group's lanes: the groups are short)
+    double s[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) s[k] = 0.0;
+    for (unsigned m = grp; m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) s[k] += __shfl_sync(grp, f[k], src);
+    }
+    if (lane == leader) {
+      double* a = acc + (size_t)v * RS_NF;
+      atomicAdd(a + 0, s[0]); atomicAdd(a + 1, s[1]); atomicAdd(a + 2, s[2]);
+      atomicAdd(a + 13, s[3]); atomicAdd(a + 14, s[4]); atomicAdd(a + 15, s[5]);
+      if (s[6] != 0.0) atomicAdd(a + 17, s[6]);
+    }
+  }
+  lmax = warp_max_i(lmax);
+  if (lane == 0 && lmax >= 0) atomicMax(&label_max[b], lmax);
+}
+
+size_t auto_prior_workspace_bytes(int B, int node_cap) {
+  return Arena::padded((size_t)B * node_cap * RS_NF, 8) + Arena::padded((size_t)B * 4, 4) +
+         Arena::padded((size_t)B * ST_FIELDS * node_cap, 4) + Arena::padded((size_t)B * node_cap, 4) * 3 + 2048;
+}
+
+int auto_prior(gg_context* ctx, Arena& ar, const int32_t* labels, const float* lab, int B, int H, int W, int node_cap,
+               double centre_sigma, double contrast_sigma, float* prior, int32_t* n_nodes, cudaStream_t st) {
+  GG_REQUIRE(B > 0 && H >= 1 && W >= 1 && node_cap > 0, "auto_prior: bad sizes");
+  double* acc = ar.take<double>((size_t)B * node_cap * RS_NF);
+  int* label_max = ar.take<int>((size_t)B * 4);
+  float* stats = ar.take<float>((size_t)B * ST_FIELDS * node_cap);
+  float* contrast = ar.take<float>((size_t)B * node_cap);
+  float* tmp2 = ar.take<float>((size_t)B * node_cap * 2);
+  GG_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)B * node_cap * RS_NF * sizeof(double), st));
+  GG_CUDA_OK(cudaMemsetAsync(label_max, 0xFF, (size_t)B * 4 * sizeof(int), st));
+  GG_TRY(status_epoch(ctx, st));
+  {
+    dim3 grid(std::min(ceil_div((long long)H * W, 256), 296), B);
+    GG_LAUNCH(ctx, k_lab_plane_sums, grid, 256, 0, st, labels, lab, H, W, node_cap, acc, label_max, ctx->status_word);
+  }
+  {
+    dim3 grid(ceil_div(node_cap, 256), B);
+    GG_LAUNCH(ctx, k_finalize_regions, grid, 256, 0, st, acc, label_max, stats, B, H, W, node_cap);
+  }
+  {
+    dim3 grid(ceil_div(node_cap, 8), B);
+    GG_LAUNCH(ctx, k_prior_contrast, grid, 256, 0, st, stats, label_max, contrast, node_cap,
+              (float)(2 * contrast_sigma * contrast_sigma));
+  }
+  GG_LAUNCH(ctx, k_prior_finish, B, 256, 0, st, stats, label_max, contrast, tmp2, (const int64_t*)nullptr, prior,
+            node_cap, (float)(2 * centre_sigma * centre_sigma), 3, 0);
+  if (n_nodes) {
+    // n_nodes[b] = label_max[b] + 1 (label_max is strided by 1 here)
+    GG_CUDA_OK(cudaMemcpyAsync(n_nodes, label_max, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
   return GG_OK;
 }
 

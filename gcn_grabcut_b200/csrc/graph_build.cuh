@@ -31,6 +31,12 @@ int region_labels(gg_context* ctx, Arena& ar, const int32_t* labels, const uint8
                   const int64_t* node_off, int B, int H, int W, long long node_cap_total,
                   double fg_thr, double bg_thr, float* fg_ratio, long long* y, cudaStream_t st);
 
+// compute_auto_prior(segments, lab, ...) (graph_builder.py:357-444) from a caller-supplied float32 Lab
+// plane; prior [B*node_cap,3] (dense rows), n_nodes_minus_1 [B] optional (= max label per image)
+size_t auto_prior_workspace_bytes(int B, int node_cap);
+int auto_prior(gg_context* ctx, Arena& ar, const int32_t* labels, const float* lab, int B, int H, int W, int node_cap,
+               double centre_sigma, double contrast_sigma, float* prior, int32_t* n_nodes, cudaStream_t st);
+
 // float32 fast paths of pixel_math.cuh vs the IEEE intrinsics; mismatches[4] (see k_selftest_math)
 int selftest_math(gg_context* ctx, Arena& ar, long long* mismatches, cudaStream_t st);
 

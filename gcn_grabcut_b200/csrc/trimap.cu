@@ -515,6 +515,180 @@ k_seed_apply(const int32_t* __restrict__ labels, const int64_t* __restrict__ nod
   else if (sv & 1) trimap[o] = 3;               // FG_PROBABLE
 }
 
+// ----------------------------------------------------------------------------- GrabCut hand-off guards
+// GrabCut.run_with_trimap (grabcut.py:127-140): cv2.grabCut needs at least one definite foreground
+// and one definite background pixel.  An image without GC_FGD gets its GC_PR_FGD pixels promoted,
+// likewise GC_PR_BGD -> GC_BGD; an image that still lacks one side afterwards is degenerate (the
+// reference then returns the trimap's own labelling instead of calling cv2.grabCut).
+// present[b]: bit l set = label l occurs in image b.
+__global__ void __launch_bounds__(256)
+k_trimap_labels_present(const uint8_t* __restrict__ trimap, int HW, int* __restrict__ present) {
+  const int b = blockIdx.y;
+  const uint8_t* t = trimap + (size_t)b * HW;
+  int bits = 0;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16; i < HW; i += gridDim.x * blockDim.x * 16) {
+    if (i + 16 <= HW && (((uintptr_t)(t + i)) & 15) == 0) {
+      const uint4 v = *reinterpret_cast<const uint4*>(t + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bits |= 1 << ((w[k] >> (8 * j)) & 3);
+    } else {
+      for (int k = i; k < min(HW, i + 16); ++k) bits |= 1 << (t[k] & 3);
+    }
+  }
+  bits = __reduce_or_sync(0xffffffffu, bits);
+  if ((threadIdx.x & 31) == 0 && bits) atomicOr(&present[b], bits);
+}
+
+__global__ void __launch_bounds__(256)
+k_trimap_promote(uint8_t* __restrict__ trimap, int HW, const int* __restrict__ present,
+                 int32_t* __restrict__ degenerate) {
+  const int b = blockIdx.y;
+  const int pr = present[b];
+  const bool no_fgd = !(pr & 2), no_bgd = !(pr & 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && degenerate)
+    degenerate[b] = (!(pr & (2 | 8)) || !(pr & (1 | 4))) ? 1 : 0;     // a side is missing even after promotion
+  if (!no_fgd && !no_bgd) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  uint8_t* t = trimap + (size_t)b * HW;
+  const uint8_t v = t[i];
+  if (no_fgd && v == 3) t[i] = 1;
+  else if (no_bgd && v == 2) t[i] = 0;
+}
+
+int grabcut_guards(gg_context* ctx, Arena& ar, uint8_t* trimap, int B, int H, int W, int32_t* degenerate,
+                   cudaStream_t st) {
+  const int HW = H * W;
+  int* present = ar.take<int>((size_t)B);
+  GG_CUDA_OK(cudaMemsetAsync(present, 0, (size_t)B * sizeof(int), st));
+  dim3 g1(std::min(ceil_div(HW, 256 * 16), 64), B);
+  GG_LAUNCH(ctx, k_trimap_labels_present, g1, 256, 0, st, trimap, HW, present);
+  dim3 g2(ceil_div(HW, 256), B);
+  GG_LAUNCH(ctx, k_trimap_promote, g2, 256, 0, st, trimap, HW, present, degenerate);
+  return GG_OK;
+}
+
+// ----------------------------------------------------------------------------- mask clean-up
+// clean_mask (pipeline.py:189-227): 8-connected components of a binary mask, drop the components
+// smaller than min_area_ratio * H * W (keep the largest one if nothing survives), or keep only the
+// largest.  Label-equivalence union-find on the pixel grid: a component's root is its smallest
+// pixel index = its first pixel in raster order, so "the first of the largest components" is the
+// one cv2.connectedComponentsWithStats + argmax picks.
+GG_D int ccl_find(int* L, int i) {
+  int r = i;
+  while (true) {
+    const int pr = reinterpret_cast<volatile int*>(L)[r];
+    if (pr == r) break;
+    r = pr;
+  }
+  return r;
+}
+GG_D void ccl_union(int* L, int a, int b) {
+  while (true) {
+    a = ccl_find(L, a);
+    b = ccl_find(L, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }          // hook the larger root under the smaller
+    const int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_init(const uint8_t* __restrict__ mask, int HW, int* __restrict__ L, int* __restrict__ area) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const size_t o = (size_t)b * HW + i;
+  L[o] = mask[o] ? i : -1;
+  area[o] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_merge(const uint8_t* __restrict__ mask, int H, int W, int* __restrict__ L) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = H * W;
+  if (i >= HW) return;
+  const uint8_t* m = mask + (size_t)b * HW;
+  if (!m[i]) return;
+  int* Lb = L + (size_t)b * HW;
+  const int y = i / W, x = i - y * W;
+  if (x > 0 && m[i - 1]) ccl_union(Lb, i, i - 1);
+  if (y > 0) {
+    if (m[i - W]) ccl_union(Lb, i, i - W);
+    if (x > 0 && m[i - W - 1]) ccl_union(Lb, i, i - W - 1);
+    if (x + 1 < W && m[i - W + 1]) ccl_union(Lb, i, i - W + 1);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_flatten(int HW, int* __restrict__ L, int* __restrict__ area) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  int* Lb = L + (size_t)b * HW;
+  if (Lb[i] < 0) return;
+  const int r = ccl_find(Lb, i);
+  Lb[i] = r;
+  atomicAdd(&area[(size_t)b * HW + r], 1);
+}
+
+// best[b]: (area << 32) | (0xffffffff - root) of the largest component (smallest root among equals);
+// any_big[b]: some component reaches min_area
+__global__ void __launch_bounds__(256)
+k_ccl_select(int HW, const int* __restrict__ L, const int* __restrict__ area, double min_area,
+             unsigned long long* __restrict__ best, int* __restrict__ any_big) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const size_t o = (size_t)b * HW + i;
+  if (L[o] != i) return;                                     // roots only
+  const int a = area[o];
+  atomicMax(&best[b], ((unsigned long long)(unsigned)a << 32) | (unsigned long long)(0xffffffffu - (unsigned)i));
+  if ((double)a >= min_area) any_big[b] = 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_apply(int HW, const int* __restrict__ L, const int* __restrict__ area, double min_area, int keep_largest,
+            const unsigned long long* __restrict__ best, const int* __restrict__ any_big,
+            uint8_t* __restrict__ out) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const size_t o = (size_t)b * HW + i;
+  const int r = L[o];
+  uint8_t keep = 0;
+  if (r >= 0) {
+    const int largest = (int)(0xffffffffu - (unsigned)(best[b] & 0xffffffffull));
+    if (keep_largest || !any_big[b]) keep = r == largest;
+    else keep = (double)area[(size_t)b * HW + r] >= min_area;
+  }
+  out[o] = keep;
+}
+
+size_t clean_workspace_bytes(int B, int H, int W) {
+  return 2 * Arena::padded((size_t)B * H * W, 4) + Arena::padded((size_t)B, 8) + Arena::padded((size_t)B, 4) + 1024;
+}
+
+int clean_masks(gg_context* ctx, Arena& ar, const uint8_t* mask, uint8_t* out, int B, int H, int W,
+                double min_area_ratio, int keep_largest, cudaStream_t st) {
+  const int HW = H * W;
+  int* L = ar.take<int>((size_t)B * HW);
+  int* area = ar.take<int>((size_t)B * HW);
+  unsigned long long* best = ar.take<unsigned long long>((size_t)B);
+  int* any_big = ar.take<int>((size_t)B);
+  GG_CUDA_OK(cudaMemsetAsync(best, 0, (size_t)B * sizeof(unsigned long long), st));
+  GG_CUDA_OK(cudaMemsetAsync(any_big, 0, (size_t)B * sizeof(int), st));
+  const double min_area = min_area_ratio * (double)HW;       // min_area_ratio * mask.size (float64)
+  dim3 grid(ceil_div(HW, 256), B);
+  GG_LAUNCH(ctx, k_ccl_init, grid, 256, 0, st, mask, HW, L, area);
+  GG_LAUNCH(ctx, k_ccl_merge, grid, 256, 0, st, mask, H, W, L);
+  GG_LAUNCH(ctx, k_ccl_flatten, grid, 256, 0, st, HW, L, area);
+  GG_LAUNCH(ctx, k_ccl_select, grid, 256, 0, st, HW, L, area, min_area, best, any_big);
+  GG_LAUNCH(ctx, k_ccl_apply, grid, 256, 0, st, HW, L, area, min_area, keep_largest, best, any_big, out);
+  return GG_OK;
+}
+
 // ----------------------------------------------------------------------------- host side
 size_t trimap_workspace_bytes(int B, int H, int W, bool need_gray) {
   size_t s = Arena::padded((size_t)B * H * W * 4, 4);      // a/b planes

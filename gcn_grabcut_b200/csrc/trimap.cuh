@@ -25,4 +25,13 @@ int seed_from_prior(gg_context* ctx, Arena& ar, uint8_t* trimap, const int32_t* 
                     const int64_t* node_off, int B, int H, int W, long long node_cap_total,
                     double seed_frac, cudaStream_t st);
 
+// GrabCut.run_with_trimap guards (grabcut.py:127-140) in place; degenerate [B] optional.
+int grabcut_guards(gg_context* ctx, Arena& ar, uint8_t* trimap, int B, int H, int W, int32_t* degenerate,
+                   cudaStream_t st);
+
+// clean_mask (pipeline.py:189-227), batched: mask / out uint8 {0,1} [B,H,W] (may alias).
+size_t clean_workspace_bytes(int B, int H, int W);
+int clean_masks(gg_context* ctx, Arena& ar, const uint8_t* mask, uint8_t* out, int B, int H, int W,
+                double min_area_ratio, int keep_largest, cudaStream_t st);
+
 }  // namespace gg

@@ -6,12 +6,19 @@ Training-data path of the graph builder -- host-side mirror of the reference's
 The per-region pixel / foreground counts are exact integers, so ``fg_ratio`` and the labels
 are bit-identical to the reference's.  ``prepare_samples`` is the batched form ("ten thousand
 graphs built in minutes", reference README): one ``gg_build_graphs`` + one
-``gg_region_labels`` call for B images.  Dataset discovery, augmentation and the ``.pt`` cache
-(``dataset.py:60-170, 363-441``) are file IO and stay with the reference.
+``gg_region_labels`` call for B images.  ``prepare_dataset`` adds the reference's on-disk graph
+cache (``dataset.py:363-441``): the same sha1 key over the sample and the configuration, the same
+blob ``{"data": Data(x, edge_index, edge_attr, node_area, fg_ratio, y), "segments"}`` written
+atomically as ``<key>.pt`` -- with the cache misses of a call built in batches on the GPU instead
+of one image per worker process.  Dataset discovery and augmentation (``dataset.py:60-170``) are
+file IO and stay with the reference.
 """
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
+import os
+from pathlib import Path
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -97,4 +104,87 @@ def prepare_samples(images: np.ndarray, gt_masks: np.ndarray, segments: Optional
                     node_area=torch.tensor(g.node_areas, dtype=torch.float32),
                     fg_ratio=ratio[lo:hi].clone(), y=yb)
         out.append((data, data.y, g.segments))
+    return out
+
+
+# ----------------------------------------------------------------------------- graph cache
+def cache_key(sample: dict, sp_config: Optional[SuperpixelGraphConfig], fg_threshold: float,
+              bg_threshold: float) -> str:
+    """The reference's cache key (dataset.py:363-377), byte for byte: sha1 over the image and mask
+    bytes (or, for a lazily decoded sample, the repr of its paths / max_size / aug_seed) followed
+    by the repr of the configuration tuple; first 20 hex digits.  Entries written by either
+    implementation are found by the other."""
+    cfg = sp_config or SuperpixelGraphConfig()
+    digest = hashlib.sha1()
+    if "image" in sample:
+        for key in ("image", "gt_mask"):
+            digest.update(np.ascontiguousarray(sample[key]))
+    else:
+        digest.update(repr((sample["image_path"], sample["mask_path"], sample.get("max_size"),
+                            sample.get("aug_seed"))).encode())
+    digest.update(repr((cfg.n_segments, cfg.compactness, cfg.sigma, cfg.use_lab, cfg.connectivity,
+                        cfg.n_nonlocal, fg_threshold, bg_threshold)).encode())
+    return digest.hexdigest()[:20]
+
+
+_cache_key = cache_key      # the reference's (private) name
+
+
+def _write_blob(path: Path, data, segments) -> None:
+    """torch.save to a temporary name, then rename: an interrupted run cannot leave a truncated
+    entry behind (dataset.py:431-440)."""
+    import torch
+    path.parent.mkdir(parents=True, exist_ok=True)
+    tmp = path.with_suffix(f".{os.getpid()}.tmp")
+    try:
+        torch.save({"data": data, "segments": segments}, tmp)
+        os.replace(tmp, path)
+    except Exception:
+        tmp.unlink(missing_ok=True)
+
+
+def prepare_dataset(samples: List[dict], sp_config: Optional[SuperpixelGraphConfig] = None,
+                    fg_threshold: float = 0.70, bg_threshold: float = 0.70, cache_dir=None,
+                    keep_segments: bool = True, segments: Optional[List[np.ndarray]] = None,
+                    batch_size: int = 64, device=None) -> List[Optional[Tuple]]:
+    """
+    Cached, batched graph preparation -- the role of the reference's ``prepare_dataset`` /
+    ``_prepare_one`` (dataset.py:402-441) for in-memory samples (dicts with ``image`` and
+    ``gt_mask``).  Per sample: look the key up in ``cache_dir`` (a hit never touches the GPU; a
+    corrupt entry is rebuilt); the misses are grouped by image shape and built ``batch_size`` at a
+    time with ``prepare_samples``; every new graph is written as ``<key>.pt``.  Returns one
+    ``(data, labels, segments or None)`` per sample, in order.  ``segments`` optionally supplies the
+    label maps (SLIC is the input producer).
+    """
+    import torch
+    cfg = sp_config or SuperpixelGraphConfig()
+    out: List[Optional[Tuple]] = [None] * len(samples)
+    paths: List[Optional[Path]] = [None] * len(samples)
+    misses = []
+    for i, smp in enumerate(samples):
+        if cache_dir is not None:
+            paths[i] = Path(cache_dir) / f"{cache_key(smp, cfg, fg_threshold, bg_threshold)}.pt"
+            if paths[i].exists():
+                try:
+                    blob = torch.load(paths[i], map_location="cpu", weights_only=False)
+                    data = blob["data"]
+                    out[i] = (data, data.y, blob["segments"] if keep_segments else None)
+                    continue
+                except Exception:
+                    pass                      # corrupt or stale entry: rebuild it
+        misses.append(i)
+    by_shape = {}
+    for i in misses:
+        by_shape.setdefault(tuple(samples[i]["image"].shape[:2]), []).append(i)
+    for idxs in by_shape.values():
+        for k in range(0, len(idxs), batch_size):
+            chunk = idxs[k:k + batch_size]
+            imgs = np.stack([samples[i]["image"] for i in chunk])
+            msks = np.stack([np.asarray(samples[i]["gt_mask"]) for i in chunk])
+            segs = None if segments is None else np.stack([segments[i] for i in chunk])
+            for i, (data, y, seg) in zip(chunk, prepare_samples(imgs, msks, segs, cfg, fg_threshold, bg_threshold,
+                                                                 device=device)):
+                if paths[i] is not None:
+                    _write_blob(paths[i], data, seg)
+                out[i] = (data, y, seg if keep_segments else None)
     return out

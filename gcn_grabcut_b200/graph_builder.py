@@ -224,21 +224,38 @@ def compute_auto_prior(segments: np.ndarray, lab: Optional[np.ndarray] = None,
                        centre_sigma: float = 0.45, contrast_sigma: float = 0.40, *,
                        image: Optional[np.ndarray] = None, device=None) -> np.ndarray:
     """
-    Per-superpixel [fg-ness, bg-ness, ambiguity] prior (reference: graph_builder.py:357-444).
-
-    The CUDA path derives CIELAB from the BGR image itself, so pass ``image=`` (BGR uint8);
-    a pre-computed ``lab`` plane alone cannot be consumed.  Only the reference's default
-    sigmas (0.45, 0.40 -- the only values its callers use, :163) are compiled in.
+    Per-superpixel [fg-ness, bg-ness, ambiguity] prior (reference: graph_builder.py:357-444), on
+    the GPU.  Same call as the reference: ``compute_auto_prior(segments, lab)`` with the float32
+    CIELAB image (H,W,3) -- its region sums are taken on the device (``gg_auto_prior``).
+    Alternatively pass ``image=`` (BGR uint8) and no ``lab``: Lab is then derived from the image
+    by the graph builder's own pixel kernel (default sigmas only).
     """
-    if image is None:
-        raise NotImplementedError("compute_auto_prior on the CUDA path needs image=<BGR uint8>; "
-                                  "a Lab plane alone is not supported")
-    if abs(centre_sigma - 0.45) > 1e-12 or abs(contrast_sigma - 0.40) > 1e-12:
-        raise NotImplementedError("only centre_sigma=0.45, contrast_sigma=0.40 are supported")
+    import torch
     seg = np.ascontiguousarray(segments, dtype=np.int32)
-    cfg = SuperpixelGraphConfig(n_nonlocal=0)
-    g = build_graph_batch(image[None], seg[None], cfg, device=device).to_graphs(seg[None])[0]
-    return g.prior_features
+    if lab is None:
+        if image is None:
+            raise ValueError("compute_auto_prior needs the Lab plane (or image=<BGR uint8>)")
+        if abs(centre_sigma - 0.45) > 1e-12 or abs(contrast_sigma - 0.40) > 1e-12:
+            raise NotImplementedError("with image= only centre_sigma=0.45, contrast_sigma=0.40 are supported")
+        cfg = SuperpixelGraphConfig(n_nonlocal=0)
+        g = build_graph_batch(image[None], seg[None], cfg, device=device).to_graphs(seg[None])[0]
+        return g.prior_features
+    lab = np.ascontiguousarray(lab, dtype=np.float32)
+    if lab.shape != seg.shape + (3,):
+        raise ValueError(f"lab shape {lab.shape} != segments shape {seg.shape} + (3,)")
+    dev = nat.device_index(device if device is not None else "cuda")
+    h = nat.handle(dev)
+    tdev = torch.device("cuda", dev)
+    n = int(seg.max()) + 1
+    H, W = seg.shape
+    seg_t, lab_t = torch.from_numpy(seg).to(tdev), torch.from_numpy(lab).to(tdev)
+    prior = torch.empty(n, 3, dtype=torch.float32, device=tdev)
+    stream = nat.current_stream(dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().gg_auto_prior(h.ptr, nat.ptr(seg_t), nat.ptr(lab_t), 1, H, W, n, float(centre_sigma),
+                                          float(contrast_sigma), nat.ptr(prior), C.c_void_p(0), C.c_void_p(stream)))
+        h.check_status(stream)
+    return prior.cpu().numpy()
 
 
 def encode_user_hints(segments: np.ndarray, fg_points, bg_points) -> np.ndarray:

@@ -105,6 +105,60 @@ def seed_from_prior(trimap: np.ndarray, graph, seed_frac: float = 0.1, device=No
 _seed_from_prior = seed_from_prior      # the reference's (private) name
 
 
+def grabcut_guards(trimaps, device=None):
+    """
+    The guards ``GrabCut.run_with_trimap`` applies before ``cv2.grabCut`` (reference
+    grabcut.py:127-140), for one (H,W) trimap or a (B,H,W) batch: without a definite-foreground
+    pixel the probable-foreground pixels are promoted to definite, likewise for the background.
+    Returns ``(trimaps, degenerate)``: ``degenerate[b]`` is True where a side is still missing --
+    the reference then returns the trimap's own labelling instead of calling ``cv2.grabCut``.
+    """
+    import torch
+    t = np.ascontiguousarray(trimaps, dtype=np.uint8)
+    single = t.ndim == 2
+    if single:
+        t = t[None]
+    dev = nat.device_index(device if device is not None else "cuda")
+    h = nat.handle(dev)
+    tdev = torch.device("cuda", dev)
+    tt = torch.from_numpy(t).to(tdev)
+    deg = torch.zeros(t.shape[0], dtype=torch.int32, device=tdev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().gg_grabcut_guards(h.ptr, nat.ptr(tt), int(t.shape[0]), int(t.shape[1]), int(t.shape[2]),
+                                              nat.ptr(deg), C.c_void_p(nat.current_stream(dev))))
+    out, d = tt.cpu().numpy(), deg.cpu().numpy().astype(bool)
+    return (out[0], bool(d[0])) if single else (out, d)
+
+
+def clean_mask(mask: np.ndarray, min_area_ratio: float = 0.002, keep_largest: bool = False,
+               device=None) -> np.ndarray:
+    """
+    Remove spurious connected components from an automatic mask (reference pipeline.py:189-227):
+    mask (H,W) uint8 {0,1}; components (8-connectivity) smaller than ``min_area_ratio`` of the
+    image are dropped -- the largest one is kept if none survives -- or only the largest is kept.
+    A (B,H,W) batch is cleaned image by image in one call (``gg_clean_masks``).
+    """
+    import torch
+    m = np.asarray(mask)
+    if min_area_ratio <= 0 and not keep_largest:               # reference early return
+        return mask
+    single = m.ndim == 2
+    mb = np.ascontiguousarray(m[None] if single else m).astype(np.uint8)
+    if single and mb.sum() == 0:
+        return mask
+    dev = nat.device_index(device if device is not None else "cuda")
+    h = nat.handle(dev)
+    tdev = torch.device("cuda", dev)
+    mt = torch.from_numpy(mb).to(tdev)
+    out = torch.empty_like(mt)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().gg_clean_masks(h.ptr, nat.ptr(mt), nat.ptr(out), int(mb.shape[0]), int(mb.shape[1]),
+                                           int(mb.shape[2]), float(min_area_ratio), int(bool(keep_largest)),
+                                           C.c_void_p(nat.current_stream(dev))))
+    res = out.cpu().numpy()
+    return res[0] if single else res
+
+
 class TrimapPath:
     """
     The whole per-image trimap path, batched:  BGR images + label maps -> OpenCV trimaps.

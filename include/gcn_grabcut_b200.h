@@ -140,6 +140,14 @@ int gg_build_graphs(gg_handle h, const uint8_t* bgr_dev /*[B,H,W,3]*/,
 int gg_pixel_planes(gg_handle h, const uint8_t* bgr_dev, int B, int H, int W, float* lab_dev,
                     float* hsv_dev, float* gray_dev, float* grad_dev, void* stream);
 
+/* compute_auto_prior(segments, lab, centre_sigma, contrast_sigma) (graph_builder.py:357-444) with a
+ * caller-supplied float32 CIELAB plane lab_dev [B,H,W,3] (the builder itself derives Lab from BGR):
+ * prior_dev [B*node_cap,3] = [fg-ness, bg-ness, ambiguity], image b's region i at row
+ * b*node_cap + i; label_max_dev [B] (optional) receives max label per image (n_nodes - 1). */
+int gg_auto_prior(gg_handle h, const int32_t* labels_dev, const float* lab_dev, int B, int H, int W,
+                  int node_cap, double centre_sigma, double contrast_sigma, float* prior_dev,
+                  int32_t* label_max_dev, void* stream);
+
 /* ------------------------------------------------------------------ trimap network
  * Replaces ResGCNNet.load_state_dict / forward / predict_probs in eval mode
  * (model.py:449-546) including the PyG GCNConv / SAGEConv layers it calls.
@@ -235,6 +243,22 @@ int gg_region_labels(gg_handle h, const int32_t* labels_dev, const uint8_t* gt_m
 int gg_seed_from_prior(gg_handle h, uint8_t* trimap_dev, const int32_t* labels_dev, const float* x_dev,
                        const int64_t* node_off_dev, int B, int H, int W, int64_t node_cap_total,
                        double seed_frac, void* stream);
+
+/* The guards of GrabCut.run_with_trimap (grabcut.py:127-140), batched and in place: an image without
+ * a GC_FGD (1) pixel gets its GC_PR_FGD (3) pixels promoted to GC_FGD, likewise GC_PR_BGD (2) ->
+ * GC_BGD (0).  degenerate_dev [B] (optional): 1 where a side is still missing afterwards -- the
+ * reference then skips cv2.grabCut and returns the trimap's own labelling. */
+int gg_grabcut_guards(gg_handle h, uint8_t* trimap_dev, int B, int H, int W, int32_t* degenerate_dev,
+                      void* stream);
+
+/* clean_mask(mask, min_area_ratio, keep_largest) (pipeline.py:189-227), batched: 8-connected
+ * components of the binary masks uint8 {0,1} [B,H,W]; components smaller than
+ * min_area_ratio * H * W are dropped (if none survives the largest one is kept), or only the
+ * largest one is kept; among equally large components the first in raster order wins, as
+ * cv2.connectedComponentsWithStats + argmax does.  out_dev may alias mask_dev.  The caller applies
+ * the reference's early returns (empty mask; min_area_ratio <= 0 and not keep_largest). */
+int gg_clean_masks(gg_handle h, const uint8_t* mask_dev, uint8_t* out_dev, int B, int H, int W,
+                   double min_area_ratio, int keep_largest, void* stream);
 
 /* guided_filter(guide, src, radius, eps) on single float32 planes (pipeline.py:71-100). */
 int gg_guided_filter(gg_handle h, const float* guide_dev, const float* src_dev, int H, int W,

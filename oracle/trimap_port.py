@@ -86,3 +86,35 @@ def seed_from_prior(trimap: np.ndarray, prior: np.ndarray, seg: np.ndarray, n_no
         ids = np.argsort(prior[:, 1], kind="stable")[::-1][:n_seed]
         trimap[np.isin(seg, ids)] = 2
     return trimap
+
+
+def grabcut_guards(trimap: np.ndarray):
+    """grabcut.py:127-140 -- promotion of probable to definite labels when a definite side is
+    missing, and the single-class short-circuit.  Returns (trimap, degenerate)."""
+    trimap = trimap.astype(np.uint8)
+    if not (trimap == cv2.GC_FGD).any():
+        trimap = trimap.copy()
+        trimap[trimap == cv2.GC_PR_FGD] = cv2.GC_FGD
+    if not (trimap == cv2.GC_BGD).any():
+        trimap = trimap.copy()
+        trimap[trimap == cv2.GC_PR_BGD] = cv2.GC_BGD
+    degenerate = (not (trimap == cv2.GC_FGD).any()) or (not (trimap == cv2.GC_BGD).any())
+    return trimap, bool(degenerate)
+
+
+def clean_mask(mask: np.ndarray, min_area_ratio: float = 0.002, keep_largest: bool = False) -> np.ndarray:
+    """pipeline.py:189-227 -- connected-component clean-up of a {0,1} mask (8-connectivity)."""
+    if mask.sum() == 0 or (min_area_ratio <= 0 and not keep_largest):
+        return mask
+    n_labels, labels, stats, _ = cv2.connectedComponentsWithStats(mask.astype(np.uint8), connectivity=8)
+    if n_labels <= 1:
+        return mask
+    areas = stats[1:, cv2.CC_STAT_AREA]
+    min_area = min_area_ratio * mask.size
+    if keep_largest:
+        keep = np.array([int(areas.argmax()) + 1])
+    else:
+        keep = np.flatnonzero(areas >= min_area) + 1
+        if keep.size == 0:
+            keep = np.array([int(areas.argmax()) + 1])
+    return np.isin(labels, keep).astype(np.uint8)

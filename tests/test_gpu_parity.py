@@ -910,3 +910,91 @@ def test_fused_gcn_blocks_vs_layerwise_and_oracle(gg):
     nt = int(res[1][2][-1])
     assert np.abs(res[1][1][:nt] - res[0][1][:nt]).max() < 2e-5
     assert np.mean(res[1][0] != res[0][0]) < 1e-4
+
+
+def test_clean_mask_and_grabcut_guards_vs_reference_golden(gg):
+    """gg_clean_masks / gg_grabcut_guards against the reference's own clean_mask and
+    GrabCut.run_with_trimap guards (tests/golden/handoff/clean_and_guards.npz): bit-exact, single
+    images and a batch; plus random masks against the oracle (cv2.connectedComponentsWithStats)."""
+    import os
+    from oracle import trimap_port
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "handoff", "clean_and_guards.npz"))
+    n = 0
+    for key in z.files:
+        parts = key.split("/")
+        if parts[0] == "mask" and parts[2] != "in":
+            ratio, largest = parts[2].split("_")
+            got = gg.clean_mask(z[f"mask/{parts[1]}/in"].copy(), float(ratio), bool(int(largest)))
+            assert got.dtype == np.uint8 and np.array_equal(got, z[key]), key
+            n += 1
+        if parts[0] == "tri" and parts[2] == "out":
+            got, deg = gg.grabcut_guards(z[f"tri/{parts[1]}/in"])
+            assert np.array_equal(got, z[key]) and deg == bool(z[f"tri/{parts[1]}/degenerate"]), key
+            n += 1
+    assert n >= 40
+    rng = np.random.RandomState(5)
+    batch = (rng.rand(6, 200, 264) < np.array([0.02, 0.2, 0.45, 0.55, 0.7, 0.0])[:, None, None]).astype(np.uint8)
+    for ratio, largest in ((0.002, False), (0.0005, False), (0.3, False), (0.002, True)):
+        got = gg.clean_mask(batch, ratio, largest)
+        for b in range(6):
+            want = trimap_port.clean_mask(batch[b].copy(), ratio, largest)
+            assert np.array_equal(got[b], want), (b, ratio, largest)
+    tri = rng.randint(0, 4, (5, 64, 80)).astype(np.uint8)
+    tri[1][tri[1] == 1] = 3
+    tri[2][tri[2] == 0] = 2
+    tri[3][:] = 2
+    tri[4][np.isin(tri[4], (1, 3))] = 0
+    got, deg = gg.grabcut_guards(tri)
+    for b in range(5):
+        want, wd = trimap_port.grabcut_guards(tri[b])
+        assert np.array_equal(got[b], want) and bool(deg[b]) == wd, b
+
+
+def test_prepare_dataset_cache_roundtrip(gg, tmp_path):
+    """prepare_dataset: misses are built in batches and written as <key>.pt blobs
+    {"data", "segments"}; a second call is served from the cache without any kernel launch; a
+    corrupt entry is rebuilt."""
+    from gcn_grabcut_b200 import _native as nat
+    from gcn_grabcut_b200.synthetic import geometric_sample, slic_like_labels
+    samples, segs = [], []
+    for i, (H, W) in enumerate(((128, 160), (128, 160), (144, 176), (128, 160), (144, 176))):
+        img, mask = geometric_sample(H, W, 50 + i)
+        samples.append({"image": img, "gt_mask": mask})
+        segs.append(slic_like_labels(H, W, 40, 50 + i))
+    cfg = gg.SuperpixelGraphConfig(n_segments=40)
+    first = gg.prepare_dataset(samples, cfg, 0.7, 0.7, cache_dir=tmp_path, segments=segs, batch_size=2)
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert files == sorted(gg.cache_key(s, cfg, 0.7, 0.7) + ".pt" for s in samples)
+    h = nat.handle(0)
+    l0 = h.launches()
+    second = gg.prepare_dataset(samples, cfg, 0.7, 0.7, cache_dir=tmp_path, segments=segs)
+    assert h.launches() == l0, "a cache hit must not touch the GPU"
+    for (d1, y1, s1), (d2, y2, s2), seg in zip(first, second, segs):
+        assert torch.equal(d1.x, d2.x) and torch.equal(d1.edge_index, d2.edge_index) and torch.equal(y1, y2)
+        assert torch.equal(d1.fg_ratio, d2.fg_ratio) and np.array_equal(s1, seg) and np.array_equal(s2, seg)
+    blob = torch.load(tmp_path / files[0], map_location="cpu", weights_only=False)
+    assert set(blob) == {"data", "segments"}
+    (tmp_path / files[0]).write_bytes(b"truncated")
+    third = gg.prepare_dataset(samples, cfg, 0.7, 0.7, cache_dir=tmp_path, segments=segs, keep_segments=False)
+    assert h.launches() > l0 and all(t[2] is None for t in third)
+    for (d1, _, _), (d3, _, _) in zip(first, third):
+        assert torch.equal(d1.x, d3.x)
+
+
+def test_compute_auto_prior_reference_signature(gg):
+    """compute_auto_prior(segments, lab, centre_sigma, contrast_sigma) with a caller-supplied float32
+    Lab plane -- the reference's own call shape (graph_builder.py:357-362) -- against the oracle,
+    default and non-default sigmas; and the image= form against the builder's prior."""
+    from gcn_grabcut_b200.synthetic import geometric_sample, slic_like_labels
+    from oracle import graph_port
+    for (H, W, nseg, seed) in ((160, 192, 48, 3), (97, 131, 20, 8), (320, 480, 300, 1)):
+        img = geometric_sample(max(H, 128), max(W, 128), seed)[0][:H, :W]
+        seg = slic_like_labels(H, W, nseg, seed)
+        lab = graph_port.pixel_planes(np.ascontiguousarray(img))["lab"]
+        for cs, ks in ((0.45, 0.40), (0.30, 0.25), (0.8, 1.1)):
+            want = graph_port.auto_prior(seg, lab, cs, ks)
+            got = gg.compute_auto_prior(seg, lab, cs, ks)
+            assert got.dtype == np.float32 and got.shape == want.shape
+            np.testing.assert_allclose(got, want, rtol=FEAT_RTOL, atol=FEAT_ATOL)
+        via_image = gg.compute_auto_prior(seg, image=np.ascontiguousarray(img))
+        np.testing.assert_allclose(via_image, graph_port.auto_prior(seg, lab), rtol=FEAT_RTOL, atol=FEAT_ATOL)

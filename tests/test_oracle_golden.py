@@ -173,3 +173,43 @@ def test_region_labels_port_matches_reference():
         labels, ratio = graph_port.derive_trimap_labels(seg, mask, 0.70, 0.70)
         assert np.array_equal(labels, z[f"{name}/y"]) and np.array_equal(ratio, z[f"{name}/fg_ratio"])
         assert set(np.unique(labels)) <= {0, 1, 2} and len(np.unique(labels)) >= 2
+
+
+def test_handoff_port_vs_reference_golden():
+    """clean_mask / GrabCut guards: the oracle restatement against the reference's own outputs
+    (tests/golden/handoff/clean_and_guards.npz, written by make_golden_handoff2.py)."""
+    import os
+    from oracle import trimap_port
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "handoff", "clean_and_guards.npz"))
+    n = 0
+    for key in z.files:
+        parts = key.split("/")
+        if parts[0] == "mask" and parts[2] != "in":
+            ratio, largest = parts[2].split("_")
+            got = trimap_port.clean_mask(z[f"mask/{parts[1]}/in"].copy(), float(ratio), bool(int(largest)))
+            assert np.array_equal(got, z[key]), key
+            n += 1
+        if parts[0] == "tri" and parts[2] == "out":
+            got, deg = trimap_port.grabcut_guards(z[f"tri/{parts[1]}/in"])
+            assert np.array_equal(got, z[key]) and deg == bool(z[f"tri/{parts[1]}/degenerate"]), key
+            n += 1
+    assert n >= 40
+
+
+def test_cache_key_known_answers():
+    """The graph-cache key (reference dataset.py:363-377): values produced by the reference's own
+    `_cache_key` for seeded samples (checked live against the reference when it is available)."""
+    from gcn_grabcut_b200.dataset import cache_key
+    from gcn_grabcut_b200.graph_builder import SuperpixelGraphConfig
+    rng = np.random.RandomState(0)
+    smp = {"image": rng.randint(0, 255, (40, 50, 3)).astype(np.uint8), "gt_mask": (rng.rand(40, 50) > 0.5).astype(np.uint8)}
+    assert cache_key(smp, SuperpixelGraphConfig(), 0.7, 0.65) == "e4b39acfa81334ab16aa"
+    assert cache_key(smp, SuperpixelGraphConfig(n_segments=77, n_nonlocal=0, connectivity=8), 0.7, 0.65) == "ae6ed2459bf60c50ce3d"
+    lazy = {"image_path": "a/b.png", "mask_path": "a/b_m.png", "max_size": 512, "aug_seed": 3}
+    from oracle import ref_loader
+    if ref_loader.available():
+        import importlib
+        ref_loader.load()
+        rd = importlib.import_module("gcn_grabcut.dataset")
+        assert rd._cache_key(lazy, None, 0.7, 0.7) == cache_key(lazy, None, 0.7, 0.7)
+        assert rd._cache_key(smp, None, 0.75, 0.75) == cache_key(smp, None, 0.75, 0.75)
