@@ -9,7 +9,7 @@ kernels in libgcn_grabcut_b200.so (see include/gcn_grabcut_b200.h).  No CPU fall
 __version__ = "0.1.0"
 
 from .graph_builder import (  # noqa: F401
-    GraphBuilder, SuperpixelGraph, SuperpixelGraphConfig, BatchedRegionGraphs, build_graph_batch,
+    GraphBuilder, SuperpixelGraph, SuperpixelGraphConfig, BatchedRegionGraphs, build_graph_batch, slic_labels,
     compute_auto_prior, encode_user_hints, N_NODE_FEATS, N_EDGE_FEATS, N_PRIOR_FEATS, N_IMAGE_FEATS,
 )
 

@@ -62,7 +62,8 @@ class PathConfig(C.Structure):
     _fields_ = [("graph", GraphConfig), ("radius", C.c_int32), ("eps", C.c_float),
                 ("thr_fg", C.c_float), ("thr_bg", C.c_float), ("edge_aware", C.c_int32),
                 ("chunk", C.c_int32), ("label_bytes", C.c_int32), ("reserved", C.c_int32),
-                ("seed_frac", C.c_double)]
+                ("seed_frac", C.c_double), ("slic_segments", C.c_int32), ("slic_iters", C.c_int32),
+                ("slic_compactness", C.c_float), ("slic_sigma", C.c_float)]
 
 
 # state-dict key -> struct field (single tensors)
@@ -93,7 +94,7 @@ EXPORTED_SYMBOLS = (
     "gg_abi_version", "gg_last_error", "gg_create", "gg_destroy", "gg_set_option",
     "gg_check_device_status", "gg_build_graphs", "gg_pixel_planes", "gg_load_weights",
     "gg_coo_to_csr", "gg_resgcn_forward", "gg_refine_trimap", "gg_project_trimap",
-    "gg_guided_filter", "gg_region_labels", "gg_seed_from_prior", "gg_grabcut_guards", "gg_clean_masks", "gg_auto_prior", "gg_trimap_path_host", "gg_trimap_path_host_submit", "gg_trimap_path_host_wait",
+    "gg_guided_filter", "gg_region_labels", "gg_seed_from_prior", "gg_grabcut_guards", "gg_clean_masks", "gg_auto_prior", "gg_slic", "gg_trimap_path_host", "gg_trimap_path_host_submit", "gg_trimap_path_host_wait",
     "gg_trimap_path_device", "gg_kernel_launch_count",
     "gg_profile_enable", "gg_profile_report", "gg_selftest_math")
 
@@ -141,6 +142,8 @@ def lib() -> C.CDLL:
                                            C.c_void_p]
             L.gg_seed_from_prior.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                              C.c_int, C.c_int, C.c_int64, C.c_double, C.c_void_p]
+            L.gg_slic.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
             L.gg_auto_prior.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
             L.gg_grabcut_guards.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

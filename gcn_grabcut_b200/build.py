@@ -33,6 +33,7 @@ SOURCES = {
     "resgcn.cu": [],
     "gemm_tc.cu": [],
     "gcn_fused.cu": [],
+    "slic.cu": [],
 }
 
 

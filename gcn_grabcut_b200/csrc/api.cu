@@ -8,6 +8,7 @@
 #include "graph_build.cuh"
 #include "pixel_math.cuh"
 #include "resgcn.cuh"
+#include "slic.cuh"
 #include "trimap.cuh"
 
 namespace gg {
@@ -133,9 +134,11 @@ static PathBuffers take_path_buffers(Arena& ar, int B, const gg_graph_config& cf
 static size_t path_workspace_bytes(gg_context* ctx, int B, int H, int W, const gg_path_config& pc) {
   const gg_graph_config cfg = norm_cfg(pc.graph);
   const long long SN = (long long)B * cfg.node_cap, SE = 2ll * B * cfg.pair_cap;
+  const size_t slic = pc.slic_segments > 0 ? slic_workspace_bytes(B, H, W, pc.slic_segments) +
+                                                 Arena::padded((size_t)B * H * W, 4) : 0;
   return path_graph_arrays_bytes(B, cfg) + graph_workspace_bytes(B, H, W, cfg) +
          resgcn_workspace_bytes(ctx->net, SN, SE, B) + trimap_workspace_bytes(B, H, W, false) +
-         seed_workspace_bytes(B, SN);
+         seed_workspace_bytes(B, SN) + slic;
 }
 
 static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* labels, int B,
@@ -161,6 +164,17 @@ static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_
   const gg_graph_config cfg = norm_cfg(pc.graph);
   const long long SN = (long long)B * cfg.node_cap, SE = 2ll * B * cfg.pair_cap;
   PathBuffers pb = take_path_buffers(ar, B, cfg);
+  if (labels == nullptr) {
+    // superpixels on the device: the workspace of SLIC is dead once the label maps exist, the
+    // stages that follow reuse it (mark / rewind)
+    GG_REQUIRE(pc.slic_segments > 0, "trimap path: no label maps and slic_segments == 0");
+    int32_t* lab = ar.take<int32_t>((size_t)B * H * W);
+    const size_t mark = ar.off;
+    GG_TRY(slic_labels(ctx, ar, bgr, B, H, W, pc.slic_segments, pc.slic_compactness > 0 ? pc.slic_compactness : 10.0,
+                       pc.slic_sigma < 0 ? 1.0 : pc.slic_sigma, pc.slic_iters > 0 ? pc.slic_iters : 10, lab, nullptr, st));
+    ar.off = mark;
+    labels = lab;
+  }
   const uint8_t* gray = nullptr;
   GG_TRY(build_graphs(ctx, ar, bgr, labels, B, H, W, cfg, pb.g, st, &gray));
   if (graph_done) GG_CUDA_OK(cudaEventRecord(graph_done, st));
@@ -352,6 +366,17 @@ int gg_build_graphs(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_d
                        "gg_build_graphs");
 }
 
+int gg_slic(gg_handle h, const uint8_t* bgr_dev, int B, int H, int W, int n_segments, double compactness, double sigma,
+            int max_iter, int32_t* labels_dev, int32_t* n_labels_dev, void* stream) {
+  GG_REQUIRE(h && bgr_dev && labels_dev, "gg_slic: null argument");
+  GG_REQUIRE(B > 0 && H >= 2 && W >= 2 && n_segments >= 1, "gg_slic: bad sizes");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_TRY(h->arena.reserve(slic_workspace_bytes(B, H, W, n_segments)));
+  return arena_checked(h->arena, slic_labels(h, h->arena, bgr_dev, B, H, W, n_segments, compactness, sigma,
+                                             max_iter > 0 ? max_iter : 10, labels_dev, n_labels_dev, (cudaStream_t)stream),
+                       "gg_slic");
+}
+
 int gg_pixel_planes(gg_handle h, const uint8_t* bgr_dev, int B, int H, int W, float* lab_dev,
                     float* hsv_dev, float* gray_dev, float* grad_dev, void* stream) {
   GG_REQUIRE(h && bgr_dev, "gg_pixel_planes: null argument");
@@ -478,7 +503,8 @@ int gg_guided_filter(gg_handle h, const float* guide_dev, const float* src_dev, 
 int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, int B, int H, int W,
                           const gg_path_config* cfg, uint8_t* trimap_dev, float* probs_dev,
                           int64_t* node_off_dev, void* stream) {
-  GG_REQUIRE(h && bgr_dev && labels_dev && cfg && trimap_dev, "gg_trimap_path_device: null argument");
+  GG_REQUIRE(h && bgr_dev && cfg && trimap_dev && (labels_dev || cfg->slic_segments > 0),
+             "gg_trimap_path_device: null argument");
   GG_CUDA_OK(cudaSetDevice(h->device));
   if (!h->net.loaded) { set_error("gg_trimap_path_device: call gg_load_weights first"); return GG_ERR_STATE; }
   GG_TRY(h->arena.reserve(path_multi_workspace_bytes(h, B, H, W, *cfg)));
@@ -496,7 +522,9 @@ int gg_trimap_path_device(gg_handle h, const uint8_t* bgr_dev, const int32_t* la
 static int host_submit(gg_handle h, const uint8_t* bgr_host, const void* labels_host_v, int B, int H,
                        int W, const gg_path_config* cfg, uint8_t* trimap_host, int32_t* n_nodes_host,
                        int32_t* n_edges_host, int* ticket, size_t chunk_input_bytes) {
-  GG_REQUIRE(h && bgr_host && labels_host_v && cfg && trimap_host && ticket, "gg_trimap_path_host: null argument");
+  GG_REQUIRE(h && bgr_host && cfg && trimap_host && ticket && (labels_host_v || cfg->slic_segments > 0),
+             "gg_trimap_path_host: null argument");
+  const bool device_slic = labels_host_v == nullptr;
   GG_REQUIRE(B > 0 && H >= 2 && W >= 2, "gg_trimap_path_host: bad shape");
   GG_REQUIRE(cfg->label_bytes == 0 || cfg->label_bytes == 4 || cfg->label_bytes == 2,
              "gg_trimap_path_host: label_bytes must be 4 (int32) or 2 (uint16)");
@@ -545,16 +573,17 @@ static int host_submit(gg_handle h, const uint8_t* bgr_host, const void* labels_
     if (h->slot_used[s]) GG_CUDA_OK(cudaStreamWaitEvent(h->s_in, ev_out[s], 0));
     h->slot_used[s] = true;
     GG_CUDA_OK(cudaMemcpyAsync(d_bgr, bgr_host + (size_t)b0 * npx * 3, (size_t)nb * npx * 3, cudaMemcpyHostToDevice, h->s_in));
-    GG_CUDA_OK(cudaMemcpyAsync(lbytes == 2 ? (void*)d_lab16 : (void*)d_lab, labels_host + (size_t)b0 * npx * lbytes,
-                               (size_t)nb * npx * lbytes, cudaMemcpyHostToDevice, h->s_in));
+    if (!device_slic)
+      GG_CUDA_OK(cudaMemcpyAsync(lbytes == 2 ? (void*)d_lab16 : (void*)d_lab, labels_host + (size_t)b0 * npx * lbytes,
+                                 (size_t)nb * npx * lbytes, cudaMemcpyHostToDevice, h->s_in));
     GG_CUDA_OK(cudaEventRecord(ev_in[s], h->s_in));
     cudaStream_t rs = par ? h->s_sub[3] : h->s_run;
     GG_CUDA_OK(cudaStreamWaitEvent(rs, ev_in[s], 0));
-    if (lbytes == 2)
+    if (lbytes == 2 && !device_slic)
       GG_LAUNCH(h, k_widen_labels, ceil_div((long long)nb * npx, 256 * 8), 256, 0, rs, d_lab16, d_lab, (size_t)nb * npx);
     h->status_word = h->d_status + 2 + par;
-    h->rs_direct = lbytes == 2 ? 1 : 0;      // 7 B/px in: copy-bound, keep the L2 atomics low (see build_graphs)
-    int st = run_path(h, ar, d_bgr, d_lab, nb, H, W, *cfg, d_tri, nullptr, nullptr,
+    h->rs_direct = (lbytes == 2 || device_slic) ? 1 : 0;   // 7 B/px in: copy-bound, keep the L2 atomics low (see build_graphs)
+    int st = run_path(h, ar, d_bgr, device_slic ? nullptr : d_lab, nb, H, W, *cfg, d_tri, nullptr, nullptr,
                       n_nodes_host ? n_nodes_host + b0 : nullptr, n_edges_host ? n_edges_host + b0 : nullptr,
                       rs);
     h->status_word = h->d_status;

@@ -1,0 +1,512 @@
+// SLIC superpixels on the device -- the input producer in front of the trimap path
+// (GraphBuilder._compute_superpixels, graph_builder.py:177-188: skimage.segmentation.slic on the
+// CIELAB image, compactness 10, sigma 1, 10 iterations, connectivity enforced).
+//
+// The algorithm follows scikit-image's (oracle/slic_port.py restates it, with citations):
+//   k_slic_lab_minmax    float32 CIELAB of the image, global min / max over all three channels
+//   k_slic_features      rescale to [0,1], separable Gaussian (scipy.ndimage "reflect" border), the
+//                        second rgb2lab that skimage applies to any 3-channel input, x 1/compactness
+//   k_slic_init          centres on skimage's regular grid
+//   k_slic_assign        per pixel: the centres of the 5 x 5 grid cells around it, skimage's window
+//                        test and distance |dc|^2 + |dxy|^2 / step^2, lowest index wins ties; the
+//                        block accumulates its pixels into per-centre sums (integers: count, y, x,
+//                        fixed-point colour -> the result does not depend on the order of the atomics)
+//   k_slic_update        centres = means
+//   k_slic_cc_*          connectivity: union-find components of equal label (4-neighbours),
+//                        components smaller than half a nominal superpixel join the component of
+//                        the pixel above (or left of) their first pixel, consecutive relabelling in
+//                        raster order of the components' first pixels -> labels 0..N-1, all used.
+// Differences from scikit-image (parity with it is unpinned anyway, no build of it can be run here):
+// a pixel looks at the 25 centres that STARTED in the cells around it instead of at every centre
+// whose window reaches it; float32 arithmetic with fused multiply-adds; the merge rule of the
+// connectivity pass is order-free instead of the sequential flood fill's "last labelled
+// neighbour".  The gate is segmentation quality against the restatement (tests).
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "pixel_math.cuh"
+#include "slic.cuh"
+
+namespace gg {
+
+GG_D int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+GG_D float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct LabF {
+  float m[9];
+};
+
+// float32 CIELAB of a uint8 pixel (same formulas as pixel_math.cuh, single precision)
+GG_D void bgr_to_lab_f32(const float* __restrict__ lin, const LabF& M, int b, int g, int r, float& L, float& A, float& B) {
+  const float lr = lin[r], lg = lin[g], lb = lin[b];
+  const float x = fmaf(M.m[2], lb, fmaf(M.m[1], lg, M.m[0] * lr));
+  const float y = fmaf(M.m[5], lb, fmaf(M.m[4], lg, M.m[3] * lr));
+  const float z = fmaf(M.m[8], lb, fmaf(M.m[7], lg, M.m[6] * lr));
+  const float fx = x > 0.008856f ? cbrtf(x) : fmaf(7.787f, x, 16.0f / 116.0f);
+  const float fy = y > 0.008856f ? cbrtf(y) : fmaf(7.787f, y, 16.0f / 116.0f);
+  const float fz = z > 0.008856f ? cbrtf(z) : fmaf(7.787f, z, 16.0f / 116.0f);
+  L = fmaf(116.0f, fy, -16.0f);
+  A = 500.0f * (fx - fy);
+  B = 200.0f * (fy - fz);
+}
+
+// rgb2lab of float channels in [0,1] (the second conversion skimage's slic applies)
+GG_D void rgbf_to_lab_f32(const LabF& M, float r, float g, float b, float& L, float& A, float& B) {
+  auto lin = [](float v) { return v > 0.04045f ? __powf((v + 0.055f) * (1.0f / 1.055f), 2.4f) : v * (1.0f / 12.92f); };
+  const float lr = lin(r), lg = lin(g), lb = lin(b);
+  const float x = fmaf(M.m[2], lb, fmaf(M.m[1], lg, M.m[0] * lr));
+  const float y = fmaf(M.m[5], lb, fmaf(M.m[4], lg, M.m[3] * lr));
+  const float z = fmaf(M.m[8], lb, fmaf(M.m[7], lg, M.m[6] * lr));
+  const float fx = x > 0.008856f ? cbrtf(x) : fmaf(7.787f, x, 16.0f / 116.0f);
+  const float fy = y > 0.008856f ? cbrtf(y) : fmaf(7.787f, y, 16.0f / 116.0f);
+  const float fz = z > 0.008856f ? cbrtf(z) : fmaf(7.787f, z, 16.0f / 116.0f);
+  L = fmaf(116.0f, fy, -16.0f);
+  A = 500.0f * (fx - fy);
+  B = 200.0f * (fy - fz);
+}
+
+// ---------------------------------------------------------------------------- Lab range
+__global__ void k_slic_minmax_init(int* __restrict__ minmax, int B) {      // {+inf, -inf} as ordered ints
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { minmax[2 * b] = 0x7f800000; minmax[2 * b + 1] = (int)(0xff800000u ^ 0x7fffffffu); }
+}
+__global__ void __launch_bounds__(256)
+k_slic_lab_minmax(const uint8_t* __restrict__ bgr, const double* __restrict__ lin_lut, LabF M, int HW,
+                  int* __restrict__ minmax /*[B][2] ordered ints*/) {
+  __shared__ float s_lin[256];
+  __shared__ float sred[32];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lin[i] = (float)lin_lut[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const uint8_t* img = bgr + (size_t)b * HW * 3;
+  const float INF = __int_as_float(0x7f800000);
+  float mn = INF, mx = -INF;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const uint8_t* p = img + (size_t)i * 3;
+    float L, A, Bv;
+    bgr_to_lab_f32(s_lin, M, p[0], p[1], p[2], L, A, Bv);
+    mn = fminf(mn, fminf(L, fminf(A, Bv)));
+    mx = fmaxf(mx, fmaxf(L, fmaxf(A, Bv)));
+  }
+  mn = block_reduce<float>(mn, INF, OpMinF(), sred);
+  mx = block_reduce<float>(mx, -INF, OpMaxF(), sred);
+  if (threadIdx.x == 0) {
+    atomicMin(&minmax[2 * b], f2ord(mn));
+    atomicMax(&minmax[2 * b + 1], f2ord(mx));
+  }
+}
+
+// ---------------------------------------------------------------------------- feature image
+constexpr int SF_T = 32;            // output tile
+constexpr int SF_MAXR = 8;          // Gaussian radius limit (sigma <= 2)
+
+struct GaussW {
+  float w[2 * SF_MAXR + 1];
+  int r;
+};
+
+GG_D int reflect_sym(int i, int n) {          // scipy.ndimage mode="reflect": d c b a | a b c d | d c b a
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - 1 - i;
+  return i;
+}
+
+__global__ void __launch_bounds__(256)
+k_slic_features(const uint8_t* __restrict__ bgr, const double* __restrict__ lin_lut, LabF M, GaussW gw,
+                const int* __restrict__ minmax, int H, int W, float inv_comp, float4* __restrict__ feat) {
+  constexpr int TP = SF_T + 2 * SF_MAXR;
+  __shared__ float s_lin[256];
+  __shared__ float s_in[3][TP][TP + 1];
+  __shared__ float s_v[3][SF_T][TP + 1];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lin[i] = (float)lin_lut[i];
+  __syncthreads();
+  const int b = blockIdx.z, y0 = blockIdx.y * SF_T, x0 = blockIdx.x * SF_T, r = gw.r;
+  const uint8_t* img = bgr + (size_t)b * H * W * 3;
+  const float mn = ord2f(minmax[2 * b]), rng = ord2f(minmax[2 * b + 1]) - mn;
+  const float inv = rng != 0.0f ? 1.0f / rng : 1.0f;
+  const int tw = SF_T + 2 * r;
+  for (int i = threadIdx.x; i < tw * tw; i += blockDim.x) {
+    const int ty = i / tw, tx = i - ty * tw;
+    const int y = reflect_sym(y0 + ty - r, H), x = reflect_sym(x0 + tx - r, W);
+    const uint8_t* p = img + ((size_t)y * W + x) * 3;
+    float L, A, Bv;
+    bgr_to_lab_f32(s_lin, M, p[0], p[1], p[2], L, A, Bv);
+    s_in[0][ty][tx] = (L - mn) * inv; s_in[1][ty][tx] = (A - mn) * inv; s_in[2][ty][tx] = (Bv - mn) * inv;
+  }
+  __syncthreads();
+  // vertical pass (axis 0 first, like scipy), then horizontal
+  for (int i = threadIdx.x; i < 3 * SF_T * tw; i += blockDim.x) {
+    const int c = i / (SF_T * tw), rem = i - c * SF_T * tw, ty = rem / tw, tx = rem - ty * tw;
+    float s = 0.0f;
+    for (int d = -r; d <= r; ++d) s = fmaf(gw.w[d + r], s_in[c][ty + r + d][tx], s);
+    s_v[c][ty][tx] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SF_T * SF_T; i += blockDim.x) {
+    const int ty = i / SF_T, tx = i - ty * SF_T;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= H || x >= W) continue;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s = 0.0f;
+      for (int d = -r; d <= r; ++d) s = fmaf(gw.w[d + r], s_v[c][ty][tx + r + d], s);
+      v[c] = s;
+    }
+    float L, A, Bv;
+    rgbf_to_lab_f32(M, v[0], v[1], v[2], L, A, Bv);
+    feat[((size_t)b * H + y) * W + x] = make_float4(L * inv_comp, A * inv_comp, Bv * inv_comp, 0.0f);
+  }
+}
+
+// ---------------------------------------------------------------------------- k-means
+struct SlicGrid {
+  int gy, gx, sy, ty, sx, tx, step;      // centres at (sy + i ty, sx + j tx), i < gy, j < gx
+};
+constexpr float SLIC_FIX = 4096.0f;      // fixed-point scale of the colour sums
+
+__global__ void k_slic_init(const float4* __restrict__ feat, SlicGrid g, int H, int W, float* __restrict__ cen /*[B][K][5]*/,
+                            int* __restrict__ sums /*[B][K][6]*/) {
+  const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = g.gy * g.gx;
+  if (k >= K) return;
+  const int i = k / g.gx, j = k - i * g.gx;
+  const int y = g.sy + i * g.ty, x = g.sx + j * g.tx;
+  const float4 f = feat[((size_t)b * H + y) * W + x];
+  float* c = cen + ((size_t)b * K + k) * 5;
+  c[0] = (float)y; c[1] = (float)x; c[2] = f.x; c[3] = f.y; c[4] = f.z;
+  int* s = sums + ((size_t)b * K + k) * 6;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) s[q] = 0;
+}
+
+constexpr int SA_TY = 16, SA_TX = 64;    // pixel tile of k_slic_assign (256 threads x 4 pixels)
+constexpr int SA_MAXC = 12;              // cells per axis that a tile can touch (tile / step + 5)
+
+GG_D int slic_cell(int p, int start, int step, int n) {       // home cell of a coordinate (boundaries midway)
+  const int c = (p - start + step / 2) / step;
+  return min(max(p - start + step / 2 < 0 ? 0 : c, 0), n - 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, SlicGrid g, int H, int W,
+              int32_t* __restrict__ labels, int* __restrict__ sums) {
+  __shared__ float s_c[SA_MAXC * SA_MAXC][5];
+  __shared__ int s_win[SA_MAXC * SA_MAXC][4];      // y_min, y_max, x_min, x_max of every loaded centre
+  __shared__ int s_sum[SA_MAXC * SA_MAXC][6];
+  const int b = blockIdx.z, y0 = blockIdx.y * SA_TY, x0 = blockIdx.x * SA_TX;
+  const int K = g.gy * g.gx;
+  const int ci0 = max(slic_cell(y0, g.sy, g.ty, g.gy) - 2, 0);
+  const int ci1 = min(slic_cell(min(y0 + SA_TY, H) - 1, g.sy, g.ty, g.gy) + 2, g.gy - 1);
+  const int cj0 = max(slic_cell(x0, g.sx, g.tx, g.gx) - 2, 0);
+  const int cj1 = min(slic_cell(min(x0 + SA_TX, W) - 1, g.sx, g.tx, g.gx) + 2, g.gx - 1);
+  const int nci = ci1 - ci0 + 1, ncj = cj1 - cj0 + 1;          // <= SA_MAXC by the launch check
+  const float* cb = cen + (size_t)b * K * 5;
+  for (int i = threadIdx.x; i < nci * ncj; i += blockDim.x) {
+    const int k = (ci0 + i / ncj) * g.gx + cj0 + i % ncj;
+    const float cy = cb[k * 5], cx = cb[k * 5 + 1];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) s_c[i][q] = cb[k * 5 + q];
+    s_win[i][0] = (int)fmaxf(cy - 2.0f * g.ty, 0.0f);
+    s_win[i][1] = (int)fminf(cy + 2.0f * g.ty + 1.0f, (float)H);
+    s_win[i][2] = (int)fmaxf(cx - 2.0f * g.tx, 0.0f);
+    s_win[i][3] = (int)fminf(cx + 2.0f * g.tx + 1.0f, (float)W);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) s_sum[i][q] = 0;
+  }
+  __syncthreads();
+  const float w_sp = 1.0f / (float)(g.step * g.step);
+  const int tx = threadIdx.x & 63, ty4 = threadIdx.x >> 6;      // 64 columns x 4 row groups
+  const int x = x0 + tx;
+  for (int rr = 0; rr < SA_TY / 4; ++rr) {
+    const int y = y0 + ty4 + 4 * rr;
+    if (y >= H || x >= W) continue;
+    const float4 f = feat[((size_t)b * H + y) * W + x];
+    const int hi = slic_cell(y, g.sy, g.ty, g.gy), hj = slic_cell(x, g.sx, g.tx, g.gx);
+    float best = __int_as_float(0x7f7fffff);
+    int best_slot = -1;
+    for (int i = max(hi - 2, ci0); i <= min(hi + 2, ci1); ++i) {
+      for (int j = max(hj - 2, cj0); j <= min(hj + 2, cj1); ++j) {     // increasing centre index: ties -> lower index
+        const int slot = (i - ci0) * ncj + (j - cj0);
+        if (y < s_win[slot][0] || y >= s_win[slot][1] || x < s_win[slot][2] || x >= s_win[slot][3]) continue;
+        const float dy = s_c[slot][0] - (float)y, dx = s_c[slot][1] - (float)x;
+        float d = (dy * dy + dx * dx) * w_sp;
+        if (!(d < best)) continue;                                   // the colour term only adds
+        const float d0 = f.x - s_c[slot][2], d1 = f.y - s_c[slot][3], d2 = f.z - s_c[slot][4];
+        d += d0 * d0 + d1 * d1 + d2 * d2;
+        if (d < best) { best = d; best_slot = slot; }
+      }
+    }
+    if (best_slot < 0) {        // no window reaches the pixel (cannot happen on a regular grid): home cell
+      best_slot = (min(max(hi, ci0), ci1) - ci0) * ncj + (min(max(hj, cj0), cj1) - cj0);
+    }
+    labels[((size_t)b * H + y) * W + x] = (ci0 + best_slot / ncj) * g.gx + cj0 + best_slot % ncj;
+    atomicAdd(&s_sum[best_slot][0], 1);
+    atomicAdd(&s_sum[best_slot][1], y);
+    atomicAdd(&s_sum[best_slot][2], x);
+    atomicAdd(&s_sum[best_slot][3], __float2int_rn(f.x * SLIC_FIX));
+    atomicAdd(&s_sum[best_slot][4], __float2int_rn(f.y * SLIC_FIX));
+    atomicAdd(&s_sum[best_slot][5], __float2int_rn(f.z * SLIC_FIX));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nci * ncj; i += blockDim.x) {
+    if (s_sum[i][0] == 0) continue;
+    const int k = (ci0 + i / ncj) * g.gx + cj0 + i % ncj;
+    int* s = sums + ((size_t)b * K + k) * 6;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) atomicAdd(&s[q], s_sum[i][q]);
+  }
+}
+
+__global__ void k_slic_update(int K, float* __restrict__ cen, int* __restrict__ sums) {
+  const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  int* s = sums + ((size_t)b * K + k) * 6;
+  float* c = cen + ((size_t)b * K + k) * 5;
+  const int n = s[0];
+  if (n > 0) {                               // an empty cluster keeps its centre (skimage: NaN, never wins again)
+    const float inv = 1.0f / (float)n;
+    c[0] = (float)s[1] * inv; c[1] = (float)s[2] * inv;
+    c[2] = (float)s[3] * inv * (1.0f / SLIC_FIX); c[3] = (float)s[4] * inv * (1.0f / SLIC_FIX);
+    c[4] = (float)s[5] * inv * (1.0f / SLIC_FIX);
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) s[q] = 0;
+}
+
+// ---------------------------------------------------------------------------- connectivity
+GG_D int cc_find(int* L, int i) {
+  int r = i;
+  while (true) {
+    const int pr = reinterpret_cast<volatile int*>(L)[r];
+    if (pr == r) break;
+    r = pr;
+  }
+  return r;
+}
+GG_D void cc_union(int* L, int a, int b) {
+  while (true) {
+    a = cc_find(L, a);
+    b = cc_find(L, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_slic_cc_init(int HW, int* __restrict__ L, int* __restrict__ size) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  L[(size_t)b * HW + i] = i;
+  size[(size_t)b * HW + i] = 0;
+}
+__global__ void __launch_bounds__(256)
+k_slic_cc_merge(const int32_t* __restrict__ labels, int H, int W, int* __restrict__ L) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = H * W;
+  if (i >= HW) return;
+  const int32_t* lab = labels + (size_t)b * HW;
+  int* Lb = L + (size_t)b * HW;
+  const int y = i / W, x = i - y * W, v = lab[i];
+  if (x > 0 && lab[i - 1] == v) cc_union(Lb, i, i - 1);
+  if (y > 0 && lab[i - W] == v) cc_union(Lb, i, i - W);
+}
+__global__ void __launch_bounds__(256)
+k_slic_cc_flatten(int HW, int* __restrict__ L, int* __restrict__ size) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  int* Lb = L + (size_t)b * HW;
+  const int r = cc_find(Lb, i);
+  Lb[i] = r;
+  atomicAdd(&size[(size_t)b * HW + r], 1);
+}
+// roots only: a small component points at the component of the pixel above / left of its first pixel
+__global__ void __launch_bounds__(256)
+k_slic_cc_target(int H, int W, const int* __restrict__ L, const int* __restrict__ size, int min_size,
+                 int* __restrict__ target) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = H * W;
+  if (i >= HW) return;
+  const int* Lb = L + (size_t)b * HW;
+  int t = -1;                                             // not a root
+  if (Lb[i] == i) {
+    t = i;                                                // kept
+    if (size[(size_t)b * HW + i] < min_size && i > 0) {
+      const int y = i / W;
+      t = y > 0 ? Lb[i - W] : Lb[i - 1];                  // an earlier component: chains end at a kept one
+    }
+  }
+  target[(size_t)b * HW + i] = t;
+}
+// kept[i] = 1 for the roots that survive; block counts for the scan
+__global__ void __launch_bounds__(1024)
+k_slic_cc_count(int HW, const int* __restrict__ target, int* __restrict__ block_cnt, int n_blocks) {
+  __shared__ int scratch[40];
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kept = (i < HW && target[(size_t)b * HW + i] == i) ? 1 : 0;
+  int total;
+  block_exclusive_scan(kept, scratch, &total);
+  if (threadIdx.x == 0) block_cnt[(size_t)b * n_blocks + blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024)
+k_slic_cc_scan_blocks(int* __restrict__ block_cnt, int n_blocks, int32_t* __restrict__ n_labels) {
+  __shared__ int scratch[40];
+  const int b = blockIdx.x;
+  int* c = block_cnt + (size_t)b * n_blocks;
+  int carry = 0;
+  for (int base = 0; base < n_blocks; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_blocks ? c[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, scratch, &total);
+    if (i < n_blocks) c[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && n_labels) n_labels[b] = carry;
+}
+__global__ void __launch_bounds__(1024)
+k_slic_cc_newid(int HW, const int* __restrict__ target, const int* __restrict__ block_cnt, int n_blocks,
+                int* __restrict__ newid) {
+  __shared__ int scratch[40];
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kept = (i < HW && target[(size_t)b * HW + i] == i) ? 1 : 0;
+  int total;
+  const int ex = block_exclusive_scan(kept, scratch, &total);
+  if (kept) newid[(size_t)b * HW + i] = block_cnt[(size_t)b * n_blocks + blockIdx.x] + ex;
+}
+__global__ void __launch_bounds__(256)
+k_slic_cc_relabel(int HW, const int* __restrict__ L, const int* __restrict__ target, const int* __restrict__ newid,
+                  int32_t* __restrict__ labels) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const size_t o = (size_t)b * HW;
+  int r = L[o + i];
+  for (int guard = 0; guard < HW; ++guard) {            // follow the merge chain to a kept root
+    const int t = target[o + r];
+    if (t == r) break;
+    r = t;
+  }
+  labels[o + i] = newid[o + r];
+}
+
+// ---------------------------------------------------------------------------- host side
+// skimage.util.regular_grid for the (1, H, W) volume (see oracle/slic_port.py)
+static SlicGrid make_grid(int H, int W, int n_segments) {
+  double dims[3] = {1.0, (double)H, (double)W};
+  int order[3] = {0, 1, 2};
+  std::sort(order, order + 3, [&](int a, int b) { return dims[a] < dims[b] || (dims[a] == dims[b] && a < b); });
+  double sd[3] = {dims[order[0]], dims[order[1]], dims[order[2]]};
+  double space = sd[0] * sd[1] * sd[2];
+  double steps[3];
+  for (double& s : steps) s = pow(space / n_segments, 1.0 / 3.0);
+  if (sd[0] < steps[0] || sd[1] < steps[1] || sd[2] < steps[2]) {
+    for (int dim = 0; dim < 3; ++dim) {
+      steps[dim] = sd[dim];
+      space = 1.0;
+      for (int q = dim + 1; q < 3; ++q) space *= sd[q];
+      if (dim < 2) {
+        const double s = pow(space / n_segments, 1.0 / (3 - dim - 1));
+        for (int q = dim + 1; q < 3; ++q) steps[q] = s;
+      }
+      if (sd[0] >= steps[0] && sd[1] >= steps[1] && sd[2] >= steps[2]) break;
+    }
+  }
+  int start[3], stepi[3];
+  for (int q = 0; q < 3; ++q) {
+    start[order[q]] = (int)floor(steps[q] / 2.0);
+    stepi[order[q]] = std::max(1, (int)nearbyint(steps[q]));      // numpy round: half to even
+  }
+  SlicGrid g;
+  g.sy = start[1]; g.ty = stepi[1]; g.sx = start[2]; g.tx = stepi[2];
+  g.gy = (H - g.sy + g.ty - 1) / g.ty; g.gx = (W - g.sx + g.tx - 1) / g.tx;
+  g.step = std::max(g.ty, g.tx);
+  return g;
+}
+
+size_t slic_workspace_bytes(int B, int H, int W, int n_segments) {
+  const SlicGrid g = make_grid(H, W, n_segments);
+  const size_t HW = (size_t)H * W, K = (size_t)g.gy * g.gx;
+  const size_t nb = (HW + 1023) / 1024;
+  return Arena::padded((size_t)B * HW, 16) + Arena::padded((size_t)B * 2, 4) + Arena::padded((size_t)B * K * 5, 4) +
+         Arena::padded((size_t)B * K * 6, 4) + Arena::padded((size_t)B * HW, 4) * 4 + Arena::padded((size_t)B * nb, 4) + 4096;
+}
+
+int slic_nominal_segments(int H, int W, int n_segments) {
+  const SlicGrid g = make_grid(H, W, n_segments);
+  return g.gy * g.gx;
+}
+
+int slic_labels(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, int W, int n_segments,
+                double compactness, double sigma, int max_iter, int32_t* labels, int32_t* n_labels, cudaStream_t st) {
+  GG_REQUIRE(B > 0 && H >= 2 && W >= 2 && n_segments >= 1, "slic: bad sizes");
+  GG_REQUIRE(compactness > 0 && sigma >= 0 && sigma <= 2.0, "slic: compactness must be > 0, sigma in [0, 2]");
+  GG_REQUIRE((long long)H * W < (1ll << 31), "slic: image too large");
+  const SlicGrid g = make_grid(H, W, n_segments);
+  GG_REQUIRE(g.gy >= 1 && g.gx >= 1, "slic: empty grid");
+  GG_REQUIRE(SA_TY / g.ty + 6 <= SA_MAXC && SA_TX / g.tx + 6 <= SA_MAXC,
+             "slic: n_segments too large for this image (grid step %d x %d pixels; need >= 11 x 11)", g.ty, g.tx);
+  const int HW = H * W, K = g.gy * g.gx;
+  const int nb = ceil_div(HW, 1024);
+  float4* feat = ar.take<float4>((size_t)B * HW);
+  int* minmax = ar.take<int>((size_t)B * 2);
+  float* cen = ar.take<float>((size_t)B * K * 5);
+  int* sums = ar.take<int>((size_t)B * K * 6);
+  int* L = ar.take<int>((size_t)B * HW);
+  int* size = ar.take<int>((size_t)B * HW);
+  int* target = ar.take<int>((size_t)B * HW);
+  int* newid = ar.take<int>((size_t)B * HW);
+  int* block_cnt = ar.take<int>((size_t)B * nb);
+
+  LabF M;
+  {
+    const LabMatrix Md = make_lab_matrix();
+    for (int i = 0; i < 9; ++i) M.m[i] = (float)Md.m[i];
+  }
+  GaussW gw{};
+  gw.r = sigma > 0 ? (int)(4.0 * sigma + 0.5) : 0;
+  {
+    double w[2 * SF_MAXR + 1], tot = 0.0;
+    for (int d = -gw.r; d <= gw.r; ++d) { w[d + gw.r] = sigma > 0 ? exp(-0.5 * d * d / (sigma * sigma)) : 1.0; tot += w[d + gw.r]; }
+    for (int d = 0; d <= 2 * gw.r; ++d) gw.w[d] = (float)(w[d] / tot);
+  }
+  GG_LAUNCH(ctx, k_slic_minmax_init, ceil_div(B, 256), 256, 0, st, minmax, B);
+  {
+    dim3 grid(std::min(ceil_div(HW, 256), 64), B);
+    GG_LAUNCH(ctx, k_slic_lab_minmax, grid, 256, 0, st, bgr, ctx->d_lin, M, HW, minmax);
+  }
+  {
+    dim3 grid(ceil_div(W, SF_T), ceil_div(H, SF_T), B);
+    GG_LAUNCH(ctx, k_slic_features, grid, 256, 0, st, bgr, ctx->d_lin, M, gw, minmax, H, W, (float)(1.0 / compactness), feat);
+  }
+  {
+    dim3 grid(ceil_div(K, 256), B);
+    GG_LAUNCH(ctx, k_slic_init, grid, 256, 0, st, feat, g, H, W, cen, sums);
+    dim3 ga(ceil_div(W, SA_TX), ceil_div(H, SA_TY), B);
+    for (int it = 0; it < max_iter; ++it) {
+      GG_LAUNCH(ctx, k_slic_assign, ga, 256, 0, st, feat, cen, g, H, W, labels, sums);
+      GG_LAUNCH(ctx, k_slic_update, grid, 256, 0, st, K, cen, sums);
+    }
+  }
+  // connectivity (skimage: min_size = int(0.5 * H W / K))
+  {
+    const int min_size = (int)(0.5 * ((double)HW / (double)K));
+    dim3 grid(ceil_div(HW, 256), B), grid1k(nb, B);
+    GG_LAUNCH(ctx, k_slic_cc_init, grid, 256, 0, st, HW, L, size);
+    GG_LAUNCH(ctx, k_slic_cc_merge, grid, 256, 0, st, labels, H, W, L);
+    GG_LAUNCH(ctx, k_slic_cc_flatten, grid, 256, 0, st, HW, L, size);
+    GG_LAUNCH(ctx, k_slic_cc_target, grid, 256, 0, st, H, W, L, size, min_size, target);
+    GG_LAUNCH(ctx, k_slic_cc_count, grid1k, 1024, 0, st, HW, target, block_cnt, nb);
+    GG_LAUNCH(ctx, k_slic_cc_scan_blocks, B, 1024, 0, st, block_cnt, nb, n_labels);
+    GG_LAUNCH(ctx, k_slic_cc_newid, grid1k, 1024, 0, st, HW, target, block_cnt, nb, newid);
+    GG_LAUNCH(ctx, k_slic_cc_relabel, grid, 256, 0, st, HW, L, target, newid, labels);
+  }
+  return GG_OK;
+}
+
+}  // namespace gg

@@ -10,20 +10,25 @@ mean-Lab space, node / edge attribute epilogues and the automatic prior.  The ar
 the reference, so the result feeds ``ResGCNNet`` / ``refine_trimap`` / ``cv2.grabCut``
 unchanged.
 
-SLIC (``GraphBuilder._compute_superpixels``, reference :177-188) is the input producer of
-the path and is not re-implemented: pass the label map as ``segments=``; if it is omitted
-and scikit-image is importable, ``skimage.segmentation.slic`` is called exactly as the
-reference does.
+SLIC (``GraphBuilder._compute_superpixels``, reference :177-188) is the input producer of the
+path.  A label map passed as ``segments=`` is used as it is; otherwise the superpixels are
+computed on the GPU (``slic_labels`` -> ``gg_slic``: scikit-image's algorithm restated, see
+csrc/slic.cu -- label-for-label parity with a scikit-image build is unpinned, none can be run
+here).  ``SLIC_BACKEND = "skimage"`` (env ``GG_SLIC=skimage``) calls
+``skimage.segmentation.slic`` exactly as the reference does when it is importable.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
 import numpy as np
 
 from . import _native as nat
+
+SLIC_BACKEND = os.environ.get("GG_SLIC", "gpu")      # "gpu" | "skimage"
 
 N_IMAGE_FEATS = 16
 N_PRIOR_FEATS = 3
@@ -177,6 +182,37 @@ def build_graph_batch(images, segments, config: Optional[SuperpixelGraphConfig] 
     return out
 
 
+def slic_labels(images, config: Optional[SuperpixelGraphConfig] = None, max_num_iter: int = 10, device=None,
+                return_counts: bool = False):
+    """
+    SLIC superpixels of a batch of BGR uint8 images (B,H,W,3) on the GPU (``gg_slic``): the
+    reference's ``slic(lab, n_segments, compactness, sigma, start_label=0)`` call
+    (graph_builder.py:177-188).  Returns int32 (B,H,W) label maps, contiguous 0..N-1 per image
+    (and the label counts with ``return_counts``).  Accepts numpy arrays or CUDA tensors (then
+    CUDA tensors are returned).
+    """
+    import torch
+    cfg = config or SuperpixelGraphConfig()
+    as_tensor = torch.is_tensor(images)
+    dev = nat.device_index(images.device if as_tensor and images.is_cuda else (device if device is not None else "cuda"))
+    h = nat.handle(dev)
+    tdev = torch.device("cuda", dev)
+    img_t = images if as_tensor else torch.from_numpy(np.ascontiguousarray(images, dtype=np.uint8))
+    img_t = img_t.to(tdev).contiguous()
+    if img_t.dtype != torch.uint8 or img_t.dim() != 4 or img_t.shape[-1] != 3:
+        raise ValueError("images must be uint8 (B,H,W,3)")
+    B, H, W = (int(v) for v in img_t.shape[:3])
+    lab = torch.empty((B, H, W), dtype=torch.int32, device=tdev)
+    cnt = torch.empty(B, dtype=torch.int32, device=tdev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().gg_slic(h.ptr, nat.ptr(img_t), B, H, W, int(cfg.n_segments), float(cfg.compactness),
+                                    float(cfg.sigma), int(max_num_iter), nat.ptr(lab), nat.ptr(cnt),
+                                    C.c_void_p(nat.current_stream(dev))))
+    if as_tensor:
+        return (lab, cnt) if return_counts else lab
+    return (lab.cpu().numpy(), cnt.cpu().numpy()) if return_counts else lab.cpu().numpy()
+
+
 # --------------------------------------------------------------------------- reference API
 class GraphBuilder:
     """
@@ -195,20 +231,20 @@ class GraphBuilder:
         self._device = device
 
     def _compute_superpixels(self) -> np.ndarray:
-        """Input producer (reference :177-188): the supplied label map, else skimage SLIC."""
+        """Input producer (reference :177-188): the supplied label map, else SLIC -- on the GPU, or
+        scikit-image's when ``SLIC_BACKEND == "skimage"``."""
         if self._segments is not None:
             return np.ascontiguousarray(self._segments, dtype=np.int32)
-        try:
+        cfg = self.config
+        if SLIC_BACKEND == "skimage":
             from skimage.segmentation import slic
             from skimage.color import rgb2lab
-        except ImportError as e:
-            raise RuntimeError(
-                "GraphBuilder needs a label map: pass segments=<(H,W) int32> (SLIC is the input "
-                "producer of the trimap path and scikit-image is not installed)") from e
-        cfg = self.config
-        img = rgb2lab(self.rgb).astype(np.float32) if cfg.use_lab else self.rgb.astype(float)
-        return slic(img, n_segments=cfg.n_segments, compactness=cfg.compactness, sigma=cfg.sigma,
-                    start_label=0, channel_axis=-1).astype(np.int32)
+            img = rgb2lab(self.rgb).astype(np.float32) if cfg.use_lab else self.rgb.astype(float)
+            return slic(img, n_segments=cfg.n_segments, compactness=cfg.compactness, sigma=cfg.sigma,
+                        start_label=0, channel_axis=-1).astype(np.int32)
+        if not cfg.use_lab:
+            raise NotImplementedError("the GPU SLIC clusters in CIELAB (use_lab=True, the reference's default)")
+        return slic_labels(self.bgr[None], cfg, device=self._device)[0]
 
     def build(self, segments: Optional[np.ndarray] = None) -> SuperpixelGraph:
         if segments is not None:

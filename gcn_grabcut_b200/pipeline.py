@@ -178,7 +178,7 @@ class TrimapPath:
     def __init__(self, model, sp_config: Optional[SuperpixelGraphConfig] = None, node_cap: int = 512,
                  pair_cap: int = 0, threshold_fg: float = 0.55, threshold_bg: float = 0.55,
                  filter_radius: int = 8, eps: float = 1e-3, edge_aware: bool = True, chunk: int = 0,
-                 seed_frac: float = 0.0, device=None):
+                 seed_frac: float = 0.0, device=None, device_slic: bool = False):
         self.cfg = sp_config or SuperpixelGraphConfig()
         self.dev = nat.device_index(device if device is not None else "cuda")
         self.h = nat.handle(self.dev)
@@ -191,7 +191,9 @@ class TrimapPath:
         self.pc = nat.PathConfig(
             nat.GraphConfig(int(self.cfg.connectivity), int(self.cfg.n_nonlocal), self.node_cap, pair_cap),
             int(filter_radius), float(eps), float(threshold_fg), float(threshold_bg), int(bool(edge_aware)),
-            int(chunk), 4, 0, float(seed_frac))
+            int(chunk), 4, 0, float(seed_frac),
+            int(self.cfg.n_segments) if device_slic else 0, 10, float(self.cfg.compactness), float(self.cfg.sigma))
+        self.device_slic = bool(device_slic)
 
     def _ensure_weights(self):
         # one device handle holds one set of weights: if another model (a ResGCNNet, another
@@ -201,13 +203,13 @@ class TrimapPath:
             nat.load_state_dict(self.h, self._state)
             self.h.weights_token = self
 
-    def __call__(self, images, labels, out: Optional[np.ndarray] = None,
+    def __call__(self, images, labels=None, out: Optional[np.ndarray] = None,
                  return_counts: bool = False):
         """Host buffers (numpy or pinned torch CPU tensors) in, host trimaps out; copies included
         (``gg_trimap_path_host``: synchronous, one batch at a time)."""
         return self.submit(images, labels, out, return_counts, _sync=True).result()
 
-    def submit(self, images, labels, out=None, return_counts: bool = False, _sync: bool = False) -> "PendingTrimaps":
+    def submit(self, images, labels=None, out=None, return_counts: bool = False, _sync: bool = False) -> "PendingTrimaps":
         """
         Asynchronous ``__call__`` for streaming many batches: enqueues the copies and kernels of
         this batch (``gg_trimap_path_host_submit``) and returns at once; ``.result()`` of the
@@ -219,28 +221,34 @@ class TrimapPath:
         import torch
         self._ensure_weights()
         img = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
-        if torch.is_tensor(labels):
+        if labels is None:
+            # superpixels on the device (TrimapPath(..., device_slic=True)): only the images cross PCIe
+            if not self.device_slic:
+                raise ValueError("labels=None needs TrimapPath(..., device_slic=True)")
+            lab = None
+        elif torch.is_tensor(labels):
             lab = labels
         elif isinstance(labels, np.ndarray) and labels.dtype == np.uint16:
             lab = torch.from_numpy(np.ascontiguousarray(labels))     # compact transport, see below
         else:
             lab = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32))
-        if img.is_cuda or lab.is_cuda:
+        if img.is_cuda or (lab is not None and lab.is_cuda):
             raise ValueError("TrimapPath.__call__ takes host buffers; use run_device for CUDA tensors")
         if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[-1] != 3:
             raise ValueError("images must be uint8 (B,H,W,3)")
         # int32 label maps are the reference layout (graph_builder.py:188); uint16 maps (labels
         # < 65536) are accepted as a compact transport: 5 instead of 7 bytes per pixel over PCIe
-        if lab.dtype not in (torch.int32, torch.uint16) or tuple(lab.shape) != tuple(img.shape[:3]):
+        if lab is not None and (lab.dtype not in (torch.int32, torch.uint16) or tuple(lab.shape) != tuple(img.shape[:3])):
             raise ValueError("labels must be int32 (or uint16) (B,H,W) matching images")
         B, H, W = int(img.shape[0]), int(img.shape[1]), int(img.shape[2])
         tri = out if out is not None else torch.empty((B, H, W), dtype=torch.uint8)
         tri_t = tri if torch.is_tensor(tri) else torch.from_numpy(tri)
         nn_ = torch.empty(B, dtype=torch.int32) if return_counts else None
         ne_ = torch.empty(B, dtype=torch.int32) if return_counts else None
-        img, lab = img.contiguous(), lab.contiguous()
+        img = img.contiguous()
+        lab = lab.contiguous() if lab is not None else None
         pc = self.pc
-        if lab.dtype == torch.uint16:
+        if lab is not None and lab.dtype == torch.uint16:
             pc = nat.PathConfig.from_buffer_copy(self.pc)
             pc.label_bytes = 2
         ticket = C.c_int(-1)
@@ -263,7 +271,7 @@ class TrimapPath:
         with torch.cuda.device(self.dev):
             self.h.check_status(nat.current_stream(self.dev))
 
-    def run_device(self, images_t, labels_t, trimap_t=None, probs_t=None, node_off_t=None, check: bool = False):
+    def run_device(self, images_t, labels_t=None, trimap_t=None, probs_t=None, node_off_t=None, check: bool = False):
         """CUDA tensors in, CUDA trimaps out, on the current stream, no host synchronisation
         (``check=False``).  The device status is sticky: call ``check_status()`` once after a run of
         calls, or pass ``check=True`` to synchronise and verify this call."""
@@ -274,7 +282,8 @@ class TrimapPath:
             trimap_t = torch.empty((B, H, W), dtype=torch.uint8, device=images_t.device)
         with torch.cuda.device(self.dev):
             nat.check(nat.lib().gg_trimap_path_device(
-                self.h.ptr, nat.ptr(images_t, torch.uint8), nat.ptr(labels_t, torch.int32), B, H, W,
+                self.h.ptr, nat.ptr(images_t, torch.uint8),
+                nat.ptr(labels_t, torch.int32) if labels_t is not None else C.c_void_p(0), B, H, W,
                 C.byref(self.pc), nat.ptr(trimap_t), nat.ptr(probs_t), nat.ptr(node_off_t),
                 C.c_void_p(nat.current_stream(self.dev))))
         if check:

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GG_ABI_VERSION 2
+#define GG_ABI_VERSION 3
 
 #define GG_N_IMAGE_FEATS 16 /* graph_builder.py:73 */
 #define GG_N_PRIOR_FEATS 3  /* graph_builder.py:74 */
@@ -134,6 +134,17 @@ typedef struct gg_graph_out {
 int gg_build_graphs(gg_handle h, const uint8_t* bgr_dev /*[B,H,W,3]*/,
                     const int32_t* labels_dev /*[B,H,W]*/, int B, int H, int W,
                     const gg_graph_config* cfg, const gg_graph_out* out, void* stream);
+
+/* GraphBuilder._compute_superpixels (graph_builder.py:177-188): skimage.segmentation.slic(lab,
+ * n_segments, compactness, sigma, start_label=0) restated on the device for a batch of BGR uint8
+ * images -- CIELAB, skimage's global min-max rescale, Gaussian pre-smoothing, its second rgb2lab of
+ * 3-channel inputs, k-means on the regular grid (max_iter rounds, 0 = 10), connectivity enforcement
+ * with min_size = half a nominal superpixel.  labels_dev [B,H,W] int32: contiguous 0..N-1 per
+ * image, every label used, in raster order of first appearance; n_labels_dev [B] optional.
+ * scikit-image cannot be run here, so label-for-label parity with it is unpinned; the restatement
+ * oracle/slic_port.py and segmentation-quality measures are the gate (tests). */
+int gg_slic(gg_handle h, const uint8_t* bgr_dev, int B, int H, int W, int n_segments, double compactness,
+            double sigma, int max_iter, int32_t* labels_dev, int32_t* n_labels_dev, void* stream);
 
 /* Per-pixel planes of GraphBuilder.__init__ (graph_builder.py:142-154): _lab [B,H,W,3],
  * _hsv [B,H,W,3], _gray [B,H,W], _grad [B,H,W], all float32; any output may be NULL. */
@@ -284,6 +295,15 @@ typedef struct gg_path_config {
   int32_t reserved;
   double seed_frac;    /* > 0: repair one-sided trimaps like _seed_from_prior (pipeline.py:149-186,
                           called by segment() with 0.1); 0 = leave the trimap as predicted */
+  /* Superpixels on the device (GraphBuilder._compute_superpixels, graph_builder.py:177-188): with
+   * slic_segments > 0 the label-map argument of the whole-path entry points may be NULL -- the
+   * maps are produced by gg_slic from the images (3 instead of 7 bytes per pixel cross PCIe) -- and
+   * graph.node_cap must leave room for the label count (about slic_segments; every label
+   * >= node_cap is reported through the status word). */
+  int32_t slic_segments;     /* SuperpixelGraphConfig.n_segments, 0 = label maps are supplied */
+  int32_t slic_iters;        /* k-means iterations, 0 = 10 (skimage max_num_iter) */
+  float slic_compactness;    /* SuperpixelGraphConfig.compactness, 0 = 10 */
+  float slic_sigma;          /* SuperpixelGraphConfig.sigma (Gaussian pre-smoothing), < 0 = 1 */
 } gg_path_config;
 
 int gg_trimap_path_host(gg_handle h, const uint8_t* bgr_host, const void* labels_host /*int32 or uint16 [B,H,W]*/, int B,

@@ -818,6 +818,9 @@ def test_reference_segment_through_the_drop_in(gg):
     res_ref = pm.GCNGrabCutPipeline(m_ref, ref.graph_builder.SuperpixelGraphConfig(n_segments=nseg),
                                     device="cpu").segment(img)
 
+    import gcn_grabcut_b200.graph_builder as ggb
+    saved_backend = ggb.SLIC_BACKEND
+    ggb.SLIC_BACKEND = "skimage"           # the same label map for both runs, through the shim's slic()
     saved = {k: getattr(pm, k) for k in ("GraphBuilder", "SuperpixelGraphConfig", "refine_trimap", "guided_filter",
                                           "_seed_from_prior", "project_to_pixels", "CLASS_BG", "CLASS_FG")}
     try:
@@ -832,6 +835,7 @@ def test_reference_segment_through_the_drop_in(gg):
         cv2.setRNGSeed(7)
         res_gg = pm.GCNGrabCutPipeline(m_gg, gg.SuperpixelGraphConfig(n_segments=nseg), device="cuda").segment(img)
     finally:
+        ggb.SLIC_BACKEND = saved_backend
         for k, v in saved.items():
             setattr(pm, k, v)
     assert set(res_gg.timing) == set(res_ref.timing) == {"graph_build", "data_prep", "gcn_inference", "grabcut",
@@ -998,3 +1002,70 @@ def test_compute_auto_prior_reference_signature(gg):
             np.testing.assert_allclose(got, want, rtol=FEAT_RTOL, atol=FEAT_ATOL)
         via_image = gg.compute_auto_prior(seg, image=np.ascontiguousarray(img))
         np.testing.assert_allclose(via_image, graph_port.auto_prior(seg, lab), rtol=FEAT_RTOL, atol=FEAT_ATOL)
+
+
+def test_slic_quality_vs_oracle(gg):
+    """GPU SLIC (gg_slic: the reference's skimage.segmentation.slic call restated, graph_builder.py:
+    177-188) against the numpy restatement of scikit-image's algorithm (oracle/slic_port.py).
+    Label-for-label parity with scikit-image is unpinned (no build of it can run here), so the gate
+    is (a) the invariants the reference tests -- labels contiguous 0..N-1, every label used
+    (tests/test.py:112-117) -- plus 4-connected regions of at least half a nominal superpixel, and
+    (b) segmentation quality on the generator's ground-truth masks: boundary recall and
+    under-segmentation error no worse than the oracle's by more than a small margin."""
+    from scipy import ndimage as ndi
+    from gcn_grabcut_b200.synthetic import geometric_sample
+    from oracle import graph_port, slic_port
+    cases = [(160, 192, 48, 3), (200, 264, 120, 7), (320, 480, 300, 1), (320, 480, 300, 2)]
+    br_g, br_o, ue_g, ue_o = [], [], [], []
+    for (H, W, nseg, seed) in cases:
+        img, mask = geometric_sample(H, W, seed)
+        cfg = gg.SuperpixelGraphConfig(n_segments=nseg)
+        lab, cnt = gg.slic_labels(img[None], cfg, return_counts=True)
+        lab, n = lab[0], int(cnt[0])
+        assert lab.dtype == np.int32 and lab.shape == (H, W)
+        assert lab.min() == 0 and lab.max() == n - 1 and len(np.unique(lab)) == n, "labels must be 0..N-1, all used"
+        sy, ty, sx, tx = slic_port.regular_grid_2d(H, W, nseg)
+        nominal = len(range(sy, H, ty)) * len(range(sx, W, tx))
+        assert 0.8 * nominal <= n <= 1.3 * nominal, (n, nominal)
+        # every label is one 4-connected region; none is smaller than min_size (the first may be)
+        sizes = np.bincount(lab.ravel())
+        min_size = int(0.5 * H * W / nominal)
+        assert (sizes[1:] >= min_size).all(), (sizes.min(), min_size)
+        comp = 0
+        for v in range(n):
+            comp += ndi.label(lab == v)[1]
+        assert comp == n, f"{comp} connected components for {n} labels"
+        oracle = slic_port.slic(graph_port.pixel_planes(img)["lab"], nseg)
+        br_g.append(slic_port.boundary_recall(lab, mask)); br_o.append(slic_port.boundary_recall(oracle, mask))
+        ue_g.append(slic_port.undersegmentation_error(lab, mask)); ue_o.append(slic_port.undersegmentation_error(oracle, mask))
+        same = float(np.mean(slic_port.boundary_map(lab) == slic_port.boundary_map(oracle)))
+        print(f"{H}x{W} n={nseg}: GPU N={n} oracle N={int(oracle.max()) + 1}; boundary recall {br_g[-1]:.3f} vs "
+              f"{br_o[-1]:.3f}; under-segmentation {ue_g[-1]:.5f} vs {ue_o[-1]:.5f}; boundary maps agree on {same:.3f}")
+    assert np.mean(br_g) >= np.mean(br_o) - 0.03
+    assert np.mean(ue_g) <= np.mean(ue_o) + 0.002
+
+
+def test_slic_in_the_path(gg):
+    """Superpixels produced on the device inside the whole-path entry points (only the images cross
+    PCIe) == gg_slic followed by the path on those label maps; GraphBuilder(image, cfg).build()
+    works without a label map; determinism (the centre sums are integers)."""
+    from gcn_grabcut_b200.synthetic import geometric_sample
+    from oracle import model_port
+    B, H, W, nseg = 6, 160, 192, 48
+    imgs = np.stack([geometric_sample(H, W, 40 + i)[0] for i in range(B)])
+    cfg = gg.SuperpixelGraphConfig(n_segments=nseg)
+    labs, cnt = gg.slic_labels(imgs, cfg, return_counts=True)
+    labs2 = gg.slic_labels(imgs, cfg)
+    assert np.array_equal(labs, labs2), "SLIC must be deterministic"
+    state = model_port.random_state_dict(32, 2, seed=3)
+    cap = int(cnt.max()) + 8
+    with_labels = gg.TrimapPath(state, cfg, node_cap=cap)(imgs, labs)
+    path = gg.TrimapPath(state, cfg, node_cap=cap, device_slic=True, chunk=4)
+    tri, nn, ne = path(imgs, return_counts=True)
+    assert np.array_equal(nn, cnt) and np.array_equal(tri, with_labels)
+    td = path.run_device(torch.from_numpy(imgs).cuda(), check=True)
+    assert np.array_equal(td.cpu().numpy(), with_labels)
+    g = gg.GraphBuilder(imgs[0], cfg).build()
+    assert g.n_nodes == int(cnt[0]) and np.array_equal(g.segments, labs[0])
+    ref = gg.GraphBuilder(imgs[0], cfg, segments=labs[0]).build()
+    assert np.array_equal(g.edge_index, ref.edge_index) and np.array_equal(g.node_features, ref.node_features)
