@@ -228,7 +228,7 @@ static int run_path_multi(gg_context* ctx, Arena& ar, const uint8_t* bgr, const 
     sub.base = ar.base + ar.off + (size_t)s * slice;
     sub.cap = slice;
     ctx->status_word = ctx->d_status + 8 + s;
-    rc = run_path(ctx, sub, bgr + (size_t)b0 * npx * 3, labels + (size_t)b0 * npx, nb, H, W, pc,
+    rc = run_path(ctx, sub, bgr + (size_t)b0 * npx * 3, labels ? labels + (size_t)b0 * npx : nullptr, nb, H, W, pc,
                   trimap + (size_t)b0 * npx, nullptr, nullptr, n_nodes_out ? n_nodes_out + b0 : nullptr,
                   n_edges_out ? n_edges_out + b0 : nullptr, ss, ctx->ev[17 + s]);
     if (sub.overflowed) ar.overflowed = true;

@@ -24,6 +24,7 @@ ap.add_argument("--layers", type=int, default=6)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--top", type=int, default=12)
 ap.add_argument("--tag", default="")
+ap.add_argument("--slic", action="store_true", help="label maps from the device SLIC (images only in)")
 a = ap.parse_args()
 
 n_unique = min(a.batch, 32)                                     # the cost does not depend on the content
@@ -33,8 +34,9 @@ reps = (a.batch + n_unique - 1) // n_unique
 imgs = np.concatenate([imgs] * reps)[:a.batch]
 labs = np.concatenate([labs] * reps)[:a.batch]
 path = gg.TrimapPath(random_state_dict(a.hidden, a.layers, seed=0),
-                     gg.SuperpixelGraphConfig(n_segments=a.segments, n_nonlocal=a.k), node_cap=int(labs.max()) + 1)
-img_d, lab_d = torch.from_numpy(imgs).cuda(), torch.from_numpy(labs).cuda()
+                     gg.SuperpixelGraphConfig(n_segments=a.segments, n_nonlocal=a.k),
+                     node_cap=int(labs.max()) + 1 + (a.segments // 4 if a.slic else 0), device_slic=a.slic)
+img_d, lab_d = torch.from_numpy(imgs).cuda(), (None if a.slic else torch.from_numpy(labs).cuda())
 tri_d = torch.empty(imgs.shape[:3], dtype=torch.uint8, device="cuda")
 for _ in range(3):
     path.run_device(img_d, lab_d, tri_d)
