@@ -932,7 +932,11 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   GG_TRY(gemm(ctx, st, GEMM_GATE, ctxv, wb + nw.eg_w, wb + nw.eg_b, gate, n_nodes_p, node_cap, D, c, 2, 0));
 
   // ---- residual GCN blocks
-  const bool fused = graph_node_cap > 0 && n > 0 && gcn_fused_supported(ctx, graph_node_cap, graph_edge_cap);
+  // the per-graph kernel wins when there are enough graphs to fill the SMs (one CTA per graph); for a handful
+  // of graphs the layer-wise kernels, which spread every graph over many SMs, have the shorter latency
+  static const int fused_min_graphs = getenv("GG_FUSED_MIN_GRAPHS") ? atoi(getenv("GG_FUSED_MIN_GRAPHS")) : 24;
+  const bool fused = graph_node_cap > 0 && n > 0 && (n_graphs >= fused_min_graphs || ctx->gcn_fused == 2) &&
+                     gcn_fused_supported(ctx, graph_node_cap, graph_edge_cap);
   if (fused)
     GG_TRY(gcn_layers_fused(ctx, st, h, z, gate, row_stats, dinv, rowptr, src, graph_off, n_graphs, graph_node_cap,
                             graph_edge_cap));

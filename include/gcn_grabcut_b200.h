@@ -70,8 +70,9 @@ void gg_destroy(gg_handle h);
  * "n_sub": number of concurrent sub-batches (internal streams) the whole-path entry points
  * cut a batch into, 1..4 (default 2; env GG_SUBBATCH).
  * "gcn_fused": 1 = run the residual GCN blocks as one per-graph kernel (x' on chip) where it
- * applies (hidden 128, graphs of <= 384 regions, tcgen05 transforms; default), 0 = layer-wise
- * kernels (validation of the fused kernel; env GG_GCN_UNFUSED). */
+ * applies (hidden 128, graphs of <= 384 regions, tcgen05 transforms) and the batch has at least 24
+ * graphs (default), 2 = also for smaller batches, 0 = layer-wise kernels (validation of the fused
+ * kernel; env GG_GCN_UNFUSED). */
 int gg_set_option(gg_handle h, const char* key, int value);
 
 /* Device-side status word of the device-pointer entry points: bit0 label / edge index out of

@@ -881,7 +881,7 @@ def test_fused_gcn_blocks_vs_layerwise_and_oracle(gg):
         ea = torch.rand(ei.size(1), 5, generator=gen)
         data = gg.Data(x=x, edge_index=ei, edge_attr=ea).to("cuda")
         out = {}
-        for fused in (1, 0):
+        for fused in (2, 0):
             h.set_option("gcn_fused", fused)
             try:
                 l0 = h.launches()
@@ -890,18 +890,18 @@ def test_fused_gcn_blocks_vs_layerwise_and_oracle(gg):
             finally:
                 h.set_option("gcn_fused", 1)
         ref = model_port.resgcn_forward(state, x, ei, ea, None)
-        assert out[1, "launches"] < out[0, "launches"], "the fused kernel did not run"
-        print(f"N={N}: fused-layerwise {float((out[1] - out[0]).abs().max()):.3g}, fused-oracle "
-              f"{float((out[1] - ref).abs().max()):.3g}; launches {out[1, 'launches']} vs {out[0, 'launches']}")
-        assert torch.allclose(out[1], out[0], atol=5e-5, rtol=1e-5)
-        assert torch.allclose(out[1], ref, atol=POST_ATOL, rtol=1e-4)
+        assert out[2, "launches"] < out[0, "launches"], "the fused kernel did not run"
+        print(f"N={N}: fused-layerwise {float((out[2] - out[0]).abs().max()):.3g}, fused-oracle "
+              f"{float((out[2] - ref).abs().max()):.3g}; launches {out[2, 'launches']} vs {out[0, 'launches']}")
+        assert torch.allclose(out[2], out[0], atol=5e-5, rtol=1e-5)
+        assert torch.allclose(out[2], ref, atol=POST_ATOL, rtol=1e-4)
     # batched path: posteriors of every image
     imgs, labs = make_batch(12, 160, 192, 60, seed0=33)
     cap = int(labs.max()) + 1
     path = gg.TrimapPath(state, gg.SuperpixelGraphConfig(n_segments=60), node_cap=cap)
     it, lt = torch.from_numpy(imgs).cuda(), torch.from_numpy(labs).cuda()
     res = {}
-    for fused in (1, 0):
+    for fused in (2, 0):
         h.set_option("gcn_fused", fused)
         try:
             probs = torch.zeros(12 * cap, 3, device="cuda")
@@ -910,10 +910,10 @@ def test_fused_gcn_blocks_vs_layerwise_and_oracle(gg):
             res[fused] = (tri.cpu().numpy(), probs.cpu().numpy(), noff.cpu().numpy())
         finally:
             h.set_option("gcn_fused", 1)
-    assert np.array_equal(res[1][2], res[0][2])
-    nt = int(res[1][2][-1])
-    assert np.abs(res[1][1][:nt] - res[0][1][:nt]).max() < 2e-5
-    assert np.mean(res[1][0] != res[0][0]) < 1e-4
+    assert np.array_equal(res[2][2], res[0][2])
+    nt = int(res[2][2][-1])
+    assert np.abs(res[2][1][:nt] - res[0][1][:nt]).max() < 2e-5
+    assert np.mean(res[2][0] != res[0][0]) < 1e-4
 
 
 def test_clean_mask_and_grabcut_guards_vs_reference_golden(gg):
