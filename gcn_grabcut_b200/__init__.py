@@ -15,7 +15,7 @@ from .graph_builder import (  # noqa: F401
 
 try:  # torch-dependent names (same guard as the reference's __init__)
     from .model import (  # noqa: F401
-        ResGCNNet, build_model, Data, _probs_to_trimap, probs_to_node_trimap, project_to_pixels,
+        ResGCNNet, GCNTrimapNet, GATTrimapNet, build_model, Data, _probs_to_trimap, probs_to_node_trimap, project_to_pixels,
         TRIMAP_BG, TRIMAP_FG, TRIMAP_PROB_BG, TRIMAP_PROB_FG, CLASS_BG, CLASS_UNK, CLASS_FG,
     )
     from .pipeline import (guided_filter, refine_trimap, seed_from_prior, TrimapPath, PendingTrimaps,  # noqa: F401

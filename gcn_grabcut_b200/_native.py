@@ -58,6 +58,11 @@ class ResGCNWeights(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("n_layers", C.c_int32)] + [(n, C.c_void_p) for n in _WEIGHT_PTRS]
 
 
+class VariantWeights(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32), ("n_heads", C.c_int32),
+                ("n_tensors", C.c_int32), ("reserved", C.c_int32), ("tensors", C.c_void_p), ("numel", C.c_void_p)]
+
+
 class PathConfig(C.Structure):
     _fields_ = [("graph", GraphConfig), ("radius", C.c_int32), ("eps", C.c_float),
                 ("thr_fg", C.c_float), ("thr_bg", C.c_float), ("edge_aware", C.c_int32),
@@ -93,7 +98,7 @@ _KEY_TO_FIELD = {
 EXPORTED_SYMBOLS = (
     "gg_abi_version", "gg_last_error", "gg_create", "gg_destroy", "gg_set_option",
     "gg_check_device_status", "gg_build_graphs", "gg_pixel_planes", "gg_load_weights",
-    "gg_coo_to_csr", "gg_resgcn_forward", "gg_refine_trimap", "gg_project_trimap",
+    "gg_coo_to_csr", "gg_resgcn_forward", "gg_variant_load_weights", "gg_variant_forward", "gg_refine_trimap", "gg_project_trimap",
     "gg_guided_filter", "gg_region_labels", "gg_seed_from_prior", "gg_grabcut_guards", "gg_clean_masks", "gg_auto_prior", "gg_slic", "gg_trimap_path_host", "gg_trimap_path_host_submit", "gg_trimap_path_host_wait",
     "gg_trimap_path_device", "gg_kernel_launch_count",
     "gg_profile_enable", "gg_profile_report", "gg_selftest_math")
@@ -130,6 +135,10 @@ def lib() -> C.CDLL:
             L.gg_resgcn_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
+            L.gg_variant_load_weights.argtypes = [C.c_void_p, C.POINTER(VariantWeights)]
+            L.gg_variant_forward.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
             L.gg_refine_trimap.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                            C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -285,3 +294,24 @@ def load_state_dict(h: Handle, state: dict) -> None:
         setattr(w, fld, C.cast(tbl, C.c_void_p))
     check(lib().gg_load_weights(h.ptr, C.byref(w)))
     del keep
+
+
+def load_variant_state_dict(h: Handle, variant: int, hidden: int, n_layers: int, n_heads: int, state: dict,
+                            keys) -> None:
+    """gg_variant_load_weights from a reference-layout state-dict; ``keys`` lists the tensors in the
+    order include/gcn_grabcut_b200.h documents for the variant."""
+    missing = [k for k in keys if k not in state]
+    if missing:
+        raise KeyError(f"state_dict is missing keys: {missing[:6]}{'…' if len(missing) > 6 else ''}")
+    arrs = []
+    for k in keys:
+        v = state[k]
+        if hasattr(v, "detach"):
+            v = v.detach().to("cpu").float().numpy()
+        arrs.append(np.ascontiguousarray(np.asarray(v, dtype=np.float32)))
+    tbl = (C.c_void_p * len(arrs))(*[a.ctypes.data_as(C.c_void_p) for a in arrs])
+    numel = (C.c_int64 * len(arrs))(*[int(a.size) for a in arrs])
+    w = VariantWeights(int(variant), int(hidden), int(n_layers), int(n_heads), len(arrs), 0,
+                       C.cast(tbl, C.c_void_p), C.cast(numel, C.c_void_p))
+    check(lib().gg_variant_load_weights(h.ptr, C.byref(w)))
+    del arrs

@@ -34,6 +34,7 @@ SOURCES = {
     "gemm_tc.cu": [],
     "gcn_fused.cu": [],
     "slic.cu": [],
+    "variants.cu": [],
 }
 
 

@@ -10,6 +10,7 @@
 #include "resgcn.cuh"
 #include "slic.cuh"
 #include "trimap.cuh"
+#include "variants.cuh"
 
 namespace gg {
 
@@ -316,6 +317,7 @@ void gg_destroy(gg_handle h) {
   h->host_arena.release();
   if (h->net.blob) cudaFree(h->net.blob);
   if (h->net.tc_blob) cudaFree(h->net.tc_blob);
+  if (h->variant.blob) cudaFree(h->variant.blob);
   if (h->d_status) cudaFree(h->d_status);
   if (h->h_ticket_status) cudaFreeHost(h->h_ticket_status);
   if (h->d_lin) cudaFree(h->d_lin);
@@ -426,6 +428,33 @@ int gg_resgcn_forward(gg_handle h, const float* x_dev, const int32_t* csr_rowptr
                                                 n_graphs == 1 && node_cap_total <= FUSED_MAX_NODES ? (int)node_cap_total : 0,
                                                 n_graphs == 1 && edge_cap_total < (1 << 18) ? (int)edge_cap_total : 0),
                        "gg_resgcn_forward");
+}
+
+int gg_variant_load_weights(gg_handle h, const gg_variant_weights* w) {
+  GG_REQUIRE(h && w, "gg_variant_load_weights: null argument");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  GG_CUDA_OK(cudaDeviceSynchronize());          // queued forwards may still read the old blob
+  return variant_load_weights(h, w);
+}
+
+int gg_variant_forward(gg_handle h, int variant, const float* x_dev, const int32_t* csr_rowptr_dev,
+                       const int32_t* csr_src_dev, const int32_t* csr_eid_dev, const float* edge_attr_dev,
+                       const int64_t* graph_off_dev, int n_graphs, int64_t n_nodes, int64_t n_edges,
+                       float* logits_dev, float* probs_dev, void* stream) {
+  GG_REQUIRE(h && x_dev && csr_rowptr_dev && graph_off_dev, "gg_variant_forward: null argument");
+  GG_REQUIRE(logits_dev || probs_dev, "gg_variant_forward: no output requested");
+  GG_REQUIRE(n_nodes >= 0 && n_edges >= 0 && n_graphs >= 1 && n_nodes < (1ll << 31) / 256 * 8 && n_edges < (1ll << 31) / 256,
+             "gg_variant_forward: bad sizes");
+  GG_REQUIRE(n_edges == 0 || (csr_src_dev && csr_eid_dev && edge_attr_dev), "gg_variant_forward: null edge arrays");
+  GG_CUDA_OK(cudaSetDevice(h->device));
+  if (!h->variant.loaded || h->variant.kind != variant) {
+    set_error("gg_variant_forward: call gg_variant_load_weights for variant %d first", variant);
+    return GG_ERR_STATE;
+  }
+  GG_TRY(h->arena.reserve(variant_workspace_bytes(h->variant, n_nodes, n_edges)));
+  return arena_checked(h->arena, variant_forward(h, h->arena, variant, x_dev, csr_rowptr_dev, csr_src_dev, csr_eid_dev,
+                                                 edge_attr_dev, graph_off_dev, n_graphs, n_nodes, n_edges, logits_dev,
+                                                 probs_dev, (cudaStream_t)stream), "gg_variant_forward");
 }
 
 int gg_refine_trimap(gg_handle h, const uint8_t* bgr_dev, const int32_t* labels_dev, const float* probs_dev,

@@ -93,6 +93,15 @@ struct NetWeights {
   std::vector<size_t> tc_off;  // byte offset of each GEMM's operand image (by GEMM id), -1 = none
 };
 
+// GCNTrimapNet / GATTrimapNet parameters (variants.cu): one blob, tensors in the order of gg_variant_weights
+struct VariantWeights {
+  bool loaded = false;
+  int kind = 0, D = 0, n_layers = 0, heads = 0;
+  float* blob = nullptr;
+  size_t blob_floats = 0;
+  std::vector<size_t> off;
+};
+
 }  // namespace gg
 
 struct gg_context {
@@ -102,6 +111,7 @@ struct gg_context {
   gg::Arena arena;        // device-pointer entry points (caller's stream)
   gg::Arena host_arena;   // gg_trimap_path_host chunk workspaces
   gg::NetWeights net;
+  gg::VariantWeights variant;
   int* d_status = nullptr;   // [16] words: 0 last call, 1 sticky (host path), 8.. per sub-batch
   int* status_word = nullptr;  // word the kernels being enqueued right now report into
   double* d_lin = nullptr;   // sRGB linearisation table (256 doubles), built in gg_create

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GG_ABI_VERSION 3
+#define GG_ABI_VERSION 4
 
 #define GG_N_IMAGE_FEATS 16 /* graph_builder.py:73 */
 #define GG_N_PRIOR_FEATS 3  /* graph_builder.py:74 */
@@ -213,6 +213,48 @@ int gg_resgcn_forward(gg_handle h, const float* x_dev, const int32_t* csr_rowptr
                       const float* edge_attr_dev, const int64_t* graph_off_dev, int n_graphs,
                       int64_t node_cap_total, int64_t edge_cap_total, float* logits_dev,
                       float* probs_dev, void* stream);
+
+/* ------------------------------------------------------------------ network variants
+ * build_model("gcn" | "gat") of the reference (model.py:593-620): GCNTrimapNet (model.py:239-316:
+ * ResGCNBlock = GCNConv + BatchNorm + ReLU + identity skip + EdgeInjectionLayer, concat head) and
+ * GATTrimapNet (model.py:323-414: GATv2Conv with edge features + LayerNorm + GELU +
+ * EdgeInjectionLayer, skip projection, GlobalContextModule, head), eval mode.
+ * tensors: HOST float32 arrays in the reference's state-dict layout, in this order
+ * (BatchNorm = weight, bias, running_mean, running_var; D = hidden, n = n_layers, H = n_heads):
+ *   gcn: in_norm.norm BatchNorm[19] | input_proj.0.{weight [D,19], bias} | input_proj.1 BatchNorm[D] |
+ *        per block: conv.bias, conv.lin.weight [D,D], bn BatchNorm[D], edge_inject.proj.0.{weight [D,5], bias},
+ *        edge_inject.proj.2.{weight [D,D], bias} | head.0.{weight [D,(n+1)D], bias} | head.1 BatchNorm[D] |
+ *        head.4.{weight [D/2,D], bias} | head.6.{weight [3,D/2], bias}                         (20 + 10 n tensors)
+ *   gat: in_norm.norm BatchNorm[19] | input_proj.0.{weight, bias} | input_proj.1.{weight, bias} (LayerNorm) |
+ *        per layer: convs.att [1,H,D/H], convs.bias, convs.lin_l.{weight [D,D], bias}, convs.lin_r.{weight, bias},
+ *        convs.lin_edge.weight [D,5], lns.{weight, bias}, edge_gates.proj.0.{weight [D,5], bias},
+ *        edge_gates.proj.2.{weight [D,D], bias} | skip_proj.weight [D,D] | ctx.attn.{weight [1,D], bias [1]} |
+ *        ctx.compress.{weight [D/2,D], bias} | ctx.expand.{weight [D,D/2], bias} | head.0.{weight [D,D], bias} |
+ *        head.3.{weight [3,D], bias}                                                            (19 + 13 n tensors)
+ * hidden: multiple of 32 in [32, 256]; n_heads must divide 32.  A handle holds one variant at a time,
+ * next to the ResGCNNet weights of gg_load_weights. */
+enum { GG_VARIANT_GCN = 1, GG_VARIANT_GAT = 2 };
+
+typedef struct gg_variant_weights {
+  int32_t variant;   /* GG_VARIANT_GCN | GG_VARIANT_GAT */
+  int32_t hidden;
+  int32_t n_layers;
+  int32_t n_heads;   /* gat only */
+  int32_t n_tensors;
+  int32_t reserved;
+  const float* const* tensors; /* [n_tensors] host pointers */
+  const int64_t* numel;        /* [n_tensors] element counts (validated against the layout above) */
+} gg_variant_weights;
+
+int gg_variant_load_weights(gg_handle h, const gg_variant_weights* w);
+
+/* forward(data) / predict_probs of the loaded variant over a batch of graphs: same graph arguments as
+ * gg_resgcn_forward (dst-sorted CSR from gg_coo_to_csr or gg_build_graphs), but n_nodes / n_edges are
+ * the exact row counts.  logits_dev / probs_dev: [n_nodes,3]; either may be NULL. */
+int gg_variant_forward(gg_handle h, int variant, const float* x_dev, const int32_t* csr_rowptr_dev,
+                       const int32_t* csr_src_dev, const int32_t* csr_eid_dev, const float* edge_attr_dev,
+                       const int64_t* graph_off_dev, int n_graphs, int64_t n_nodes, int64_t n_edges,
+                       float* logits_dev, float* probs_dev, void* stream);
 
 /* ------------------------------------------------------------------ region -> pixel projection
  * gg_refine_trimap replaces refine_trimap (pipeline.py:103-146): guided filter of the BG

@@ -168,3 +168,176 @@ def probs_to_trimap(probs: np.ndarray, seg: np.ndarray, thr_fg: float, thr_bg: f
     if lab.shape[0] < need:
         lab = np.concatenate([lab, np.full(need - lab.shape[0], TRIMAP_PROB_BG, dtype=np.uint8)])
     return lab[seg].astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------- GCNTrimapNet (baseline variant)
+def _bn_eval(x, state, prefix):
+    """BatchNorm1d in eval mode (running statistics, eps 1e-5)."""
+    return (x - state[prefix + ".running_mean"]) / torch.sqrt(state[prefix + ".running_var"] + 1e-5) * \
+        state[prefix + ".weight"] + state[prefix + ".bias"]
+
+
+def gcn_trimap_dims(state: Dict[str, torch.Tensor]):
+    D = int(state["input_proj.0.weight"].shape[0])
+    n = sum(1 for k in state if k.startswith("blocks.") and k.endswith(".conv.bias"))
+    return D, n
+
+
+@torch.no_grad()
+def gcn_trimap_forward(state: Dict[str, torch.Tensor], x: torch.Tensor, edge_index: torch.Tensor,
+                       edge_attr: torch.Tensor) -> torch.Tensor:
+    """GCNTrimapNet.forward in eval mode (model.py:290-304) with ResGCNBlock (:216-233) and
+    EdgeInjectionLayer (:142-162): logits (N, 3)."""
+    D, n = gcn_trimap_dims(state)
+    x, edge_attr = x.float(), edge_attr.float()
+    N = x.size(0)
+    h = F.relu(_bn_eval(F.linear(_bn_eval(x, state, "in_norm.norm"), state["input_proj.0.weight"],
+                                 state["input_proj.0.bias"]), state, "input_proj.1"))
+    all_h = [h]
+    for i in range(n):
+        p = f"blocks.{i}."
+        c = _gcn_conv(h, edge_index, state[p + "conv.lin.weight"], state[p + "conv.bias"])
+        c = F.relu(_bn_eval(c, state, p + "bn")) + h                       # skip = Identity (in_dim == out_dim)
+        e = torch.sigmoid(F.linear(F.relu(F.linear(edge_attr, state[p + "edge_inject.proj.0.weight"],
+                                                   state[p + "edge_inject.proj.0.bias"])),
+                                   state[p + "edge_inject.proj.2.weight"], state[p + "edge_inject.proj.2.bias"]))
+        h = c * _scatter_mean(e, edge_index[1], N)
+        all_h.append(h)
+    t = F.relu(_bn_eval(F.linear(torch.cat(all_h, -1), state["head.0.weight"], state["head.0.bias"]), state, "head.1"))
+    t = F.relu(F.linear(t, state["head.4.weight"], state["head.4.bias"]))
+    return F.linear(t, state["head.6.weight"], state["head.6.bias"])
+
+
+def random_gcn_trimap_state(hidden: int = 128, n_layers: int = 6, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded random GCNTrimapNet state-dict with the reference's keys (non-trivial norms / biases)."""
+    g = torch.Generator().manual_seed(seed)
+    D = hidden
+
+    def lin(o, i):
+        return torch.randn(o, i, generator=g) * (2.0 / i) ** 0.5
+
+    def vec(n, scale=0.1, shift=0.0):
+        return torch.randn(n, generator=g) * scale + shift
+
+    def bn(prefix, n, s):
+        s[prefix + ".weight"], s[prefix + ".bias"] = vec(n, 0.1, 1.0), vec(n)
+        s[prefix + ".running_mean"], s[prefix + ".running_var"] = vec(n, 0.2, 0.1), vec(n, 0.1, 0.6).abs() + 0.05
+        s[prefix + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    s: Dict[str, torch.Tensor] = {}
+    bn("in_norm.norm", 19, s)
+    s["input_proj.0.weight"], s["input_proj.0.bias"] = lin(D, 19), vec(D)
+    bn("input_proj.1", D, s)
+    for i in range(n_layers):
+        p = f"blocks.{i}."
+        s[p + "conv.bias"] = vec(D)
+        s[p + "conv.lin.weight"] = (torch.rand(D, D, generator=g) * 2 - 1) * (6.0 / (2 * D)) ** 0.5
+        bn(p + "bn", D, s)
+        s[p + "edge_inject.proj.0.weight"], s[p + "edge_inject.proj.0.bias"] = lin(D, 5), vec(D)
+        s[p + "edge_inject.proj.2.weight"], s[p + "edge_inject.proj.2.bias"] = lin(D, D), vec(D)
+    s["head.0.weight"], s["head.0.bias"] = lin(D, D * (n_layers + 1)), vec(D)
+    bn("head.1", D, s)
+    s["head.4.weight"], s["head.4.bias"] = lin(D // 2, D), vec(D // 2)
+    s["head.6.weight"], s["head.6.bias"] = lin(3, D // 2), vec(3)
+    return {k: v.contiguous() for k, v in s.items()}
+
+
+# ----------------------------------------------------------------------------- GATTrimapNet (attention variant)
+def _gatv2_conv(x, edge_index, edge_attr, state, p, heads):
+    """PyG GATv2Conv as the reference configures it (model.py:360-366; thirdparty.GATv2Conv)."""
+    n = x.size(0)
+    xl = F.linear(x, state[p + "lin_l.weight"], state[p + "lin_l.bias"])
+    xr = F.linear(x, state[p + "lin_r.weight"], state[p + "lin_r.bias"])
+    D = xl.size(1)
+    C_ = D // heads
+    src, dst = edge_index[0], edge_index[1]
+    keep = src != dst
+    src, dst, ea = src[keep], dst[keep], edge_attr[keep]
+    loop_attr = _scatter_mean(ea, dst, n)                                          # fill_value="mean"
+    loop = torch.arange(n, dtype=src.dtype)
+    src, dst, ea = torch.cat([src, loop]), torch.cat([dst, loop]), torch.cat([ea, loop_attr])
+    m = F.leaky_relu(xl[src] + xr[dst] + F.linear(ea, state[p + "lin_edge.weight"]), 0.2).view(-1, heads, C_)
+    score = (m * state[p + "att"].view(1, heads, C_)).sum(-1)
+    out = torch.zeros(n, heads, C_)
+    for i in range(n):                                                              # softmax over the edges entering i
+        sel = (dst == i).nonzero().flatten()
+        s = score[sel]
+        e = torch.exp(s - s.max(0, keepdim=True).values)
+        a = e / (e.sum(0, keepdim=True) + 1e-16)
+        out[i] = (xl[src[sel]].view(-1, heads, C_) * a.unsqueeze(-1)).sum(0)
+    return out.view(n, D) + state[p + "bias"]
+
+
+def gat_trimap_dims(state: Dict[str, torch.Tensor]):
+    D = int(state["input_proj.0.weight"].shape[0])
+    n = sum(1 for k in state if k.startswith("convs.") and k.endswith(".att"))
+    heads = int(state["convs.0.att"].shape[1])
+    return D, n, heads
+
+
+@torch.no_grad()
+def gat_trimap_forward(state: Dict[str, torch.Tensor], x: torch.Tensor, edge_index: torch.Tensor,
+                       edge_attr: torch.Tensor, batch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GATTrimapNet.forward in eval mode (model.py:384-404): logits (N, 3)."""
+    D, n, heads = gat_trimap_dims(state)
+    x, edge_attr = x.float(), edge_attr.float()
+    N = x.size(0)
+    h = F.gelu(F.layer_norm(F.linear(_bn_eval(x, state, "in_norm.norm"), state["input_proj.0.weight"],
+                                     state["input_proj.0.bias"]), (D,), state["input_proj.1.weight"],
+                            state["input_proj.1.bias"], 1e-5))
+    skip = F.linear(h, state["skip_proj.weight"])
+    for i in range(n):
+        c = _gatv2_conv(h, edge_index, edge_attr, state, f"convs.{i}.", heads)
+        c = F.gelu(F.layer_norm(c, (D,), state[f"lns.{i}.weight"], state[f"lns.{i}.bias"], 1e-5))
+        p = f"edge_gates.{i}."
+        e = torch.sigmoid(F.linear(F.relu(F.linear(edge_attr, state[p + "proj.0.weight"], state[p + "proj.0.bias"])),
+                                   state[p + "proj.2.weight"], state[p + "proj.2.bias"]))
+        h = c * _scatter_mean(e, edge_index[1], N)
+    h = h + skip
+    w = _graph_softmax(F.linear(h, state["ctx.attn.weight"], state["ctx.attn.bias"]), batch)   # model.py:176-188
+    if batch is None:
+        g = (w * h).sum(0, keepdim=True).expand(N, -1)
+    else:
+        g = torch.zeros(int(batch.max()) + 1, D).index_add_(0, batch, w * h)[batch]
+    g = torch.sigmoid(F.linear(F.relu(F.linear(g, state["ctx.compress.weight"], state["ctx.compress.bias"])),
+                               state["ctx.expand.weight"], state["ctx.expand.bias"]))
+    h = h * g
+    t = F.gelu(F.linear(h, state["head.0.weight"], state["head.0.bias"]))
+    return F.linear(t, state["head.3.weight"], state["head.3.bias"])
+
+
+def random_gat_trimap_state(hidden: int = 128, n_heads: int = 8, n_layers: int = 5, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded random GATTrimapNet state-dict with the reference's keys."""
+    g = torch.Generator().manual_seed(seed)
+    D = hidden
+
+    def lin(o, i):
+        return torch.randn(o, i, generator=g) * (2.0 / i) ** 0.5
+
+    def vec(n, scale=0.1, shift=0.0):
+        return torch.randn(n, generator=g) * scale + shift
+
+    s: Dict[str, torch.Tensor] = {}
+    s["in_norm.norm.weight"], s["in_norm.norm.bias"] = vec(19, 0.1, 1.0), vec(19)
+    s["in_norm.norm.running_mean"], s["in_norm.norm.running_var"] = vec(19, 0.2, 0.1), vec(19, 0.1, 0.6).abs() + 0.05
+    s["in_norm.norm.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    s["input_proj.0.weight"], s["input_proj.0.bias"] = lin(D, 19), vec(D)
+    s["input_proj.1.weight"], s["input_proj.1.bias"] = vec(D, 0.1, 1.0), vec(D)
+    for i in range(n_layers):
+        p = f"convs.{i}."
+        s[p + "att"] = torch.randn(1, n_heads, D // n_heads, generator=g) * 0.5
+        s[p + "bias"] = vec(D)
+        s[p + "lin_l.weight"], s[p + "lin_l.bias"] = lin(D, D) * 0.7, vec(D)
+        s[p + "lin_r.weight"], s[p + "lin_r.bias"] = lin(D, D) * 0.7, vec(D)
+        s[p + "lin_edge.weight"] = lin(D, 5)
+        s[f"lns.{i}.weight"], s[f"lns.{i}.bias"] = vec(D, 0.1, 1.0), vec(D)
+        q = f"edge_gates.{i}.proj."
+        s[q + "0.weight"], s[q + "0.bias"] = lin(D, 5), vec(D)
+        s[q + "2.weight"], s[q + "2.bias"] = lin(D, D), vec(D)
+    s["skip_proj.weight"] = lin(D, D) * 0.5
+    s["ctx.attn.weight"], s["ctx.attn.bias"] = lin(1, D), vec(1)
+    s["ctx.compress.weight"], s["ctx.compress.bias"] = lin(D // 2, D), vec(D // 2)
+    s["ctx.expand.weight"], s["ctx.expand.bias"] = lin(D, D // 2), vec(D)
+    s["head.0.weight"], s["head.0.bias"] = lin(D, D), vec(D)
+    s["head.3.weight"], s["head.3.bias"] = lin(3, D), vec(3)
+    return {k: v.contiguous() for k, v in s.items()}

@@ -227,13 +227,59 @@ if _TORCH:
             return self.lin_l(agg) + self.lin_r(x)
 
     class GATv2Conv(nn.Module):
-        """Constructible stub: the GAT variant is outside the trimap path."""
+        """
+        PyG GATv2Conv (Brody et al., "How attentive are graph attention networks?") as the reference
+        constructs it (model.py:360-366): heads=H, concat=True, edge_dim given, share_weights=False,
+        negative_slope=0.2, add_self_loops=True, fill_value="mean", bias=True, no residual.
+        Parameters: lin_l / lin_r (PyG Linear with bias, glorot), lin_edge (no bias), att [1,H,C],
+        bias [H*C].  forward: existing self loops are removed and one loop per node is appended
+        whose edge attribute is the mean of the attributes of the node's incoming edges (0 if none);
+        for an edge j -> i:  m = lin_l(x)_j + lin_r(x)_i + lin_edge(a_ji);
+        score_h = sum_c att[h,c] * leaky_relu(m[h,c], 0.2);  alpha = softmax over the edges entering i
+        (exp(s - max) / (sum + 1e-16));  out_i = sum_j alpha_ji * lin_l(x)_j, heads concatenated, + bias.
+        Attention dropout is inactive in eval mode.
+        """
 
-        def __init__(self, *args, **kwargs):
+        def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
+                     negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True,
+                     edge_dim: Optional[int] = None, fill_value="mean", bias: bool = True,
+                     share_weights: bool = False, **kwargs):
             super().__init__()
+            if not concat or share_weights or edge_dim is None or not add_self_loops or fill_value != "mean":
+                raise NotImplementedError("only the configuration the reference uses is restated")
+            self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+            self.negative_slope, self.dropout = negative_slope, dropout
+            self.lin_l = PyGLinear(in_channels, heads * out_channels, bias=True, weight_initializer="glorot")
+            self.lin_r = PyGLinear(in_channels, heads * out_channels, bias=True, weight_initializer="glorot")
+            self.lin_edge = PyGLinear(edge_dim, heads * out_channels, bias=False, weight_initializer="glorot")
+            self.att = nn.Parameter(torch.empty(1, heads, out_channels))
+            self.bias = nn.Parameter(torch.zeros(heads * out_channels))
+            a = math.sqrt(6.0 / (heads + out_channels))
+            nn.init.uniform_(self.att, -a, a)
 
-        def forward(self, *args, **kwargs):
-            raise NotImplementedError("GATv2Conv is not restated (out of the hot path)")
+        def forward(self, x, edge_index, edge_attr):
+            n, H, Cc = x.size(0), self.heads, self.out_channels
+            x_l = self.lin_l(x).view(n, H, Cc)
+            x_r = self.lin_r(x).view(n, H, Cc)
+            src, dst = edge_index[0], edge_index[1]
+            keep = src != dst
+            src, dst, ea = src[keep], dst[keep], edge_attr[keep]
+            loop_attr = torch.zeros(n, ea.size(1), device=x.device, dtype=ea.dtype).index_add_(0, dst, ea)
+            cnt = torch.zeros(n, device=x.device, dtype=ea.dtype).scatter_add_(
+                0, dst, torch.ones(dst.numel(), device=x.device, dtype=ea.dtype))
+            loop_attr = loop_attr / cnt.clamp(min=1).unsqueeze(1)
+            loop = torch.arange(n, device=x.device, dtype=src.dtype)
+            src, dst, ea = torch.cat([src, loop]), torch.cat([dst, loop]), torch.cat([ea, loop_attr])
+            m = x_l[src] + x_r[dst] + self.lin_edge(ea).view(-1, H, Cc)
+            m = torch.nn.functional.leaky_relu(m, self.negative_slope)
+            score = (m * self.att).sum(-1)                                           # [E', H]
+            peak = torch.full((n, H), float("-inf"), device=x.device, dtype=score.dtype)
+            peak = peak.scatter_reduce(0, dst.unsqueeze(1).expand(-1, H), score, "amax", include_self=True)
+            ex = torch.exp(score - peak[dst])
+            tot = torch.zeros(n, H, device=x.device, dtype=score.dtype).index_add_(0, dst, ex)
+            alpha = ex / (tot[dst] + 1e-16)
+            out = torch.zeros(n, H, Cc, device=x.device, dtype=x.dtype).index_add_(0, dst, x_l[src] * alpha.unsqueeze(-1))
+            return out.view(n, H * Cc) + self.bias
 
     class Data:
         """torch_geometric.data.Data: attribute bag with .to(); absent attrs read as None."""

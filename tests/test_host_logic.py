@@ -77,8 +77,23 @@ def test_resgcn_container_matches_reference_checkpoints():
     assert len(groups) > 1 and any(g["lr"] < 1e-3 for g in groups)
     with pytest.raises(ValueError):
         gg.build_model("nope")
-    with pytest.raises(NotImplementedError):
-        gg.build_model("gat")
+    # the variants keep the reference's state-dict keys and shapes (model.py:239-414) and its README
+    # parameter counts; without a GPU a forward fails loudly (no CPU fallback)
+    from oracle.model_port import random_gcn_trimap_state, random_gat_trimap_state
+    for net, state in ((gg.build_model("gcn", hidden_channels=64, n_layers=3), random_gcn_trimap_state(64, 3)),
+                       (gg.GATTrimapNet(hidden_channels=64, n_heads=8, n_layers=2), random_gat_trimap_state(64, 8, 2))):
+        assert set(net.state_dict()) == set(state)
+        for k, v in net.state_dict().items():
+            assert tuple(v.shape) == tuple(state[k].shape), k
+        net.load_state_dict(state)
+        assert sorted(net._tensor_keys()) == sorted(k for k in state if not k.endswith("num_batches_tracked"))
+    assert isinstance(gg.build_model("gat"), gg.GATTrimapNet) and gg.build_model("gat").n_layers == 6
+    with pytest.raises(ValueError):
+        gg.GATTrimapNet(n_heads=3)
+    if not torch.cuda.is_available():
+        from gcn_grabcut_b200 import _native as nat
+        with pytest.raises(nat.NativeError):
+            gg.build_model("gcn", hidden_channels=32, n_layers=1)(gg.Data(x=torch.zeros(2, 19), edge_index=torch.zeros(2, 0, dtype=torch.long)))
 
 
 def test_host_side_label_helpers():

@@ -49,7 +49,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert sorted(nat.EXPORTED_SYMBOLS) == declared, set(declared) ^ set(nat.EXPORTED_SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), f"{sym} declared in the header but not exported"
-    assert lib.gg_abi_version() == 3
+    assert lib.gg_abi_version() == 4
 
 
 @pytest.mark.parametrize("cname,ctype", [("gg_graph_config", nat.GraphConfig), ("gg_graph_out", nat.GraphOut),

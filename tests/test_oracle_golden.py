@@ -213,3 +213,39 @@ def test_cache_key_known_answers():
         rd = importlib.import_module("gcn_grabcut.dataset")
         assert rd._cache_key(lazy, None, 0.7, 0.7) == cache_key(lazy, None, 0.7, 0.7)
         assert rd._cache_key(smp, None, 0.75, 0.75) == cache_key(smp, None, 0.75, 0.75)
+
+
+# ----------------------------------------------------------------------------- GCNTrimapNet / GATTrimapNet
+def variant_cases():
+    import os
+    from helpers import GOLDEN_DIR
+    z = dict(np.load(os.path.join(GOLDEN_DIR, "variants", "reference.npz")))
+    tags = sorted({k.split("/")[0] for k in z})
+    return z, tags
+
+
+def variant_state(z, tag):
+    D, n, H, seed = (int(v) for v in z[f"{tag}/meta"])
+    if tag.startswith("gcn"):
+        state = model_port.random_gcn_trimap_state(D, n, seed=seed)
+    else:
+        state = model_port.random_gat_trimap_state(D, H, n, seed=seed)
+    stored = {k[len(tag) + 7:]: v for k, v in z.items() if k.startswith(tag + "/state/")}
+    for k, v in stored.items():                # the small cases pin the seeded generator itself
+        assert np.array_equal(state[k].numpy(), v), f"{tag}: seeded state drifted at {k}"
+    return state
+
+
+@pytest.mark.parametrize("tag", variant_cases()[1])
+def test_variant_ports_match_reference(tag):
+    """oracle GCNTrimapNet / GATTrimapNet restatements against logits of the unmodified reference classes
+    (tests/golden/make_golden_variants.py)."""
+    z, _ = variant_cases()
+    state = variant_state(z, tag)
+    x, ei, ea = torch.tensor(z[f"{tag}/x"]), torch.tensor(z[f"{tag}/edge_index"]), torch.tensor(z[f"{tag}/edge_attr"])
+    batch = torch.tensor(z[f"{tag}/batch"]) if f"{tag}/batch" in z else None
+    if tag.startswith("gcn"):
+        mine = model_port.gcn_trimap_forward(state, x, ei, ea)
+    else:
+        mine = model_port.gat_trimap_forward(state, x, ei, ea, batch)
+    np.testing.assert_allclose(mine.numpy(), z[f"{tag}/logits"], atol=2e-5)
