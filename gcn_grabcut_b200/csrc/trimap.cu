@@ -174,30 +174,44 @@ k_guided_ab(const GuidedParams p) {
   const bool prob_in_smem = kTrimap && nn <= GF_PROB_TABLE;
   const int* rowtab = sRow + (r + 1) - y_begin;     // rowtab[yy] for yy in [y_begin-r-1, y_end+r)
 
-  // base planes of one pixel of this thread's column: g and the NSRC source planes
+  // base planes of one pixel of this thread's column: g and the NSRC source planes.  Two steps, so
+  // that a prefetch only ISSUES the global loads (raw grey byte + label, or the two floats) and the
+  // look-ups that depend on them run one iteration later, when the data has arrived.
   struct Px { float g, sv[NS]; };
-  auto fetch = [&](int yy, Px& px) {
+  struct Raw { int gr, l; float u, s; };
+  auto fetch_raw = [&](int yy) {
     const int ro = rowtab[yy];
+    Raw rw;
     if (kTrimap) {
-      const int gr = gcol[ro];
-      const int l = lcol[ro];
-      px.g = sLut[gr];
+      rw.gr = gcol[ro];
+      rw.l = lcol[ro];
+      rw.u = rw.s = 0.0f;
+    } else {
+      rw.gr = rw.l = 0;
+      rw.u = ucol[ro];
+      rw.s = scol[ro];
+    }
+    return rw;
+  };
+  auto resolve = [&](const Raw& rw, Px& px) {
+    if (kTrimap) {
+      px.g = sLut[rw.gr];
       px.sv[0] = 0.0f;
       px.sv[NS - 1] = 0.0f;                            // project_to_pixels zero padding
-      if (l >= 0 && l < nn) {
+      if (rw.l >= 0 && rw.l < nn) {
         if (prob_in_smem) {
-          const float2 pr = sProb[l];
+          const float2 pr = sProb[rw.l];
           px.sv[0] = pr.x;
           px.sv[NS - 1] = pr.y;
         } else {
-          const float* row = prob0 + (size_t)l * 3;
+          const float* row = prob0 + (size_t)rw.l * 3;
           px.sv[0] = row[0];
           px.sv[NS - 1] = row[2];
         }
       }
     } else {
-      px.g = ucol[ro];
-      px.sv[0] = scol[ro];
+      px.g = rw.u;
+      px.sv[0] = rw.s;
     }
   };
   double vs[NP];
@@ -221,22 +235,29 @@ k_guided_ab(const GuidedParams p) {
       vs[3 + 2 * c] -= (double)__fmul_rn(px.g, px.sv[c]);
     }
   };
-  for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
-    Px px;
-    fetch(yy, px);
-    add(px);
+  for (int yy = y_begin - r; yy < y_begin + r; yy += 4) {       // window warm-up: loads of four rows in flight
+    Raw rw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rw[k] = fetch_raw(min(yy + k, y_begin + r - 1));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (yy + k < y_begin + r) {
+        Px px;
+        resolve(rw[k], px);
+        add(px);
+      }
+    }
   }
   // software pipeline: the rows entering / leaving the window of the NEXT row are in flight
   // while the current row is reduced
-  Px cn, co, nn_, no_;
-  co.g = 0.f; nn_.g = 0.f; no_.g = 0.f;
-#pragma unroll
-  for (int c = 0; c < NS; ++c) co.sv[c] = nn_.sv[c] = no_.sv[c] = 0.f;
-  fetch(y_begin + r, cn);
+  Raw rn = fetch_raw(y_begin + r), ro_ = rn;
   for (int y = y_begin; y < y_end; ++y) {
+    Px cn, co;
+    resolve(rn, cn);
+    if (y > y_begin) resolve(ro_, co);
     if (y + 1 < y_end) {
-      fetch(y + 1 + r, nn_);
-      fetch(y - r, no_);
+      rn = fetch_raw(y + 1 + r);
+      ro_ = fetch_raw(y - r);
     }
     add(cn);
     if (y > y_begin) sub(co);
@@ -264,8 +285,6 @@ k_guided_ab(const GuidedParams p) {
       if (NS == 2) *reinterpret_cast<float4*>(p.ab + op * 4) = make_float4(abv[0], abv[1], abv[2 * NS - 2], abv[2 * NS - 1]);
       else *reinterpret_cast<float2*>(p.ab + op * 2) = make_float2(abv[0], abv[1]);
     }
-    cn = nn_;
-    co = no_;
   }
 }
 
@@ -304,21 +323,34 @@ k_guided_out(const GuidedParams p) {
       v[0] = t2.x; v[1] = t2.y;
     }
   };
-  for (int yy = y_begin - r; yy < y_begin + r; ++yy) {
-    float v[NP];
-    load_row(yy, v);
+  for (int yy = y_begin - r; yy < y_begin + r; yy += 4) {       // window warm-up: loads of four rows in flight
+    float v[4][NP];
 #pragma unroll
-    for (int q = 0; q < NP; ++q) vs[q] += (double)v[q];
+    for (int k = 0; k < 4; ++k) load_row(min(yy + k, y_begin + r - 1), v[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (yy + k < y_begin + r) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) vs[q] += (double)v[k][q];
+      }
+    }
   }
   float cn[NP], co[NP], nn_[NP], no_[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) co[q] = nn_[q] = no_[q] = 0.f;
   load_row(y_begin + r, cn);
+  const int o = t - r, x = x0 + o;
+  const bool writer = o >= 0 && o < hp.tx && x < W;
   for (int y = y_begin; y < y_end; ++y) {
     if (y + 1 < y_end) {
       load_row(y + 1 + r, nn_);
       load_row(y - r, no_);
     }
+    // guide value of the output pixel: issued here, consumed after the two barriers
+    const size_t op = img_off + (size_t)y * W + (writer ? x : 0);
+    int g_raw = 0;
+    float g_val = 0.0f;
+    if (writer) { if (kTrimap) g_raw = p.gray[op]; else g_val = p.guide[op]; }
 #pragma unroll
     for (int q = 0; q < NP; ++q) vs[q] += (double)cn[q];
     if (y > y_begin) {
@@ -330,11 +362,9 @@ k_guided_out(const GuidedParams p) {
     __syncthreads();
     horizontal_means<NP, NT, RT>(sV, sM, hp, r, scale);
     __syncthreads();
-    const int o = t - r, x = x0 + o;
-    if (o >= 0 && o < hp.tx && x < W) {
+    if (writer) {
       const float* m = sM + o;
-      const size_t op = img_off + (size_t)y * W + x;
-      const float g = kTrimap ? sLut[p.gray[op]] : p.guide[op];
+      const float g = kTrimap ? sLut[g_raw] : g_val;
       float q[T::NSRC];
 #pragma unroll
       for (int c = 0; c < T::NSRC; ++c)
