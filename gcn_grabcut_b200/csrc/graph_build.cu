@@ -1133,37 +1133,53 @@ k_node_features(const float* __restrict__ st_all, const int* __restrict__ label_
 
 // ============================================================================ S7
 // Global colour contrast (graph_builder.py:405-412): one warp per region.
+// PC_ROWS = regions per warp: 2 for small graphs (more warps in flight), 4 for large ones (fewer loads per pair)
+template <int PC_ROWS>
 __global__ void __launch_bounds__(256)
 k_prior_contrast(const float* __restrict__ st_all, const int* __restrict__ label_max,
                  float* __restrict__ contrast_all, int node_cap, float two_sig2 /* float32(2*contrast_sigma**2) */) {
   const int b = blockIdx.y;
   const int n = min(label_max[b] + 1, node_cap);
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= n) return;
+  // a warp owns PC_ROWS consecutive regions: the values of region j are loaded once for all of them
+  // and the independent rows hide each other's latency (same per-row summation order as one row per warp)
+  const int i0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PC_ROWS;
+  if (i0 >= n) return;
   const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
   const float* mL = st + (size_t)ST_MEAN_L * node_cap;
   const float* mA = mL + node_cap;
   const float* mB = mA + node_cap;
   const float* pcy = st + (size_t)ST_PCY * node_cap;
   const float* pcx = st + (size_t)ST_PCX * node_cap;
-  const float* cnt = st + (size_t)ST_COUNT * node_cap;
   // area_w = counts / counts.sum() (graph_builder.py:409): every pixel carries a label, so
   // counts.sum() is H*W (exact in float32) and area_w is the area ratio k_finalize_regions stored
   const float* area = st + (size_t)ST_AREA * node_cap;
-  const float li = mL[i], ai = mA[i], bi = mB[i], yi = pcy[i], xi = pcx[i];
-  double s = 0.0;
-  for (int j = lane; j < n; j += 32) {
-    const float dl = __fsub_rn(li, mL[j]), da = __fsub_rn(ai, mA[j]), db = __fsub_rn(bi, mB[j]);
-    const float cd = __fsqrt_rn(
-        __fadd_rn(__fadd_rn(__fmul_rn(dl, dl), __fmul_rn(da, da)), __fmul_rn(db, db)));
-    const float dy = __fsub_rn(yi, pcy[j]), dx = __fsub_rn(xi, pcx[j]);
-    const float sd = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
-    const float sw = expf(__fdiv_rn(-__fmul_rn(sd, sd), two_sig2));
-    s += (double)__fmul_rn(__fmul_rn(cd, sw), area[j]);
+  float li[PC_ROWS], ai[PC_ROWS], bi[PC_ROWS], yi[PC_ROWS], xi[PC_ROWS];
+  double s[PC_ROWS];
+#pragma unroll
+  for (int k = 0; k < PC_ROWS; ++k) {
+    const int i = min(i0 + k, n - 1);
+    li[k] = mL[i]; ai[k] = mA[i]; bi[k] = mB[i]; yi[k] = pcy[i]; xi[k] = pcx[i];
+    s[k] = 0.0;
   }
-  s = warp_sum(s);
-  if (lane == 0) contrast_all[(size_t)b * node_cap + i] = (float)s;
+  for (int j = lane; j < n; j += 32) {
+    const float lj = mL[j], aj = mA[j], bj = mB[j], yj = pcy[j], xj = pcx[j], wj = area[j];
+#pragma unroll
+    for (int k = 0; k < PC_ROWS; ++k) {
+      const float dl = __fsub_rn(li[k], lj), da = __fsub_rn(ai[k], aj), db = __fsub_rn(bi[k], bj);
+      const float cd = __fsqrt_rn(
+          __fadd_rn(__fadd_rn(__fmul_rn(dl, dl), __fmul_rn(da, da)), __fmul_rn(db, db)));
+      const float dy = __fsub_rn(yi[k], yj), dx = __fsub_rn(xi[k], xj);
+      const float sd = __fsqrt_rn(__fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dx, dx)));
+      const float sw = expf(__fdiv_rn(-__fmul_rn(sd, sd), two_sig2));
+      s[k] += (double)__fmul_rn(__fmul_rn(cd, sw), wj);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PC_ROWS; ++k) {
+    const double t = warp_sum(s[k]);
+    if (lane == 0 && i0 + k < n) contrast_all[(size_t)b * node_cap + i0 + k] = (float)t;
+  }
 }
 
 // Block-wide unit-norm helpers: min and max of v over [0,n) strided by the block.
@@ -1746,8 +1762,13 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
   GG_LAUNCH(ctx, k_node_features, B, 256, 0, st, stats, label_max, out.node_off, out.x,
             out.centroids, out.areas, nc);
   {
-    dim3 grid(ceil_div(nc, 8), B);
-    GG_LAUNCH(ctx, k_prior_contrast, grid, 256, 0, st, stats, label_max, contrast, nc, (float)(2 * 0.40 * 0.40));
+    if (nc >= 1024) {
+      dim3 grid(ceil_div(nc, 8 * 4), B);
+      GG_LAUNCH(ctx, k_prior_contrast<4>, grid, 256, 0, st, stats, label_max, contrast, nc, (float)(2 * 0.40 * 0.40));
+    } else {
+      dim3 grid(ceil_div(nc, 8 * 2), B);
+      GG_LAUNCH(ctx, k_prior_contrast<2>, grid, 256, 0, st, stats, label_max, contrast, nc, (float)(2 * 0.40 * 0.40));
+    }
   }
   GG_LAUNCH(ctx, k_prior_finish, B, 256, 0, st, stats, label_max, contrast, tmp2, out.node_off,
             out.x, nc, (float)(2 * 0.45 * 0.45), GG_N_NODE_FEATS, GG_N_IMAGE_FEATS);
@@ -1835,9 +1856,15 @@ int auto_prior(gg_context* ctx, Arena& ar, const int32_t* labels, const float* l
     GG_LAUNCH(ctx, k_finalize_regions, grid, 256, 0, st, acc, label_max, stats, B, H, W, node_cap);
   }
   {
-    dim3 grid(ceil_div(node_cap, 8), B);
-    GG_LAUNCH(ctx, k_prior_contrast, grid, 256, 0, st, stats, label_max, contrast, node_cap,
-              (float)(2 * contrast_sigma * contrast_sigma));
+    if (node_cap >= 1024) {
+      dim3 grid(ceil_div(node_cap, 8 * 4), B);
+      GG_LAUNCH(ctx, k_prior_contrast<4>, grid, 256, 0, st, stats, label_max, contrast, node_cap,
+                (float)(2 * contrast_sigma * contrast_sigma));
+    } else {
+      dim3 grid(ceil_div(node_cap, 8 * 2), B);
+      GG_LAUNCH(ctx, k_prior_contrast<2>, grid, 256, 0, st, stats, label_max, contrast, node_cap,
+                (float)(2 * contrast_sigma * contrast_sigma));
+    }
   }
   GG_LAUNCH(ctx, k_prior_finish, B, 256, 0, st, stats, label_max, contrast, tmp2, (const int64_t*)nullptr, prior,
             node_cap, (float)(2 * centre_sigma * centre_sigma), 3, 0);

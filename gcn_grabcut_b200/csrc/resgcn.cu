@@ -445,7 +445,8 @@ k_sage_finish(const float* __restrict__ t_in, const float* __restrict__ g, const
 // ------------------------------------------------------------------ global context
 // One block per graph: a = softmax_graph(u.z + c); g = sum a_i z_i;
 // gvec = sigmoid(W_e relu(W_c g + b_c) + b_e)          (model.py:165-188, 90-108)
-__global__ void __launch_bounds__(256)
+constexpr int GC_WARPS = 16;      // warps of k_graph_context (one block per graph; the node loops are latency-bound)
+__global__ void __launch_bounds__(GC_WARPS * 32)
 k_graph_context(const float* __restrict__ z, const int64_t* __restrict__ graph_off,
                 const float* __restrict__ wb, NetOffsets o, int n_graphs,
                 float* __restrict__ score, float* __restrict__ gvec) {
@@ -481,7 +482,7 @@ k_graph_context(const float* __restrict__ z, const int64_t* __restrict__ graph_o
   // g = sum_v a_v z_v: the nodes are split over the warps (a lane owns channels lane, lane+32,
   // ...); the per-warp partial sums are combined in a fixed order (deterministic)
   {
-    __shared__ float s_part[8][256];             // blockDim.x == 256 -> 8 warps, D <= 256
+    __shared__ float s_part[GC_WARPS][256];      // blockDim.x == GC_WARPS * 32, D <= 256
     float part[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) part[j] = 0.0f;
@@ -971,7 +972,7 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   {
     const size_t smem = (size_t)(D + D / 2) * sizeof(float);
     if (ceil_div(node_cap, n_graphs) <= 1024) {
-      GG_LAUNCH(ctx, k_graph_context, n_graphs, 256, smem, st, z, graph_off, wb, o, n_graphs, score, gvec);
+      GG_LAUNCH(ctx, k_graph_context, n_graphs, GC_WARPS * 32, smem, st, z, graph_off, wb, o, n_graphs, score, gvec);
     } else {
       // large graphs: the readout is split over CTX_PARTS blocks per graph
       GG_CUDA_OK(cudaMemsetAsync(ctx_gmax, 0x80, (size_t)n_graphs * sizeof(int), st));   // ordered(-huge)

@@ -213,25 +213,34 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
   const int cj1 = min(slic_cell(min(x0 + SA_TX, W) - 1, g.sx, g.tx, g.gx) + NEIGH, g.gx - 1);
   const int nci = ci1 - ci0 + 1, ncj = cj1 - cj0 + 1;          // <= SA_MAXC by the launch check
   const float* cb = cen + (size_t)b * K * 5;
+  const int y_hi = min(y0 + SA_TY, H), x_hi = min(x0 + SA_TX, W);
+  const float inv_step = 1.0f / (float)g.step;
+  bool full = true;                              // every window of this tile's centres covers the whole tile
   for (int i = threadIdx.x; i < nci * ncj; i += blockDim.x) {
     const int k = (ci0 + i / ncj) * g.gx + cj0 + i % ncj;
     const float cy = cb[k * 5], cx = cb[k * 5 + 1];
-    s_yx[i] = make_float2(cy, cx);
+    s_yx[i] = NEIGH == 1 ? make_float2(cy * inv_step, cx * inv_step) : make_float2(cy, cx);
     s_col[i] = make_float4(cb[k * 5 + 2], cb[k * 5 + 3], cb[k * 5 + 4], 0.0f);
-    s_win[i] = make_int4((int)fmaxf(cy - 2.0f * g.ty, 0.0f), (int)fminf(cy + 2.0f * g.ty + 1.0f, (float)H),
-                         (int)fmaxf(cx - 2.0f * g.tx, 0.0f), (int)fminf(cx + 2.0f * g.tx + 1.0f, (float)W));
+    const int4 w = make_int4((int)fmaxf(cy - 2.0f * g.ty, 0.0f), (int)fminf(cy + 2.0f * g.ty + 1.0f, (float)H),
+                             (int)fmaxf(cx - 2.0f * g.tx, 0.0f), (int)fminf(cx + 2.0f * g.tx + 1.0f, (float)W));
+    s_win[i] = w;
+    full = full && w.x <= y0 && w.y >= y_hi && w.z <= x0 && w.w >= x_hi;
 #pragma unroll
     for (int q = 0; q < 6; ++q) s_sum[i][q] = 0;
   }
   if (threadIdx.x < SA_TY) s_rowcell[threadIdx.x] = slic_cell(y0 + threadIdx.x, g.sy, g.ty, g.gy);
   if (threadIdx.x >= 64 && threadIdx.x < 64 + SA_TX) s_colcell[threadIdx.x - 64] = slic_cell(x0 + threadIdx.x - 64, g.sx, g.tx, g.gx);
-  __syncthreads();
+  const bool all_full = __syncthreads_and(full) != 0;
   const float w_sp = 1.0f / (float)(g.step * g.step);
   const int tx = threadIdx.x & 63, ty4 = threadIdx.x >> 6;      // 64 columns x 4 row groups
   const int x = x0 + tx;
   const int lane = threadIdx.x & 31;
   const int hj = s_colcell[tx];
   const int j_lo = max(hj - NEIGH, cj0), j_hi = min(hj + NEIGH, cj1);
+  // NEIGH == 1: the three candidate columns, clamped to the grid (a clamped duplicate is evaluated
+  // twice with the same distance and never wins a second time)
+  const int jc0 = max(hj - 1, 0) - cj0, jc1 = hj - cj0, jc2 = min(hj + 1, g.gx - 1) - cj0;
+  const float fxs = (float)x * inv_step;
   for (int rr = 0; rr < SA_TY / 4; ++rr) {
     const int y = y0 + ty4 + 4 * rr;
     const bool in = y < H && x < W;
@@ -240,14 +249,36 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
     if (in) {
       f = feat[((size_t)b * H + y) * W + x];
       const int hi = s_rowcell[ty4 + 4 * rr];
-      const float fy = (float)y, fx = (float)x;
       float best = __int_as_float(0x7f7fffff);
+      if (NEIGH == 1 && all_full) {
+        // straight-line search over the 3 x 3 cells in increasing centre index; ties keep the lower
+        // index (strict <), exactly the rule of the general path below.  Positions are in units of the
+        // grid step, so the 5-d distance needs no weights.
+        const float fys = (float)y * inv_step;
+        const int rb[3] = {(max(hi - 1, 0) - ci0) * ncj, (hi - ci0) * ncj, (min(hi + 1, g.gy - 1) - ci0) * ncj};
+        const int jc[3] = {jc0, jc1, jc2};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int slot = rb[a] + jc[c];
+            const float2 cp = s_yx[slot];
+            const float4 cc = s_col[slot];
+            const float dy = cp.x - fys, dx = cp.y - fxs;
+            const float d0 = f.x - cc.x, d1 = f.y - cc.y, d2 = f.z - cc.z;
+            const float d = fmaf(dy, dy, dx * dx) + fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+            if (d < best) { best = d; best_slot = slot; }
+          }
+        }
+      } else {
+      const float ps = NEIGH == 1 ? (float)g.step : 1.0f;         // centre positions are stored in step units for NEIGH == 1
+      const float fy = (float)y, fx = (float)x;
       // distance with the spatial term first -- it alone rules out most centres once a near one has
       // been seen -- then skimage's window test, then the colour term; slots are visited in
       // increasing centre index after the home cell, equal distances go to the lower index
       auto consider = [&](int slot, bool home) {
         const float2 c = s_yx[slot];
-        const float dy = c.x - fy, dx = c.y - fx;
+        const float dy = c.x * ps - fy, dx = c.y * ps - fx;
         float d = (dy * dy + dx * dx) * w_sp;
         if (d > best) return;
         const int4 w = s_win[slot];
@@ -265,6 +296,7 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
           if (row + j != home_slot) consider(row + j, false);
       }
       if (best_slot < 0) best_slot = home_slot;           // no window reaches the pixel (cannot happen on a regular grid)
+      }
       const int bi = best_slot / ncj;
       labels[((size_t)b * H + y) * W + x] = (ci0 + bi) * g.gx + cj0 + (best_slot - bi * ncj);
     }
@@ -272,14 +304,17 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
     // shared-memory atomic per field and distinct centre instead of one per pixel)
     const unsigned act = __ballot_sync(0xffffffffu, in);
     if (in) {
-      const unsigned grp = __match_any_sync(act, best_slot);
-      const int v1 = __reduce_add_sync(grp, y), v2 = __reduce_add_sync(grp, x);
+      // a warp covers 32 consecutive pixels of ONE row: mostly one or two centres; the row sum is y * count
+      const int first = __shfl_sync(act, best_slot, __ffs(act) - 1);
+      const unsigned grp = __all_sync(act, best_slot == first) ? act : __match_any_sync(act, best_slot);
+      const int v2 = __reduce_add_sync(grp, x);
       const int v3 = __reduce_add_sync(grp, __float2int_rn(f.x * SLIC_FIX));
       const int v4 = __reduce_add_sync(grp, __float2int_rn(f.y * SLIC_FIX));
       const int v5 = __reduce_add_sync(grp, __float2int_rn(f.z * SLIC_FIX));
       if (lane == __ffs(grp) - 1) {
-        atomicAdd(&s_sum[best_slot][0], __popc(grp));
-        atomicAdd(&s_sum[best_slot][1], v1);
+        const int n = __popc(grp);
+        atomicAdd(&s_sum[best_slot][0], n);
+        atomicAdd(&s_sum[best_slot][1], y * n);
         atomicAdd(&s_sum[best_slot][2], v2);
         atomicAdd(&s_sum[best_slot][3], v3);
         atomicAdd(&s_sum[best_slot][4], v4);
