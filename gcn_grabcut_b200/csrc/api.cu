@@ -183,7 +183,7 @@ static int run_path(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_
                         pb.g.node_off, B, SN, SE, nullptr, pb.probs, st, cfg.node_cap, 2 * cfg.pair_cap));
   if (pc.edge_aware) {
     GG_TRY(refine_trimap(ctx, ar, bgr, gray, labels, pb.probs, pb.g.node_off, B, H, W, pc.radius,
-                         pc.eps, pc.thr_fg, pc.thr_bg, trimap, nullptr, nullptr, st));
+                         pc.eps, pc.thr_fg, pc.thr_bg, trimap, nullptr, nullptr, st, cfg.node_cap));
   } else {
     GG_TRY(project_trimap(ctx, labels, pb.probs, pb.g.node_off, B, H, W, pc.thr_fg, pc.thr_bg, trimap, st));
   }

@@ -1415,6 +1415,81 @@ k_csr(const int2* __restrict__ pairs_all, const int* __restrict__ n_adj,
   }
 }
 
+// The same CSR built in shared memory (one block per image, when 2 * pair_cap entries fit): row
+// counts, scan, fill and the per-row insertion sort touch shared memory only -- the sort's dependent
+// load / compare / store chains run at shared-memory instead of L2 latency -- and the finished arrays
+// leave with coalesced stores.
+__global__ void __launch_bounds__(512)
+k_csr_smem(const int2* __restrict__ pairs_all, const int* __restrict__ n_adj,
+           const int* __restrict__ n_nl, const int* __restrict__ label_max,
+           const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off,
+           int32_t* __restrict__ rowptr, int32_t* __restrict__ csr_src,
+           int32_t* __restrict__ csr_eid, int node_cap, int pair_cap, int B) {
+  extern __shared__ int cs_smem[];
+  __shared__ int scratch[40];
+  int* s_rp = cs_smem;                       // [node_cap + 1]
+  int* s_cur = s_rp + node_cap + 1;          // [node_cap]
+  int* s_src = s_cur + node_cap;             // [2 * pair_cap]
+  int* s_eid = s_src + 2 * pair_cap;         // [2 * pair_cap]
+  const int b = blockIdx.x;
+  const int n = min(label_max[b] + 1, node_cap);
+  const int2* pairs = pairs_all + (size_t)b * pair_cap;
+  const int P = min(n_adj[b] + n_nl[b], pair_cap);     // (an overflow is reported through the status word upstream)
+  const int64_t no = node_off[b], eo = edge_off[b];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { s_rp[i] = 0; s_cur[i] = 0; }
+  __syncthreads();
+  for (int q = threadIdx.x; q < P; q += blockDim.x) {
+    const int2 pr = pairs[q];
+    atomicAdd(&s_rp[pr.x], 1);
+    atomicAdd(&s_rp[pr.y], 1);
+  }
+  __syncthreads();
+  int carry = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < n) ? s_rp[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, scratch, &total);
+    __syncthreads();
+    if (i < n) s_rp[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_rp[n] = carry;
+  __syncthreads();
+  for (int q = threadIdx.x; q < P; q += blockDim.x) {
+    const int2 pr = pairs[q];
+    int pos = s_rp[pr.y] + atomicAdd(&s_cur[pr.y], 1);     // edge lo -> hi  (forward row q)
+    s_src[pos] = (int)no + pr.x;
+    s_eid[pos] = (int)eo + q;
+    pos = s_rp[pr.x] + atomicAdd(&s_cur[pr.x], 1);         // edge hi -> lo  (reversed row P+q)
+    s_src[pos] = (int)no + pr.y;
+    s_eid[pos] = (int)eo + P + q;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int s0 = s_rp[i], s1 = s_rp[i + 1];
+    for (int a = s0 + 1; a < s1; ++a) {
+      const int sv = s_src[a], ev = s_eid[a];
+      int j = a - 1;
+      while (j >= s0 && s_src[j] > sv) {
+        s_src[j + 1] = s_src[j];
+        s_eid[j + 1] = s_eid[j];
+        --j;
+      }
+      s_src[j + 1] = sv;
+      s_eid[j + 1] = ev;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) rowptr[no + i] = (int)eo + s_rp[i];
+  if (b == B - 1 && threadIdx.x == 0) rowptr[no + n] = (int)eo + carry;   // rowptr[total nodes]
+  for (int k = threadIdx.x; k < 2 * P; k += blockDim.x) {
+    csr_src[eo + k] = s_src[k];
+    csr_eid[eo + k] = s_eid[k];
+  }
+}
+
 // ============================================================================ debug planes
 // GraphBuilder.__init__ planes (_lab, _hsv, _gray, _grad) for parity tests.
 __global__ void k_pixel_planes(const uint8_t* __restrict__ bgr, const double* __restrict__ lin_lut,
@@ -1774,8 +1849,17 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
             out.x, nc, (float)(2 * 0.45 * 0.45), GG_N_NODE_FEATS, GG_N_IMAGE_FEATS);
   GG_LAUNCH(ctx, k_edge_attrs, B, 256, 0, st, stats, pairs, shared, n_adj, n_nl, max_shared,
             out.edge_off, out.edge_index, (int64_t)2 * B * pc, out.edge_attr, nc, pc);
-  GG_LAUNCH(ctx, k_csr, B, 512, 0, st, pairs, n_adj, n_nl, label_max, out.node_off, out.edge_off,
-            cursor, out.csr_rowptr, out.csr_src, out.csr_eid, nc, pc, B);
+  {
+    const size_t csr_smem = ((size_t)2 * nc + 1 + (size_t)4 * pc) * sizeof(int);
+    if (csr_smem <= 160 * 1024) {
+      GG_SMEM_ATTR_ONCE(ctx, 54, k_csr_smem, 160 * 1024);
+      GG_LAUNCH(ctx, k_csr_smem, B, 512, csr_smem, st, pairs, n_adj, n_nl, label_max, out.node_off, out.edge_off,
+                out.csr_rowptr, out.csr_src, out.csr_eid, nc, pc, B);
+    } else {
+      GG_LAUNCH(ctx, k_csr, B, 512, 0, st, pairs, n_adj, n_nl, label_max, out.node_off, out.edge_off,
+                cursor, out.csr_rowptr, out.csr_src, out.csr_eid, nc, pc, B);
+    }
+  }
   if (out.shared_cnt)
     GG_CUDA_OK(cudaMemcpyAsync(out.shared_cnt, shared, (size_t)B * pc * sizeof(int),
                                cudaMemcpyDeviceToDevice, st));

@@ -68,7 +68,8 @@ k_input_stage(const float* __restrict__ x, const float* __restrict__ wb, NetOffs
   float* s_pb2 = s_pb0 + q * 3;         // [q][D] (transposed: conflict-free across lanes)
   for (int i = threadIdx.x; i < D * 19; i += blockDim.x) s_win[i] = wb[o.w_in + i];
   for (int i = threadIdx.x; i < q * 3; i += blockDim.x) s_pb0[i] = wb[o.pb0_w + i];
-  for (int i = threadIdx.x; i < D * q; i += blockDim.x) s_pb2[(i % q) * D + i / q] = wb[o.pb2_w + i];
+  // transposed copy with LINEAR shared-memory stores (the strided side is the L2-cached global read)
+  for (int i = threadIdx.x; i < D * q; i += blockDim.x) s_pb2[i] = wb[o.pb2_w + (size_t)(i % D) * q + i / D];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -895,7 +896,8 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
   // ---- input stage
   {
     const size_t smem = ((size_t)D * 19 + (size_t)nw.q * 3 + (size_t)D * nw.q) * sizeof(float);
-    const int blocks = min(warp_blocks, ctx->sm_count * 8);
+    // few resident blocks per SM, many nodes per warp: the 26 KB weight image is staged once per block
+    const int blocks = min(warp_blocks, ctx->sm_count * 3);
     GG_CPL_SWITCH(D, {
       GG_SMEM_ATTR_ONCE(ctx, 1 + CPL, k_input_stage<CPL>, smem);
       GG_LAUNCH(ctx, k_input_stage<CPL>, blocks, 256, smem, st, x, wb, o, sizes, h, z, row_stats);

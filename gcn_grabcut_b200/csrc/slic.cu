@@ -215,7 +215,7 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
   const float* cb = cen + (size_t)b * K * 5;
   const int y_hi = min(y0 + SA_TY, H), x_hi = min(x0 + SA_TX, W);
   const float inv_step = 1.0f / (float)g.step;
-  bool full = true;                              // every window of this tile's centres covers the whole tile
+  bool full = true;                              // every window covers all the pixels of the tile that consider its centre
   for (int i = threadIdx.x; i < nci * ncj; i += blockDim.x) {
     const int k = (ci0 + i / ncj) * g.gx + cj0 + i % ncj;
     const float cy = cb[k * 5], cx = cb[k * 5 + 1];
@@ -224,7 +224,16 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
     const int4 w = make_int4((int)fmaxf(cy - 2.0f * g.ty, 0.0f), (int)fminf(cy + 2.0f * g.ty + 1.0f, (float)H),
                              (int)fmaxf(cx - 2.0f * g.tx, 0.0f), (int)fminf(cx + 2.0f * g.tx + 1.0f, (float)W));
     s_win[i] = w;
-    full = full && w.x <= y0 && w.y >= y_hi && w.z <= x0 && w.w >= x_hi;
+    // the pixels of this tile that can see centre k are those whose home cell is within one cell of
+    // k's cell: rows [begin(i-1), end(i+1)) x columns [begin(j-1), end(j+1)), cut to the tile
+    {
+      const int ci = ci0 + i / ncj, cj = cj0 + i % ncj;
+      const int ry0 = max(ci - 1 <= 0 ? 0 : g.sy - g.ty / 2 + (ci - 1) * g.ty, y0);
+      const int ry1 = min(ci + 1 >= g.gy - 1 ? H : g.sy - g.ty / 2 + (ci + 2) * g.ty, y_hi);
+      const int rx0 = max(cj - 1 <= 0 ? 0 : g.sx - g.tx / 2 + (cj - 1) * g.tx, x0);
+      const int rx1 = min(cj + 1 >= g.gx - 1 ? W : g.sx - g.tx / 2 + (cj + 2) * g.tx, x_hi);
+      if (ry0 < ry1 && rx0 < rx1) full = full && w.x <= ry0 && w.y >= ry1 && w.z <= rx0 && w.w >= rx1;
+    }
 #pragma unroll
     for (int q = 0; q < 6; ++q) s_sum[i][q] = 0;
   }

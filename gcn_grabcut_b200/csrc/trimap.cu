@@ -23,7 +23,8 @@ namespace gg {
 
 constexpr int GF_MAX_STRIP = 512;   // output rows per block (strip height), runtime <= this
 constexpr int GF_MAX_RADIUS = 24;
-constexpr int GF_PROB_TABLE = 1024;  // labels whose (p_bg, p_fg) are staged in shared memory
+constexpr int GF_PROB_TABLE = 2048;  // most labels whose (p_bg, p_fg) are staged in (dynamic) shared memory
+constexpr int GF_PROB_DEFAULT = 1024;  // ... when the caller gives no bound on the labels of an image
 
 struct GuidedParams {
   // trimap mode
@@ -43,6 +44,7 @@ struct GuidedParams {
   float* q0;                // optional filtered planes (p_bg / out)
   float* q1;                // optional (p_fg)
   int H, W, radius, strip;
+  int prob_cap;             // entries of the shared (p_bg, p_fg) table (dynamic shared memory of stage 1)
   float eps, thr_fg, thr_bg;
 };
 
@@ -146,7 +148,7 @@ k_guided_ab(const GuidedParams p) {
   __shared__ float sM[NP * NT];
   __shared__ int sRow[GF_MAX_STRIP + 2 * GF_MAX_RADIUS + 2];
   __shared__ float sLut[kTrimap ? 256 : 1];
-  __shared__ float2 sProb[kTrimap ? GF_PROB_TABLE : 1];     // (p_bg, p_fg) per label, if it fits
+  extern __shared__ float2 sProb[];                         // [p.prob_cap] (p_bg, p_fg) per label, if it fits
   const int r = RT > 0 ? RT : p.radius, H = p.H, W = p.W, b = blockIdx.z, t = threadIdx.x;
   const HorizontalPlan<NP, NT> hp(r);
   const int x0 = blockIdx.x * hp.tx;
@@ -167,11 +169,11 @@ k_guided_ab(const GuidedParams p) {
     nn = (int)(p.node_off[b + 1] - no);
     prob0 = p.probs + (size_t)no * 3;
     for (int i = t; i < 256; i += NT) sLut[i] = __fdiv_rn((float)i, 255.0f);   // guide = gray/255
-    if (nn <= GF_PROB_TABLE)
+    if (nn <= p.prob_cap)
       for (int i = t; i < nn; i += NT) sProb[i] = make_float2(prob0[(size_t)i * 3], prob0[(size_t)i * 3 + 2]);
   }
   __syncthreads();
-  const bool prob_in_smem = kTrimap && nn <= GF_PROB_TABLE;
+  const bool prob_in_smem = kTrimap && nn <= p.prob_cap;
   const int* rowtab = sRow + (r + 1) - y_begin;     // rowtab[yy] for yy in [y_begin-r-1, y_end+r)
 
   // base planes of one pixel of this thread's column: g and the NSRC source planes.  Two steps, so
@@ -404,10 +406,11 @@ static int gf_strip(int H) {
 template <bool kTrimap, int NT>
 static int launch_guided_ab(gg_context* ctx, GuidedParams p, int B, cudaStream_t st) {
   p.strip = gf_strip(p.H);
+  const size_t dyn = kTrimap ? (size_t)p.prob_cap * sizeof(float2) : 0;
   dim3 grid(ceil_div(p.W, NT - 2 * p.radius), ceil_div(p.H, p.strip), B);
-  if (p.radius == 8) GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 8, NT>), grid, NT, 0, st, p);
-  else if (p.radius == 4) GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 4, NT>), grid, NT, 0, st, p);
-  else GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 0, NT>), grid, NT, 0, st, p);
+  if (p.radius == 8) GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 8, NT>), grid, NT, dyn, st, p);
+  else if (p.radius == 4) GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 4, NT>), grid, NT, dyn, st, p);
+  else GG_LAUNCH(ctx, (k_guided_ab<kTrimap, 0, NT>), grid, NT, dyn, st, p);
   return GG_OK;
 }
 
@@ -729,7 +732,7 @@ size_t trimap_workspace_bytes(int B, int H, int W, bool need_gray) {
 int refine_trimap(gg_context* ctx, Arena& ar, const uint8_t* bgr, const uint8_t* gray_in,
                   const int32_t* labels, const float* probs, const int64_t* node_off, int B, int H,
                   int W, int radius, float eps, float thr_fg, float thr_bg, uint8_t* trimap,
-                  float* p_bg, float* p_fg, cudaStream_t st) {
+                  float* p_bg, float* p_fg, cudaStream_t st, int node_cap_hint) {
   GG_REQUIRE(radius >= 0 && radius <= GF_MAX_RADIUS, "refine_trimap: radius must be in [0,%d]",
              GF_MAX_RADIUS);
   GG_REQUIRE(B > 0 && H >= 2 && W >= 2, "refine_trimap: bad shape");
@@ -745,6 +748,7 @@ int refine_trimap(gg_context* ctx, Arena& ar, const uint8_t* bgr, const uint8_t*
   p.gray = gray; p.labels = labels; p.probs = probs; p.node_off = node_off;
   p.ab = ab; p.plane_stride = npx; p.trimap = trimap; p.q0 = p_bg; p.q1 = p_fg;
   p.H = H; p.W = W; p.radius = radius; p.eps = eps; p.thr_fg = thr_fg; p.thr_bg = thr_bg;
+  p.prob_cap = node_cap_hint > 0 ? std::min(node_cap_hint, GF_PROB_TABLE) : GF_PROB_DEFAULT;
   GG_TRY(launch_guided<true>(ctx, p, B, st));
   return GG_OK;
 }

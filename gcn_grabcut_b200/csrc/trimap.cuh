@@ -10,7 +10,9 @@ size_t trimap_workspace_bytes(int B, int H, int W, bool need_gray);
 int refine_trimap(gg_context* ctx, Arena& ar, const uint8_t* bgr, const uint8_t* gray_in,
                   const int32_t* labels, const float* probs, const int64_t* node_off, int B, int H,
                   int W, int radius, float eps, float thr_fg, float thr_bg, uint8_t* trimap,
-                  float* p_bg, float* p_fg, cudaStream_t st);
+                  float* p_bg, float* p_fg, cudaStream_t st, int node_cap_hint = 0);
+// node_cap_hint: upper bound of the labels of one image when the caller knows it (0 = unknown); sizes the
+// shared (p_bg, p_fg) table of the first filter stage.
 
 int guided_filter_plane(gg_context* ctx, Arena& ar, const float* guide, const float* src, int H,
                         int W, int radius, float eps, float* out, cudaStream_t st);
