@@ -186,8 +186,8 @@ __global__ void k_slic_init(const float4* __restrict__ feat, SlicGrid g, int H, 
   for (int q = 0; q < 6; ++q) s[q] = 0;
 }
 
-constexpr int SA_TY = 16, SA_TX = 64;    // pixel tile of k_slic_assign (256 threads x 4 pixels)
-constexpr int SA_MAXC = 12;              // cells per axis that a tile can touch (tile / step + 5)
+constexpr int SA_TY = 32, SA_TX = 64;    // pixel tile of k_slic_assign (256 threads x 8 pixels)
+constexpr int SA_MAXC = 16;              // cells per axis that a tile can touch (tile / step + 5)
 
 GG_D int slic_cell(int p, int start, int step, int n) {       // home cell of a coordinate (boundaries midway)
   const int num = p - start + step / 2;
@@ -203,6 +203,9 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
   __shared__ float2 s_yx[SA_MAXC * SA_MAXC];       // centre position
   __shared__ float4 s_col[SA_MAXC * SA_MAXC];      // centre colour
   __shared__ int4 s_win[SA_MAXC * SA_MAXC];        // skimage's window of the centre: y_min, y_max, x_min, x_max
+  // fast path: |f - c|^2 - |f|^2 = |c|^2 - 2 f.c  ->  (-2cy, -2cx, -2L, -2A), (-2B, |c|^2): five FMAs per centre
+  __shared__ float4 s_q4[SA_MAXC * SA_MAXC];
+  __shared__ float2 s_q2[SA_MAXC * SA_MAXC];
   __shared__ int s_sum[SA_MAXC * SA_MAXC][6];
   __shared__ int s_rowcell[SA_TY], s_colcell[SA_TX];
   const int b = blockIdx.z, y0 = blockIdx.y * SA_TY, x0 = blockIdx.x * SA_TX;
@@ -221,6 +224,11 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
     const float cy = cb[k * 5], cx = cb[k * 5 + 1];
     s_yx[i] = NEIGH == 1 ? make_float2(cy * inv_step, cx * inv_step) : make_float2(cy, cx);
     s_col[i] = make_float4(cb[k * 5 + 2], cb[k * 5 + 3], cb[k * 5 + 4], 0.0f);
+    if (NEIGH == 1) {
+      const float ys = cy * inv_step, xs = cx * inv_step, cl = cb[k * 5 + 2], ca = cb[k * 5 + 3], cbb = cb[k * 5 + 4];
+      s_q4[i] = make_float4(-2.0f * ys, -2.0f * xs, -2.0f * cl, -2.0f * ca);
+      s_q2[i] = make_float2(-2.0f * cbb, fmaf(ys, ys, fmaf(xs, xs, fmaf(cl, cl, fmaf(ca, ca, cbb * cbb)))));
+    }
     const int4 w = make_int4((int)fmaxf(cy - 2.0f * g.ty, 0.0f), (int)fminf(cy + 2.0f * g.ty + 1.0f, (float)H),
                              (int)fmaxf(cx - 2.0f * g.tx, 0.0f), (int)fminf(cx + 2.0f * g.tx + 1.0f, (float)W));
     s_win[i] = w;
@@ -250,13 +258,15 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
   // twice with the same distance and never wins a second time)
   const int jc0 = max(hj - 1, 0) - cj0, jc1 = hj - cj0, jc2 = min(hj + 1, g.gx - 1) - cj0;
   const float fxs = (float)x * inv_step;
+  float4 f_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (y0 + ty4 < H && x < W) f_next = feat[((size_t)b * H + y0 + ty4) * W + x];
   for (int rr = 0; rr < SA_TY / 4; ++rr) {
     const int y = y0 + ty4 + 4 * rr;
     const bool in = y < H && x < W;
     int best_slot = -1;
-    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 f = f_next;                                  // loaded one iteration ago
+    if (rr + 1 < SA_TY / 4 && y + 4 < H && x < W) f_next = feat[((size_t)b * H + y + 4) * W + x];
     if (in) {
-      f = feat[((size_t)b * H + y) * W + x];
       const int hi = s_rowcell[ty4 + 4 * rr];
       float best = __int_as_float(0x7f7fffff);
       if (NEIGH == 1 && all_full) {
@@ -271,11 +281,9 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const int slot = rb[a] + jc[c];
-            const float2 cp = s_yx[slot];
-            const float4 cc = s_col[slot];
-            const float dy = cp.x - fys, dx = cp.y - fxs;
-            const float d0 = f.x - cc.x, d1 = f.y - cc.y, d2 = f.z - cc.z;
-            const float d = fmaf(dy, dy, dx * dx) + fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+            const float4 q4 = s_q4[slot];
+            const float2 q2 = s_q2[slot];
+            const float d = fmaf(q4.x, fys, fmaf(q4.y, fxs, fmaf(q4.z, f.x, fmaf(q4.w, f.y, fmaf(q2.x, f.z, q2.y)))));
             if (d < best) { best = d; best_slot = slot; }
           }
         }

@@ -68,6 +68,36 @@ def test_variant_on_built_graph(gg, variant):
     assert np.array_equal(tri, model_port.probs_to_trimap(probs, graph.segments, 0.55, 0.55))
 
 
+@pytest.mark.parametrize("variant", ["gcn", "gat"])
+def test_variant_degenerate_graphs(gg, variant):
+    """Graphs the reference accepts at the edges of its domain: no edges at all (every gate is 0 ->
+    GCNTrimapNet still has its input row in the concat head, GATTrimapNet reduces to skip + context), a
+    single node, self loops in the edge list (GCNConv / GATv2Conv drop and re-add them), missing edge_attr."""
+    from oracle import model_port
+    state = model_port.random_gcn_trimap_state(32, 2, seed=3) if variant == "gcn" else \
+        model_port.random_gat_trimap_state(32, 4, 2, seed=3)
+    net = gg.build_model(variant, hidden_channels=32, n_layers=2) if variant == "gcn" else \
+        gg.GATTrimapNet(hidden_channels=32, n_heads=4, n_layers=2)
+    net.load_state_dict(state)
+    net = net.to("cuda")
+    fwd = model_port.gcn_trimap_forward if variant == "gcn" else model_port.gat_trimap_forward
+    gen = torch.Generator().manual_seed(0)
+    cases = {
+        "no_edges": (torch.randn(6, 19, generator=gen), torch.zeros(2, 0, dtype=torch.long), torch.zeros(0, 5)),
+        "one_node": (torch.randn(1, 19, generator=gen), torch.zeros(2, 0, dtype=torch.long), torch.zeros(0, 5)),
+        "self_loops": (torch.randn(5, 19, generator=gen), torch.tensor([[0, 1, 2, 2, 3, 4, 1], [1, 0, 2, 3, 2, 4, 3]]),
+                       torch.rand(7, 5, generator=gen)),
+    }
+    for name, (x, ei, ea) in cases.items():
+        got = net(gg.Data(x=x, edge_index=ei, edge_attr=ea).to("cuda")).cpu().numpy()
+        want = fwd(state, x, ei, ea).numpy()
+        assert np.isfinite(got).all(), name
+        np.testing.assert_allclose(got, want, atol=5e-4, rtol=1e-4, err_msg=name)
+    x, ei, _ = cases["self_loops"]
+    got = net(gg.Data(x=x, edge_index=ei).to("cuda")).cpu().numpy()               # edge_attr None -> zeros (model.py:290)
+    np.testing.assert_allclose(got, fwd(state, x, ei, torch.zeros(7, 5)).numpy(), atol=5e-4, rtol=1e-4)
+
+
 def test_variant_state_errors(gg):
     """A forward for a variant whose weights are not loaded fails with GG_ERR_STATE; a state-dict with a
     missing key is rejected before anything reaches the device."""
