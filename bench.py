@@ -473,6 +473,45 @@ def run_other_config(gg, nat, dev, letter, B, H, W, nseg, k, hidden, layers, rad
     return rec
 
 
+def run_variants(gg, nat, dev):
+    """forward(data) of the three build_model() networks on the same batch of region graphs
+    (64 config-B images, one Batch as the reference would collate them), device-resident, CUDA events."""
+    import torch
+    from gcn_grabcut_b200.synthetic import make_batch, random_state_dict
+    from oracle import model_port                      # seeded random state-dicts with the reference's keys only
+    Bv = 64
+    imgs, labs = make_batch(Bv, 320, 480, 300, seed0=5000)
+    cfg = gg.SuperpixelGraphConfig(n_segments=300)
+    g = gg.build_graph_batch(torch.from_numpy(imgs).to(dev), torch.from_numpy(labs).to(dev), cfg, node_cap=int(labs.max()) + 1)
+    n_nodes, n_edges = int(g.node_off[-1].item()), int(g.edge_off[-1].item())
+    counts = (g.node_off[1:] - g.node_off[:-1]).to(torch.int64)
+    batch = torch.repeat_interleave(torch.arange(Bv, device=dev), counts)
+    ecounts = (g.edge_off[1:] - g.edge_off[:-1]).to(torch.int64)
+    edge_image = torch.repeat_interleave(torch.arange(Bv, device=dev), ecounts)
+    ei = g.edge_index[:, :n_edges] + g.node_off[:-1][edge_image]        # image-local ids -> ids in the collated batch
+    data = gg.Data(x=g.x[:n_nodes], edge_index=ei, edge_attr=g.edge_attr[:n_edges], batch=batch)
+    out = {"graphs": Bv, "nodes": n_nodes, "directed_edges": n_edges}
+    nets = {"resgcn": (gg.build_model("resgcn", hidden_channels=128, n_layers=6), random_state_dict(128, 6, seed=0)),
+            "gcn": (gg.build_model("gcn", hidden_channels=128, n_layers=6), model_port.random_gcn_trimap_state(128, 6, seed=0)),
+            "gat": (gg.GATTrimapNet(hidden_channels=128, n_heads=8, n_layers=5), model_port.random_gat_trimap_state(128, 8, 5, seed=0))}
+    for name, (net, state) in nets.items():
+        net.load_state_dict(state)
+        net = net.to(dev)
+        for _ in range(3):
+            net(data)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            logits = net(data)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        assert bool(torch.isfinite(logits).all())
+        out[name] = {"forward_ms": ms, "graphs_per_s": Bv / (ms * 1e-3),
+                     "what": "forward(data) incl. the COO -> CSR conversion (gg_coo_to_csr), logits on the device"}
+    return out
+
+
 def run_config_a(gg, nat, dev, hidden, layers):
     """Config A: one 320x480 image through the drop-in per-image API (the three calls
     pipeline.segment() makes, numpy in / numpy out) and through TrimapPath with B = 1."""
@@ -809,6 +848,7 @@ def run_ours(a):
                           "workload": "A: one 320x480 synthetic image, ~300 regions, random-init ResGCNNet(D=128, n=6)"}
             other["C"] = run_other_config(gg, nat, dev, "C", 64, 1080, 1920, 2000, 16, 128, 6, a.radius, 10, 3, cores)
             other["E"] = run_other_config(gg, nat, dev, "E", 8, 2160, 3840, 10000, 4, 256, 8, a.radius, 10, 3, cores)
+            other["variants"] = run_variants(gg, nat, dev)
         except Exception as e:      # the headline line must survive a failure of an extra record
             other["error"] = repr(e)
 

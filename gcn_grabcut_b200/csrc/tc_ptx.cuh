@@ -46,12 +46,27 @@ GG_D bool mbar_test_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// one probe that the hardware may suspend for a bounded time while the phase is pending (a waiting
+// warp then does not burn issue slots of the warps it is waiting for)
+GG_D bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a barrier that does not complete within ~0.2 s is a protocol bug; instead of
 // hanging the GPU the thread reports `code` in the device status word and stops waiting for good.
 GG_D void mbar_wait_bounded(uint32_t bar, uint32_t parity, int* status, int code, bool& dead) {
   if (dead) return;
   const long long t0 = clock64();
-  while (!mbar_test_wait(bar, parity)) {
+  while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 400000000ll) {
       dead = true;
       atomicOr(status, code);
