@@ -318,6 +318,8 @@ void gg_destroy(gg_handle h) {
   if (h->net.blob) cudaFree(h->net.blob);
   if (h->net.tc_blob) cudaFree(h->net.tc_blob);
   if (h->variant.blob) cudaFree(h->variant.blob);
+  if (h->variant.tc_blob) cudaFree(h->variant.tc_blob);
+  if (h->variant.d_rows) cudaFree(h->variant.d_rows);
   if (h->d_status) cudaFree(h->d_status);
   if (h->h_ticket_status) cudaFreeHost(h->h_ticket_status);
   if (h->d_lin) cudaFree(h->d_lin);

@@ -100,6 +100,10 @@ struct VariantWeights {
   float* blob = nullptr;
   size_t blob_floats = 0;
   std::vector<size_t> off;
+  // tcgen05 operand images of the per-layer EdgeInjectionLayer.proj.2 weights (hidden 64 / 128)
+  unsigned char* tc_blob = nullptr;
+  size_t tc_stride = 0;      // bytes between consecutive layers' images
+  int* d_rows = nullptr;     // device int: row count of the edge transform (the tensor-core kernel reads M on the device)
 };
 
 }  // namespace gg

@@ -121,15 +121,16 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
             const int row = row0 + warp * RPW + i * rpp + sub;
             if (row < M) {
               float a5[5];
+              const size_t arow = pro.row_index ? (size_t)__ldg(pro.row_index + row) : (size_t)row;
 #pragma unroll
-              for (int j = 0; j < 5; ++j) a5[j] = __ldg(A + (size_t)row * 5 + j);
+              for (int j = 0; j < 5; ++j) a5[j] = __ldg(A + arow * 5 + j);
               float o[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 float sacc = b0[u];
 #pragma unroll
                 for (int j = 0; j < 5; ++j) sacc = fmaf(w0[u][j], a5[j], sacc);
-                o[u] = gelu_erf_tc(sacc);
+                o[u] = pro.relu ? fmaxf(sacc, 0.0f) : gelu_erf_tc(sacc);
               }
               v[i] = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -377,10 +378,19 @@ static int gemm_tc_block(gg_context* ctx, cudaStream_t st, const uint8_t* img, c
     return GG_OK;                                                                                 \
   }
   GG_TC_CASE(0, 0, 16) GG_TC_CASE(1, 0, 17) GG_TC_CASE(2, 0, 18)
-  GG_TC_CASE(0, 1, 19) GG_TC_CASE(1, 1, 20) GG_TC_CASE(0, 2, 21)
+  GG_TC_CASE(0, 1, 19) GG_TC_CASE(1, 1, 20) GG_TC_CASE(0, 2, 21) GG_TC_CASE(2, 2, 22)
 #undef GG_TC_CASE
   set_error("gemm_tc: unsupported act/prologue combination %d/%d", act, pro.mode);
   return GG_ERR_INVALID;
+}
+
+size_t tc_image_bytes_padded(int N, int K) { return (tc_image_bytes(N, K) + 1023) & ~size_t(1023); }
+void tc_pack_weight(const float* W, int ldw, int N, int K, unsigned char* img) { pack_weight(W, ldw, N, K, img); }
+int gemm_tc_image(gg_context* ctx, cudaStream_t st, const unsigned char* img_dev, const float* A, const float* bias,
+                  float* C, const int* m_ptr, long long m_cap, int N, int K, int lda, int ldc, int act, int accumulate,
+                  const TcPrologue& pro) {
+  GG_REQUIRE((N == 64 || N == 128) && (K == 64 || K == 128), "gemm_tc_image: N, K must be 64 or 128");
+  return gemm_tc_block(ctx, st, img_dev, A, bias, C, m_ptr, m_cap, N, K, lda, ldc, act, accumulate, pro);
 }
 
 int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* bias, float* C,

@@ -53,11 +53,19 @@ struct TcPrologue {
   const float2* row_stats = nullptr; // [M] optional (mean, rstd) of every row, precomputed by the producer of A (mode 1, no gvec)
   const float* w0 = nullptr;         // [K,5]  (mode 2)
   const float* b0 = nullptr;         // [K]
+  const int* row_index = nullptr;    // mode 2: attribute row of output row r is row_index[r] (e.g. CSR position -> edge id)
+  int relu = 0;                      // mode 2: ReLU instead of GELU after the first layer (EdgeInjectionLayer, model.py:152-155)
 };
 
 // gemm_tc.cu: tcgen05 path
 int gemm_tc_prepare_weights(gg_context* ctx, const std::vector<float>& blob);
 bool gemm_tc_supported(const gg_context* ctx, int which, int N, int K);
+// One launch over a caller-owned operand image (tc_pack_weight layout; N, K in {64, 128}); used by variants.cu.
+size_t tc_image_bytes_padded(int N, int K);
+void tc_pack_weight(const float* W, int ldw, int N, int K, unsigned char* img);
+int gemm_tc_image(gg_context* ctx, cudaStream_t st, const unsigned char* img_dev, const float* A, const float* bias,
+                  float* C, const int* m_ptr, long long m_cap, int N, int K, int lda, int ldc, int act, int accumulate,
+                  const TcPrologue& pro);
 int gemm_tc(gg_context* ctx, cudaStream_t st, int which, const float* A, const float* bias, float* C,
             const int* m_ptr, long long m_cap, int N, int K, int act, int accumulate,
             const TcPrologue* prologue = nullptr);

@@ -7,9 +7,13 @@
 //   * dense per-node transforms: k_lin (64x64x16 SIMT tiles; optional input / output affine =
 //     eval-mode BatchNorm, bias, activation; strided rows so the jumping-knowledge concat of
 //     GCNTrimapNet is written in place and read by the head without a copy);
-//   * EdgeInjectionLayer: the per-edge MLP 5 -> D -> D is the same tiled kernel with its A operand
-//     generated on the fly (relu(W1 a_e + b1) never touches memory), rows taken in CSR order, so
-//     the scatter-mean over incoming edges is a mean over CONTIGUOUS rows inside the node kernel;
+//   * EdgeInjectionLayer: the per-edge MLP 5 -> D -> D (E x D x D multiply-adds per layer, >90 % of the
+//     variants' FLOPs) runs on the tensor cores for D = 64 / 128: k_tc_gemm (gemm_tc.cu) with the first
+//     layer as its A-operand producer (relu(W1 a_e + b1), 5 -> D per row, never stored), bf16x3 split
+//     operands, fp32 accumulators in TMEM, sigmoid epilogue; the weight images are packed at load time.
+//     Other widths (and gemm_impl = 0) use the SIMT tile kernel with the same on-the-fly A operand.
+//     Rows are taken in CSR order (eid gather), so the scatter-mean over incoming edges is a mean over
+//     CONTIGUOUS rows inside the node kernel;
 //   * message passing: one warp per destination node over the dst-sorted CSR -- GCN aggregation +
 //     BatchNorm + ReLU + residual + gate (k_gcn_block), or GATv2 attention with an online softmax
 //     per head + LayerNorm + GELU + gate (k_gat_layer).  No atomics, fixed summation order.
@@ -18,6 +22,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "resgcn.cuh"
 #include "variants.cuh"
 
 namespace gg {
@@ -353,6 +358,8 @@ __global__ void k_var_softmax3(const float* __restrict__ logits, float* __restri
   probs[(size_t)v * 3 + 2] = e2 * inv;
 }
 
+__global__ void k_var_set_int(int* p, int v) { *p = v; }
+
 // ------------------------------------------------------------------ weights
 // Tensor order of gg_variant_weights (see the header).  BatchNorm groups (weight, bias, mean, var) are
 // folded at load time into (scale, shift, -, -) in double precision.
@@ -437,6 +444,19 @@ int variant_load_weights(gg_context* ctx, const gg_variant_weights* w) {
   vw.blob_floats = blob.size();
   vw.off = off;
   vw.kind = kind; vw.D = D; vw.n_layers = n; vw.heads = H;
+  // tensor-core operand images of the edge-gate second layers (the bulk of the FLOPs: E x D x D per layer)
+  if (vw.tc_blob) { cudaFree(vw.tc_blob); vw.tc_blob = nullptr; }
+  if (D == 64 || D == 128) {
+    vw.tc_stride = tc_image_bytes_padded(D, D);
+    std::vector<unsigned char> img((size_t)n * vw.tc_stride, 0);
+    for (int i = 0; i < n; ++i) {
+      const int t2 = kind == GG_VARIANT_GCN ? 10 + 10 * i + 8 : 8 + 13 * i + 11;      // proj.2.weight
+      tc_pack_weight(&blob[off[t2]], D, D, D, img.data() + (size_t)i * vw.tc_stride);
+    }
+    GG_CUDA_OK(cudaMalloc(&vw.tc_blob, img.size()));
+    GG_CUDA_OK(cudaMemcpy(vw.tc_blob, img.data(), img.size(), cudaMemcpyHostToDevice));
+  }
+  if (!vw.d_rows) GG_CUDA_OK(cudaMalloc(&vw.d_rows, 2 * sizeof(int)));
   vw.loaded = true;
   return GG_OK;
 }
@@ -491,7 +511,17 @@ int variant_forward(gg_context* ctx, Arena& ar, int kind, const float* x, const 
     a.C = C; a.ldc = ldc; a.M = Ni; a.O = O; a.K = K; a.act = act;
     return launch_lin(ctx, st, a, false);
   };
-  auto edge_gate = [&](const float* w1, const float* b1, const float* w2, const float* b2) {
+  const bool edge_tc = vw.tc_blob != nullptr && ctx->gemm_impl == 1 && Ei > 0;
+  if (edge_tc) GG_LAUNCH(ctx, k_var_set_int, 1, 1, 0, st, vw.d_rows, Ei);
+  auto edge_gate = [&](const float* w1, const float* b1, const float* w2, const float* b2, int layer) {
+    if (edge_tc) {
+      // G = sigmoid(relu(W1 a_e + b1) W2^T + b2) on the tensor cores: the first layer is the A-operand
+      // producer (5 -> D per row, never stored), rows in CSR order through the eid gather
+      TcPrologue pro{};
+      pro.mode = 2; pro.w0 = w1; pro.b0 = b1; pro.row_index = eid; pro.relu = 1;
+      return gemm_tc_image(ctx, st, vw.tc_blob + (size_t)layer * vw.tc_stride, edge_attr, b2, G, vw.d_rows, Ei, D, D, 5, D,
+                           2, 0, pro);
+    }
     LinArgs a{};
     a.W = w2; a.bias = b2; a.C = G; a.ldc = D; a.M = Ei; a.O = D; a.K = D; a.act = 2;
     a.attr = edge_attr; a.eid = eid; a.w1 = w1; a.b1 = b1;
@@ -511,7 +541,7 @@ int variant_forward(gg_context* ctx, Arena& ar, int kind, const float* x, const 
       const int b = 10 + 10 * i;
       const float* hprev = allh + (size_t)i * D;
       GG_TRY(lin(hprev, ld, D, T(b + 1), nullptr, xp, D, D, 0));            // GCNConv.lin (no bias)
-      GG_TRY(edge_gate(T(b + 6), T(b + 7), T(b + 8), T(b + 9)));            // EdgeInjectionLayer.proj per edge
+      GG_TRY(edge_gate(T(b + 6), T(b + 7), T(b + 8), T(b + 9), i));         // EdgeInjectionLayer.proj per edge
       GG_TRY(dispatch_cpl(D, [&](auto cpl) -> int {
         constexpr int CPL = decltype(cpl)::value;
         GG_LAUNCH(ctx, k_gcn_block<CPL>, node_blocks, 256, 0, st, xp, hprev, ld, G, rowptr, src, dinv, T(b), T(b + 2),
@@ -547,7 +577,7 @@ int variant_forward(gg_context* ctx, Arena& ar, int kind, const float* x, const 
       const int b = 8 + 13 * i;
       GG_TRY(lin(cur, D, D, T(b + 2), T(b + 3), xl, D, D, 0));
       GG_TRY(lin(cur, D, D, T(b + 4), T(b + 5), xr, D, D, 0));
-      GG_TRY(edge_gate(T(b + 9), T(b + 10), T(b + 11), T(b + 12)));
+      GG_TRY(edge_gate(T(b + 9), T(b + 10), T(b + 11), T(b + 12), i));
       GG_TRY(dispatch_cpl(D, [&](auto cpl) -> int {
         constexpr int CPL = decltype(cpl)::value;
         GG_LAUNCH(ctx, k_gat_layer<CPL>, node_blocks, 256, 0, st, xl, xr, edge_attr, G, rowptr, src, eid, T(b + 6), T(b),
