@@ -337,6 +337,7 @@ void gg_destroy(gg_handle h) {
 int gg_set_option(gg_handle h, const char* key, int value) {
   GG_REQUIRE(h && key, "gg_set_option: null");
   if (!strcmp(key, "gemm_impl")) { h->gemm_impl = value; return GG_OK; }
+  if (!strcmp(key, "knn_legacy")) { h->knn_legacy = value != 0; return GG_OK; }
   if (!strcmp(key, "n_sub")) { h->n_sub = std::max(1, std::min(4, value)); return GG_OK; }
   if (!strcmp(key, "gcn_fused")) { h->gcn_fused = value; return GG_OK; }   // 0 off, 1 auto (>= 24 graphs), 2 always
   set_error("gg_set_option: unknown key %s", key);

@@ -125,6 +125,7 @@ struct gg_context {
   uint64_t attr_done = 0;   // one bit per kernel whose max-dynamic-smem attribute is already set
   int gemm_impl = 1;      // 0 = SIMT fp32 (validation), 1 = tcgen05 bf16x3
   int rs_direct = 1;      // k_region_stats hand-over: 1 = RED.F64 per run, 0 = per-warp smem table
+  int knn_legacy = 0;     // 1 = per-lane top-k kernel k_knn<K> for every size (it otherwise serves N > 2048 only)
   int gcn_fused = 1;      // 1 = per-graph fused residual GCN blocks where they apply (gcn_fused.cu), 0 = layer-wise
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   cudaStream_t s_sub[4] = {nullptr, nullptr, nullptr, nullptr};   // concurrent sub-batch streams

@@ -731,24 +731,17 @@ k_adj_sort(const unsigned long long* __restrict__ keys_all, const int* __restric
 // (graph_builder.py:333-347).  One warp per region; ties on distance -> lower index.
 GG_D bool knn_less(float d, int j, float bd, int bj) { return d < bd || (d == bd && j < bj); }
 
+// Non-local neighbours for graphs of any size.  k_knn (below) keeps ONE sorted candidate list per warp and
+// tests adjacency for the winners only; this routine is its exact fall-back for a row whose nearest
+// regions are mostly adjacent ones.  It is the original form of the kernel -- per-lane sorted lists,
+// adjacency tested before every insertion -- whose insertions run in divergent code, one lane at a
+// time (ncu at config E: 83 % issue slots, 17 of 32 threads active, ~220 instructions per 32
+// candidates; 3.96 ms for 8 x 10^4 regions).
 template <int K>
-__global__ void __launch_bounds__(256)
-k_knn(const float* __restrict__ st_all, const int* __restrict__ label_max,
-      const int2* __restrict__ pairs_all, const int* __restrict__ start_all,
-      int* __restrict__ picks_all, int node_cap, int pair_cap, int k) {
-  const int b = blockIdx.y;
-  const int n = min(label_max[b] + 1, node_cap);
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= n) return;
-  const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
-  const float* mL = st + (size_t)ST_MEAN_L * node_cap;
-  const float* mA = mL + node_cap;
-  const float* mB = mA + node_cap;
-  const int2* pairs = pairs_all + (size_t)b * pair_cap;
-  const int* start = start_all + (size_t)b * (node_cap + 1);
+__device__ void knn_row_exact(const float* __restrict__ mL, const float* __restrict__ mA, const float* __restrict__ mB,
+                              const int2* __restrict__ pairs, const int* __restrict__ start, int n, int i, int k,
+                              int lane, int* __restrict__ out) {
   const float INF = __int_as_float(0x7f800000);
-
   float bd[K];
   int bj[K];
 #pragma unroll
@@ -783,7 +776,6 @@ k_knn(const float* __restrict__ st_all, const int* __restrict__ label_max,
     }
   }
   // merge the 32 sorted lists: k rounds of warp arg-min on (d, j)
-  int* out = picks_all + ((size_t)b * node_cap + i) * k;
   for (int r = 0; r < k; ++r) {
     float d = bd[0];
     int j = bj[0];
@@ -800,6 +792,84 @@ k_knn(const float* __restrict__ st_all, const int* __restrict__ label_max,
       bd[K - 1] = INF; bj[K - 1] = 0x7fffffff;
     }
   }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_knn(const float* __restrict__ st_all, const int* __restrict__ label_max,
+      const int2* __restrict__ pairs_all, const int* __restrict__ start_all,
+      int* __restrict__ picks_all, int node_cap, int pair_cap, int k) {
+  const int b = blockIdx.y;
+  const int n = min(label_max[b] + 1, node_cap);
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float* st = st_all + (size_t)b * ST_FIELDS * node_cap;
+  const float* mL = st + (size_t)ST_MEAN_L * node_cap;
+  const float* mA = mL + node_cap;
+  const float* mB = mA + node_cap;
+  const int2* pairs = pairs_all + (size_t)b * pair_cap;
+  const int* start = start_all + (size_t)b * (node_cap + 1);
+  const float INF = __int_as_float(0x7f800000);
+  int* out = picks_all + ((size_t)b * node_cap + i) * k;
+
+  // ONE sorted list per warp, rank t in lane t: the kl = min(32, k + 8) nearest regions of region i,
+  // adjacent or not.  A sweep step looks at 32 candidates; almost always none beats the list's last
+  // entry (one compare + one ballot).  A candidate that does is inserted by the whole warp (rank by
+  // ballot, shift by shuffle): ~kl ln(n / kl) insertions per row, none of them in divergent code.
+  const int kl = min(32, k + 8);
+  float my_d = INF;                            // this lane's list entry (rank = lane)
+  int my_j = 0x7fffffff;
+  float thr_d = INF;                           // entry of rank kl - 1
+  int thr_j = 0x7fffffff;
+  const float li = mL[i], ai = mA[i], bi = mB[i];
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int j = j0 + lane;
+    float d = INF;
+    if (j < n && j != i) {
+      const float dx = __fsub_rn(li, mL[j]), dy = __fsub_rn(ai, mA[j]), dz = __fsub_rn(bi, mB[j]);
+      d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      if (!(d < INF)) d = INF;                 // inf / nan never selected (np.isfinite filter, …:346)
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, d < INF && knn_less(d, j, thr_d, thr_j));
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const float cd = __shfl_sync(0xffffffffu, d, src);
+      const int cj = __shfl_sync(0xffffffffu, j, src);
+      if (!knn_less(cd, cj, thr_d, thr_j)) continue;          // the list moved on since the ballot
+      const int pos = __popc(__ballot_sync(0xffffffffu, knn_less(my_d, my_j, cd, cj)));   // entries before it
+      const float up_d = __shfl_up_sync(0xffffffffu, my_d, 1);
+      const int up_j = __shfl_up_sync(0xffffffffu, my_j, 1);
+      if (lane == pos) { my_d = cd; my_j = cj; }
+      else if (lane > pos) { my_d = up_d; my_j = up_j; }
+      thr_d = __shfl_sync(0xffffffffu, my_d, kl - 1);
+      thr_j = __shfl_sync(0xffffffffu, my_j, kl - 1);
+    }
+  }
+  // the first k entries that are not spatially adjacent (warp-parallel scan of the sorted pair list);
+  // the list is the exact, ordered top kl, so the result is exact iff k of them are found in it --
+  // otherwise (more than kl - k adjacent regions among the nearest kl: never on SLIC-like maps) the row
+  // is redone by the per-candidate routine
+  int r = 0, t = 0;
+  bool complete = false;
+  for (; t < kl; ++t) {
+    const float d = __shfl_sync(0xffffffffu, my_d, t);
+    const int j = __shfl_sync(0xffffffffu, my_j, t);
+    if (!(d < INF)) { complete = true; break; }               // fewer than kl finite candidates in total: all seen
+    const int lo = min(i, j), hi = max(i, j);
+    bool found = false;
+    for (int q = start[lo] + lane; q < start[lo + 1]; q += 32) found |= pairs[q].y == hi;
+    if (__any_sync(0xffffffffu, found)) continue;
+    if (lane == 0) out[r] = j;
+    if (++r == k) { complete = true; break; }
+  }
+  if (!complete) {
+    knn_row_exact<K>(mL, mA, mB, pairs, start, n, i, k, lane, out);
+    return;
+  }
+  if (lane == 0)
+    for (; r < k; ++r) out[r] = -1;
 }
 
 // Selection form of the same search for images with at most 32*T regions: each lane keeps the
@@ -1844,7 +1914,8 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
             cursor, n_adj, max_shared, ctx->status_word, nc, tc, pc);
   if (k > 0) {
     dim3 grid(ceil_div(nc, 8), B);
-    static const bool knn_legacy = getenv("GG_KNN_LEGACY") != nullptr;
+    static const bool knn_env = getenv("GG_KNN_LEGACY") != nullptr;
+    const bool knn_legacy = knn_env || ctx->knn_legacy;
     if (!knn_legacy && nc <= 2048) {
       if (nc <= 320) GG_LAUNCH(ctx, k_knn_sel<10>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);
       else if (nc <= 512) GG_LAUNCH(ctx, k_knn_sel<16>, grid, 256, 0, st, stats, label_max, pairs, start_adj, picks, nc, pc, k);

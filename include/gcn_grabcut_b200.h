@@ -72,7 +72,10 @@ void gg_destroy(gg_handle h);
  * "gcn_fused": 1 = run the residual GCN blocks as one per-graph kernel (x' on chip) where it
  * applies (hidden 128, graphs of <= 384 regions, tcgen05 transforms) and the batch has at least 24
  * graphs (default), 2 = also for smaller batches, 0 = layer-wise kernels (validation of the fused
- * kernel; env GG_GCN_UNFUSED). */
+ * kernel; env GG_GCN_UNFUSED).
+ * "knn_legacy": 1 = non-local neighbours by the per-lane top-k kernel for every graph size (it otherwise
+ * serves graphs of more than 2048 regions only; validation, env GG_KNN_LEGACY), 0 = selection kernels
+ * (default). */
 int gg_set_option(gg_handle h, const char* key, int value);
 
 /* Device-side status word of the device-pointer entry points: bit0 label / edge index out of

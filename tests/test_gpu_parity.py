@@ -382,6 +382,26 @@ def test_knn_ties_lower_index_rule(gg):
 
 
 # ----------------------------------------------------------------------------- larger configurations
+def test_knn_topk_kernel_vs_oracle(gg):
+    """The per-lane top-k kernel k_knn<K> (graphs of more than 2048 regions in production, also covered at N ~ 10^4 by the config E test) forced on a
+    700-region graph with the "knn_legacy" option: same edge list as the oracle, bit for bit, for k = 4 and 16."""
+    from gcn_grabcut_b200 import _native as nat
+    from gcn_grabcut_b200.synthetic import make_batch
+    from oracle import graph_port
+    imgs, labs = make_batch(1, 333, 1001, 700, seed0=21)
+    h = nat.handle(0)
+    h.set_option("knn_legacy", 1)
+    try:
+        for k in (4, 16):
+            g = gg.build_graph_batch(imgs, labs, gg.SuperpixelGraphConfig(n_segments=700, n_nonlocal=k)).to_graphs(labs)[0]
+            o = graph_port.build_graph(imgs[0], labs[0], n_nonlocal=k)
+            if int(o.stages["knn_ties"]) > 0:
+                o = graph_port.build_graph(imgs[0], labs[0], n_nonlocal=k, tie_break="lower_index")
+            assert g.n_edges == o.n_edges and np.array_equal(g.edge_index, o.edge_index), f"k={k}"
+    finally:
+        h.set_option("knn_legacy", 0)
+
+
 def test_config_c_full_hd_dense_nonlocal(gg):
     """BASELINE config C shape: 1080x1920, ~2000 superpixels, dense non-local edges (k=16),
     against the oracle on one image (the CPU side takes a few seconds per image)."""
