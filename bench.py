@@ -218,6 +218,34 @@ def reference_segment_timing(hidden, layers, n_images=3):
                     "(scikit-image is not installable here), so graph_build excludes SLIC"}
 
 
+def _cpu_legs_child(q, a_dict, rank, cores, sample, extras):
+    """Child process of the `ours` arm: the CPU baseline (and config A's CPU side).  Runs BEFORE the GPU
+    legs, in its own process, so that neither its worker pool nor the numpy / OpenCV / torch thread pools
+    the reference brings up stay behind in the process that drives the GPU (lingering runtime threads cost
+    the streaming submit loop ~10 % of its end-to-end rate)."""
+    try:
+        a = argparse.Namespace(**a_dict)
+        cpu = CpuPath(a, cores)
+        imgs, labs = make_inputs(sample, a.height, a.width, a.segments, seed0=1000 * rank, pool=cpu.pool)
+        cpu.run(imgs[:min(cores, sample)], labs[:min(cores, sample)])            # warm-up (imports, page-in)
+        dt = cpu.run(imgs[:sample], labs[:sample])
+        cpu.close()
+        rec = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": cpu.kind,
+               "sample": f"{sample} images of the same batch in {dt:.2f} s wall, one process per core "
+                         f"(1 BLAS/OpenCV thread each), label maps supplied (SLIC excluded); "
+                         + ("the reference's own files (oracle/_ref) over the third-party shims"
+                            if cpu.kind == "reference" else "oracle port")}
+        ref_a = None
+        if extras:
+            try:
+                ref_a = reference_segment_timing(a.hidden, a.layers)
+            except Exception as e:      # the CPU side of config A is a report, never a reason to lose the line
+                ref_a = {"error": repr(e)}
+        q.put((rec, ref_a))
+    except Exception as e:
+        q.put(({"error": repr(e)}, None))
+
+
 def run_reference(a):
     """--impl reference: the reference's CPU implementation of the path on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -641,20 +669,17 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         sample = a.cpu_sample or max(64, 8 * cores)
         sample = min(sample, a.batch)
-        cpu = CpuPath(a, cores)
-        cpu.run(imgs[:min(cores, sample)], labs[:min(cores, sample)])            # warm-up (imports, page-in)
-        dt = cpu.run(imgs[:sample], labs[:sample])
-        cpu.close()
-        cpu_baseline = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": cpu.kind,
-                        "sample": f"{sample} images of the same batch in {dt:.2f} s wall, one process per core "
-                                  f"(1 BLAS/OpenCV thread each), label maps supplied (SLIC excluded); "
-                                  + ("the reference's own files (oracle/_ref) over the third-party shims"
-                                     if cpu.kind == "reference" else "oracle port")}
-        if extras:
-            try:
-                ref_a = reference_segment_timing(a.hidden, a.layers)
-            except Exception as e:      # the CPU side of config A is a report, never a reason to lose the line
-                ref_a = {"error": repr(e)}
+        ctx_sp = mp.get_context("spawn")
+        q = ctx_sp.Queue()
+        child = ctx_sp.Process(target=_cpu_legs_child, args=(q, vars(a), rank, cores, sample, extras))
+        child.start()
+        try:
+            cpu_baseline, ref_a = q.get(timeout=900)
+        except Exception as e:
+            cpu_baseline, ref_a = {"error": repr(e)}, None
+        child.join(timeout=60)
+        if child.is_alive():
+            child.terminate()
 
     import torch
     import torch.distributed as dist
