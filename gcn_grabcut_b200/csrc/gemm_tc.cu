@@ -20,6 +20,13 @@
 //     x 32 columns per instruction), apply bias / activation / accumulate, store fp32 rows and
 //     hand the accumulator back (mbarrier) -- the epilogue of tile i overlaps the producers'
 //     work on tile i+1 and MMA(i+1).
+// Measured with clock64 stamps (config B, 4 tiles per CTA, ~20 000 cycles per tile): A loads + prologue
+// 9-12 k cycles (every CTA bursts at once), split + store 2.5 k, the tcgen05.mma issue ~5 k (the issuing
+// thread stalls on the tensor pipe's queue), epilogue 9-16 k with erf-GELU (now the 16-instruction
+// evaluation).  Two restructurings were measured SLOWER (0.165 against 0.123 ms for the three plain
+// transforms of config B): a 25th warp that only issues the MMAs (800 threads cap the kernel at 72
+// registers -- warps are allocated in fours -- and the producers spill), and requesting the next tile's
+// rows right after the split, before the MMA issue.
 // SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UBLKCP (bulk TMA).
 #include <cuda_bf16.h>
 
@@ -274,7 +281,7 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float vv = __uint_as_float(rr[4 * i + u]) + bp[u] + pp[u];
-              if (ACT == 1) vv = gelu_erf_tc(vv);
+              if (ACT == 1) vv = gelu_fast_tc(vv);
               if (ACT == 2) vv = 1.0f / (1.0f + expf(-vv));
               op[u] = vv;
             }
