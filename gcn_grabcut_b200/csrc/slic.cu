@@ -117,6 +117,10 @@ GG_D int reflect_sym(int i, int n) {          // scipy.ndimage mode="reflect": d
   return i;
 }
 
+// RT > 0: Gaussian radius known at compile time (sigma = 1 -> 4): the tile width is a constant, so the
+// index decompositions are multiply-shifts instead of runtime integer divisions (they were half of the
+// kernel's 1143 warp-instructions per 32 pixels) and the tap loops unroll; RT == 0: runtime radius.
+template <int RT>
 __global__ void __launch_bounds__(256)
 k_slic_features(const uint8_t* __restrict__ bgr, const double* __restrict__ lin_lut, LabF M, GaussW gw,
                 const int* __restrict__ minmax, int H, int W, float inv_comp, float4* __restrict__ feat) {
@@ -126,7 +130,7 @@ k_slic_features(const uint8_t* __restrict__ bgr, const double* __restrict__ lin_
   __shared__ float s_v[3][SF_T][TP + 1];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lin[i] = (float)lin_lut[i];
   __syncthreads();
-  const int b = blockIdx.z, y0 = blockIdx.y * SF_T, x0 = blockIdx.x * SF_T, r = gw.r;
+  const int b = blockIdx.z, y0 = blockIdx.y * SF_T, x0 = blockIdx.x * SF_T, r = RT > 0 ? RT : gw.r;
   const uint8_t* img = bgr + (size_t)b * H * W * 3;
   const float mn = ord2f(minmax[2 * b]), rng = ord2f(minmax[2 * b + 1]) - mn;
   const float inv = rng != 0.0f ? 1.0f / rng : 1.0f;
@@ -144,7 +148,12 @@ k_slic_features(const uint8_t* __restrict__ bgr, const double* __restrict__ lin_
   for (int i = threadIdx.x; i < 3 * SF_T * tw; i += blockDim.x) {
     const int c = i / (SF_T * tw), rem = i - c * SF_T * tw, ty = rem / tw, tx = rem - ty * tw;
     float s = 0.0f;
-    for (int d = -r; d <= r; ++d) s = fmaf(gw.w[d + r], s_in[c][ty + r + d][tx], s);
+    if (RT > 0) {
+#pragma unroll
+      for (int d = 0; d <= 2 * RT; ++d) s = fmaf(gw.w[d], s_in[c][ty + d][tx], s);
+    } else {
+      for (int d = -r; d <= r; ++d) s = fmaf(gw.w[d + r], s_in[c][ty + r + d][tx], s);
+    }
     s_v[c][ty][tx] = s;
   }
   __syncthreads();
@@ -156,7 +165,12 @@ k_slic_features(const uint8_t* __restrict__ bgr, const double* __restrict__ lin_
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float s = 0.0f;
-      for (int d = -r; d <= r; ++d) s = fmaf(gw.w[d + r], s_v[c][ty][tx + r + d], s);
+      if (RT > 0) {
+#pragma unroll
+        for (int d = 0; d <= 2 * RT; ++d) s = fmaf(gw.w[d], s_v[c][ty][tx + d], s);
+      } else {
+        for (int d = -r; d <= r; ++d) s = fmaf(gw.w[d + r], s_v[c][ty][tx + r + d], s);
+      }
       v[c] = s;
     }
     float L, A, Bv;
@@ -599,7 +613,8 @@ int slic_labels(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, in
   }
   {
     dim3 grid(ceil_div(W, SF_T), ceil_div(H, SF_T), B);
-    GG_LAUNCH(ctx, k_slic_features, grid, 256, 0, st, bgr, ctx->d_lin, M, gw, minmax, H, W, (float)(1.0 / compactness), feat);
+    if (gw.r == 4) GG_LAUNCH(ctx, k_slic_features<4>, grid, 256, 0, st, bgr, ctx->d_lin, M, gw, minmax, H, W, (float)(1.0 / compactness), feat);
+    else GG_LAUNCH(ctx, k_slic_features<0>, grid, 256, 0, st, bgr, ctx->d_lin, M, gw, minmax, H, W, (float)(1.0 / compactness), feat);
   }
   {
     dim3 grid(ceil_div(K, 256), B);
