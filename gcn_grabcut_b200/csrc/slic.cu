@@ -446,11 +446,15 @@ k_slic_cc_merge(const int32_t* __restrict__ labels, int H, int W, int* __restric
 __global__ void __launch_bounds__(256)
 k_slic_cc_flatten(int HW, int* __restrict__ L, int* __restrict__ size) {
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned act = __ballot_sync(0xffffffffu, i < HW);
   if (i >= HW) return;
   int* Lb = L + (size_t)b * HW;
   const int r = cc_find(Lb, i);
   Lb[i] = r;
-  atomicAdd(&size[(size_t)b * HW + r], 1);
+  // neighbouring pixels mostly share their root: one atomic per distinct root of the warp (a few hundred
+  // roots per image collect 150k increments -- per-pixel atomics serialise on them)
+  const unsigned grp = __match_any_sync(act, r);
+  if ((threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&size[(size_t)b * HW + r], __popc(grp));
 }
 // roots only: a small component points at the component of the pixel above / left of its first pixel
 __global__ void __launch_bounds__(256)
@@ -473,12 +477,19 @@ k_slic_cc_target(int H, int W, const int* __restrict__ L, const int* __restrict_
 // kept[i] = 1 for the roots that survive; block counts for the scan
 __global__ void __launch_bounds__(1024)
 k_slic_cc_count(int HW, const int* __restrict__ target, int* __restrict__ block_cnt, int n_blocks) {
-  __shared__ int scratch[40];
+  __shared__ int s_w[32];
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int kept = (i < HW && target[(size_t)b * HW + i] == i) ? 1 : 0;
-  int total;
-  block_exclusive_scan(kept, scratch, &total);
-  if (threadIdx.x == 0) block_cnt[(size_t)b * n_blocks + blockIdx.x] = total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool kept = i < HW && target[(size_t)b * HW + i] == i;
+  const unsigned m = __ballot_sync(0xffffffffu, kept);          // kept roots are sparse: one ballot per warp
+  if (lane == 0) s_w[wid] = __popc(m);
+  __syncthreads();
+  if (wid == 0) {
+    int v = s_w[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) block_cnt[(size_t)b * n_blocks + blockIdx.x] = v;
+  }
 }
 __global__ void __launch_bounds__(1024)
 k_slic_cc_scan_blocks(int* __restrict__ block_cnt, int n_blocks, int32_t* __restrict__ n_labels) {
@@ -500,12 +511,26 @@ k_slic_cc_scan_blocks(int* __restrict__ block_cnt, int n_blocks, int32_t* __rest
 __global__ void __launch_bounds__(1024)
 k_slic_cc_newid(int HW, const int* __restrict__ target, const int* __restrict__ block_cnt, int n_blocks,
                 int* __restrict__ newid) {
-  __shared__ int scratch[40];
+  __shared__ int s_w[32];
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int kept = (i < HW && target[(size_t)b * HW + i] == i) ? 1 : 0;
-  int total;
-  const int ex = block_exclusive_scan(kept, scratch, &total);
-  if (kept) newid[(size_t)b * HW + i] = block_cnt[(size_t)b * n_blocks + blockIdx.x] + ex;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool kept = i < HW && target[(size_t)b * HW + i] == i;
+  const unsigned m = __ballot_sync(0xffffffffu, kept);
+  if (lane == 0) s_w[wid] = __popc(m);
+  __syncthreads();
+  if (wid == 0) {                                               // exclusive prefix of the 32 warp counts
+    const int v = s_w[lane];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    s_w[lane] = inc - v;
+  }
+  __syncthreads();
+  if (kept)
+    newid[(size_t)b * HW + i] = block_cnt[(size_t)b * n_blocks + blockIdx.x] + s_w[wid] + __popc(m & ((1u << lane) - 1u));
 }
 __global__ void __launch_bounds__(256)
 k_slic_cc_relabel(int HW, const int* __restrict__ L, const int* __restrict__ target, const int* __restrict__ newid,
