@@ -222,6 +222,7 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
   __shared__ float2 s_q2[SA_MAXC * SA_MAXC];
   __shared__ int s_sum[SA_MAXC * SA_MAXC][6];
   __shared__ int s_rowcell[SA_TY], s_colcell[SA_TX];
+  __shared__ int s_cid[SA_MAXC * SA_MAXC];         // global centre index of a slot (the label a pixel gets)
   const int b = blockIdx.z, y0 = blockIdx.y * SA_TY, x0 = blockIdx.x * SA_TX;
   const int K = g.gy * g.gx;
   const int ci0 = max(slic_cell(y0, g.sy, g.ty, g.gy) - NEIGH, 0);
@@ -236,6 +237,7 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
   for (int i = threadIdx.x; i < nci * ncj; i += blockDim.x) {
     const int k = (ci0 + i / ncj) * g.gx + cj0 + i % ncj;
     const float cy = cb[k * 5], cx = cb[k * 5 + 1];
+    s_cid[i] = k;
     s_yx[i] = NEIGH == 1 ? make_float2(cy * inv_step, cx * inv_step) : make_float2(cy, cx);
     s_col[i] = make_float4(cb[k * 5 + 2], cb[k * 5 + 3], cb[k * 5 + 4], 0.0f);
     if (NEIGH == 1) {
@@ -328,8 +330,7 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
       }
       if (best_slot < 0) best_slot = home_slot;           // no window reaches the pixel (cannot happen on a regular grid)
       }
-      const int bi = best_slot / ncj;
-      labels[((size_t)b * H + y) * W + x] = (ci0 + bi) * g.gx + cj0 + (best_slot - bi * ncj);
+      labels[((size_t)b * H + y) * W + x] = s_cid[best_slot];
     }
     // per-centre sums: the lanes of a warp that chose the same centre are reduced first (one
     // shared-memory atomic per field and distinct centre instead of one per pixel)
