@@ -330,7 +330,7 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
       }
       if (best_slot < 0) best_slot = home_slot;           // no window reaches the pixel (cannot happen on a regular grid)
       }
-      labels[((size_t)b * H + y) * W + x] = s_cid[best_slot];
+      if (labels) labels[((size_t)b * H + y) * W + x] = s_cid[best_slot];
     }
     // per-centre sums: the lanes of a warp that chose the same centre are reduced first (one
     // shared-memory atomic per field and distinct centre instead of one per pixel)
@@ -647,8 +647,10 @@ int slic_labels(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, in
     GG_LAUNCH(ctx, k_slic_init, grid, 256, 0, st, feat, g, H, W, cen, sums);
     dim3 ga(ceil_div(W, SA_TX), ceil_div(H, SA_TY), B);
     for (int it = 0; it < max_iter; ++it) {
-      if (neigh >= 2) GG_LAUNCH(ctx, k_slic_assign<2>, ga, 256, 0, st, feat, cen, g, H, W, labels, sums);
-      else GG_LAUNCH(ctx, k_slic_assign<1>, ga, 256, 0, st, feat, cen, g, H, W, labels, sums);
+      // only the labels of the last iteration are read (the centre sums are accumulated inside the kernel)
+      int32_t* lab_out = it == max_iter - 1 ? labels : nullptr;
+      if (neigh >= 2) GG_LAUNCH(ctx, k_slic_assign<2>, ga, 256, 0, st, feat, cen, g, H, W, lab_out, sums);
+      else GG_LAUNCH(ctx, k_slic_assign<1>, ga, 256, 0, st, feat, cen, g, H, W, lab_out, sums);
       GG_LAUNCH(ctx, k_slic_update, grid, 256, 0, st, K, cen, sums);
     }
   }
