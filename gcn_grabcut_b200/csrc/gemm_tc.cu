@@ -282,7 +282,7 @@ k_tc_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, const f
             for (int u = 0; u < 4; ++u) {
               float vv = __uint_as_float(rr[4 * i + u]) + bp[u] + pp[u];
               if (ACT == 1) vv = gelu_fast_tc(vv);
-              if (ACT == 2) vv = 1.0f / (1.0f + expf(-vv));
+              if (ACT == 2) vv = sigmoid_fast_tc(vv);
               op[u] = vv;
             }
             *reinterpret_cast<float4*>(crow + 4 * i) = o;

@@ -127,6 +127,13 @@ GG_HD uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// 1 / (1 + 2^(-x log2 e)) with the approximate ex2 / rcp units (2 + 1 ulp)
+GG_D float sigmoid_fast_tc(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 GG_D float gelu_erf_tc(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // Exact-erf GELU x Phi(x) with Phi from the complementary error function in Abramowitz-Stegun form 7.1.26
 // (|error of erf| <= 1.5e-7, no cancellation on the negative side): 16 instructions instead of erff's 30
