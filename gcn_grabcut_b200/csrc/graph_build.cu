@@ -253,7 +253,10 @@ __device__ __noinline__ void pair_emit(unsigned long long* keys, int* cnts, int 
 // DIRECT: finished runs go straight to the global accumulators (one RED.F64 per field and run)
 // instead of through the per-warp shared-memory table: ~14x more L2 atomics, ~80 fewer
 // instructions per row.
-template <int RS_WARPS, int MINB, bool DIRECT, bool VELT>
+// PAIRS: the kernel also collects the adjacency transitions (label pairs + shared-boundary counts); with
+// PAIRS == false that is k_adjacency_pairs' job (a labels-only pass) and this kernel carries neither the
+// pair cache nor the run-aggregation registers (measured by ablation: 0.127 of the 0.71 ms).
+template <int RS_WARPS, int MINB, bool DIRECT, bool VELT, bool PAIRS>
 __global__ void __launch_bounds__(RS_WARPS * 32, MINB)
 k_region_stats(const RegionStatsParams p) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -401,6 +404,7 @@ k_region_stats(const RegionStatsParams p) {
 
   // one undirected pair (a, b, n), warp-uniform: bump the cached slot or take a slot over
   auto pair_add = [&](int a, int b_, int n) {
+    if (!PAIRS) return;
     const int lo = min(a, b_), hi = max(a, b_);
     if (lo == hi || (unsigned)lo >= node_cap || (unsigned)hi >= node_cap) return;
     const unsigned hit = __ballot_sync(0xffffffffu, pk_lo == lo && pk_hi == hi);
@@ -443,6 +447,7 @@ k_region_stats(const RegionStatsParams p) {
         cnt = bnd = 0;
         aL = aA = aB = aL2 = aA2 = aB2 = aH = aS = aV = aG = aGs = 0.0;
       }
+      if (!PAIRS) return;
       // down-neighbour pairs of the finished runs, one insertion per distinct pair
       const unsigned long long key =
           ((unsigned long long)(uint32_t)min(cur, nxt) << 32) | (uint32_t)max(cur, nxt);
@@ -551,7 +556,7 @@ k_region_stats(const RegionStatsParams p) {
     // ---- adjacency transitions (graph_builder.py:267-281)
     // right neighbour: identical transitions are run-aggregated down the column in registers;
     // down neighbour: emitted with the run hand-over above.
-    {
+    if (PAIRS) {
       const int cb = (lab_r != lab_c) ? lab_r : -1;
       const bool changed = (lab_c != rp_a) | (cb != rp_b);
       unsigned em = __ballot_sync(0xffffffffu, changed && rp_b >= 0 && valid);
@@ -564,7 +569,7 @@ k_region_stats(const RegionStatsParams p) {
       if (changed) { rp_a = lab_c; rp_b = cb; rp_cnt = 0; }
       rp_cnt += 1;
     }
-    if (p.connectivity == 8) {
+    if (PAIRS && p.connectivity == 8) {
       // the two diagonals below: (y+1, x+1) and (y+1, x-1); outside the image -> own label
       int dn_r = __shfl_down_sync(0xffffffffu, lab_dn, 1);
       int dn_l = __shfl_up_sync(0xffffffffu, lab_dn, 1);
@@ -597,7 +602,7 @@ k_region_stats(const RegionStatsParams p) {
   //      at the bottom of the image), pending right-neighbour runs, the pair cache, the table
   const unsigned fm = __ballot_sync(0xffffffffu, cnt > 0 && valid);
   if (fm) flush_lanes(fm, y_end, lab_c);
-  {
+  if (PAIRS) {
     unsigned em = __ballot_sync(0xffffffffu, rp_b >= 0 && valid);
     while (em) {
       const int src = __ffs(em) - 1;
@@ -606,10 +611,144 @@ k_region_stats(const RegionStatsParams p) {
                __shfl_sync(0xffffffffu, rp_cnt, src));
     }
   }
-  if (pk_lo >= 0) pair_emit(keys, cnts, p.table_cap, pk_lo, pk_hi, pk_n, p.status);
+  if (PAIRS && pk_lo >= 0) pair_emit(keys, cnts, p.table_cap, pk_lo, pk_hi, pk_n, p.status);
   for (int s_ = 0; s_ < RS_SLOTS; ++s_) evict_slot(s_, __shfl_sync(0xffffffffu, mytag, s_));
   lmax = warp_max_i(lmax);
   if (lane == 0 && lmax >= 0) atomicMax(&p.label_max[b], lmax);
+}
+
+// ============================================================================ S0b
+// Adjacency transitions (graph_builder.py:265-286) as a labels-only pass: one warp per 32-column x
+// `rows`-row strip, lane = column, walking down the rows.  Right-neighbour transitions are run-aggregated
+// down the column in registers (a vertical boundary repeats the same pair row after row), down-neighbour
+// (and diagonal) transitions are aggregated across the lanes by key; distinct pairs go through a 32-entry
+// register cache (lane = slot) to the per-image open-addressing hash table -- the bookkeeping that used to
+// ride inside k_region_stats, without its 119 registers and float64 chains around it.
+struct AdjParams {
+  const int32_t* labels;
+  unsigned long long* pair_keys;
+  int* pair_cnts;
+  int* status;
+  int B, H, W, node_cap, table_cap, connectivity, n_sx, n_sy, rows;
+};
+
+constexpr int ADJ_QUEUE = 128;      // pending (lo, hi, count) records per warp
+
+__global__ void __launch_bounds__(256)
+k_adjacency_pairs(const AdjParams p) {
+  __shared__ int s_q[8][ADJ_QUEUE][3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_tasks = (long long)p.B * p.n_sy * p.n_sx;
+  if (task >= n_tasks) return;
+  const int sx = (int)(task % p.n_sx);
+  const int sy = (int)((task / p.n_sx) % p.n_sy);
+  const int b = (int)(task / ((long long)p.n_sx * p.n_sy));
+  const int H = p.H, W = p.W;
+  const int x = sx * 32 + lane;
+  const bool valid = x < W;
+  const int xc = valid ? x : W - 1;
+  const int y_begin = sy * p.rows, y_end = min(H, y_begin + p.rows);
+  const int32_t* lab = p.labels + (size_t)b * H * W;
+  unsigned long long* keys = p.pair_keys + (size_t)b * p.table_cap;
+  int* cnts = p.pair_cnts + (size_t)b * p.table_cap;
+  const unsigned node_cap = (unsigned)p.node_cap;
+  const bool is_l0 = lane == 0, is_l31 = lane == 31;
+  const bool own_r = x >= W - 1;                       // no pixel to the right
+  const bool edge_lane = (is_l0 || is_l31) && valid;
+  const int ldelta = is_l0 ? (x > 0 ? -1 : 0) : (x + 1 < W ? 1 : 0);
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // Finished records are queued lane-parallel (slot = ballot prefix, the fill level is warp-uniform) and
+  // the queue is drained lane-parallel into the hash table: no warp-uniform loop over the lanes that
+  // have something to report (such loops were 60 % of this kernel's instructions).
+  int (*q)[3] = s_q[wid];
+  int qn = 0;
+  auto drain = [&]() {
+    __syncwarp();
+    for (int i = lane; i < qn; i += 32) {
+      const int a = q[i][0], c = q[i][1], n = q[i][2];
+      const int lo = min(a, c), hi = max(a, c);
+      if (lo != hi && (unsigned)lo < node_cap && (unsigned)hi < node_cap)
+        pair_emit(keys, cnts, p.table_cap, lo, hi, n, p.status);
+    }
+    __syncwarp();
+    qn = 0;
+  };
+  auto push = [&](bool want, int a, int c, int n) {    // called by the whole warp
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const int k = __popc(m);
+    if (qn + k > ADJ_QUEUE) drain();
+    if (want) {
+      const int pos = qn + __popc(m & lt_mask);
+      q[pos][0] = a; q[pos][1] = c; q[pos][2] = n;
+    }
+    qn += k;
+  };
+  // transitions towards `other` (per lane): equal neighbouring transitions along the row are merged --
+  // the first lane of a stretch reports the stretch length
+  auto push_stretches = [&](bool trans, int mine, int other) {
+    const unsigned tm = __ballot_sync(0xffffffffu, trans);
+    if (!tm) return;
+    const int lm = __shfl_up_sync(0xffffffffu, mine, 1), lo_ = __shfl_up_sync(0xffffffffu, other, 1);
+    const bool head = trans && (is_l0 || !(tm >> (lane - 1) & 1u) || lm != mine || lo_ != other);
+    const unsigned hm = __ballot_sync(0xffffffffu, head);
+    const unsigned stop = (hm | ~tm) & ~lt_mask & ~(1u << lane);     // next head or non-transition lane above me
+    const int len = (stop ? __ffs(stop) - 1 : 32) - lane;
+    push(head, mine, other, len);
+  };
+
+  const uint32_t off0 = (uint32_t)(y_begin * W + xc);
+  int lab_c = valid ? lab[off0] : -1;
+  int e_lab = edge_lane ? lab[off0 + ldelta] : 0;      // outer label neighbour of the edge lanes
+  int rp_a = -1, rp_b = -1, rp_cnt = 0;                // run of identical right-neighbour transitions
+  // the rows below are loaded two iterations ahead: the register hand-down at the end of an iteration
+  // (row y+2 becomes row y+1) then never waits for a load issued in the same iteration
+  auto load_row = [&](int yy, int fallback, int& c, int& e) {   // labels of row yy (below the image: `fallback`)
+    c = fallback; e = 0;
+    if (yy < H) {
+      const int32_t* pl = lab + (size_t)yy * W + xc;
+      if (valid) c = pl[0];
+      if (edge_lane) e = pl[ldelta];
+    }
+  };
+  int lab_dn, e_lab_n, lab_dn2, e_lab_n2;
+  load_row(y_begin + 1, lab_c, lab_dn, e_lab_n);
+  load_row(y_begin + 2, lab_dn, lab_dn2, e_lab_n2);
+  for (int y = y_begin; y < y_end; ++y) {
+    const bool has_dn = y + 1 < H;
+    int lab_dn3, e_lab_n3;                             // row y+3
+    load_row(y + 3, lab_dn2, lab_dn3, e_lab_n3);
+    int lab_r = __shfl_down_sync(0xffffffffu, lab_c, 1);
+    if (is_l31) lab_r = e_lab;
+    if (own_r) lab_r = lab_c;
+    // right neighbour, run-aggregated down the column: a finished run is one record
+    {
+      const int cb = (lab_r != lab_c) ? lab_r : -1;
+      const bool changed = (lab_c != rp_a) | (cb != rp_b);
+      push(changed && rp_b >= 0 && valid, rp_a, rp_b, rp_cnt);
+      if (changed) { rp_a = lab_c; rp_b = cb; rp_cnt = 0; }
+      rp_cnt += 1;
+    }
+    // down neighbour
+    push_stretches(valid && lab_dn != lab_c, lab_c, lab_dn);
+    if (p.connectivity == 8) {
+      // the two diagonals below: (y+1, x+1) and (y+1, x-1); outside the image -> own label
+      int dn_r = __shfl_down_sync(0xffffffffu, lab_dn, 1);
+      int dn_l = __shfl_up_sync(0xffffffffu, lab_dn, 1);
+      if (is_l31) dn_r = e_lab_n;
+      if (is_l0) dn_l = e_lab_n;
+      if (own_r || !has_dn) dn_r = lab_c;
+      if (x == 0 || !has_dn) dn_l = lab_c;
+      push_stretches(valid && dn_r != lab_c, lab_c, dn_r);
+      push_stretches(valid && dn_l != lab_c, lab_c, dn_l);
+    }
+    lab_c = lab_dn; lab_dn = lab_dn2; lab_dn2 = lab_dn3;
+    e_lab = e_lab_n; e_lab_n = e_lab_n2; e_lab_n2 = e_lab_n3;
+  }
+  push(rp_b >= 0 && valid, rp_a, rp_b, rp_cnt);
+  drain();
 }
 
 // ============================================================================ S1
@@ -1891,12 +2030,30 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     // blocks/SM (102 registers), 2 = 4 warps x 4 blocks/SM; +4 = keep the F2F conversions (no Veltkamp)
     static const int variant = getenv("GG_RS_VARIANT") ? atoi(getenv("GG_RS_VARIANT")) : 6;
     const int direct = forced >= 0 ? forced : ctx->rs_direct;
+    // adjacency transitions: inside k_region_stats (GG_RS_PAIRS=1) or by the labels-only kernel (default)
+    static const int pairs_inside = getenv("GG_RS_PAIRS") ? atoi(getenv("GG_RS_PAIRS")) : 0;
 #define GG_RS_LAUNCH(BIT, W_, MINB_, DIRECT_, VELT_)                                                              \
     do {                                                                                                          \
-      GG_SMEM_ATTR_ONCE(ctx, BIT, (k_region_stats<W_, MINB_, DIRECT_, VELT_>), rs_smem_bytes(W_, DIRECT_));        \
-      GG_LAUNCH(ctx, (k_region_stats<W_, MINB_, DIRECT_, VELT_>), ceil_div(tasks, W_), W_ * 32,                    \
+      GG_SMEM_ATTR_ONCE(ctx, BIT, (k_region_stats<W_, MINB_, DIRECT_, VELT_, true>), rs_smem_bytes(W_, DIRECT_));  \
+      GG_LAUNCH(ctx, (k_region_stats<W_, MINB_, DIRECT_, VELT_, true>), ceil_div(tasks, W_), W_ * 32,              \
                 rs_smem_bytes(W_, DIRECT_), st, p);                                                               \
     } while (0)
+#define GG_RS_LAUNCH_NP(BIT, W_, MINB_, DIRECT_, VELT_)                                                           \
+    do {                                                                                                          \
+      GG_SMEM_ATTR_ONCE(ctx, BIT, (k_region_stats<W_, MINB_, DIRECT_, VELT_, false>), rs_smem_bytes(W_, DIRECT_)); \
+      GG_LAUNCH(ctx, (k_region_stats<W_, MINB_, DIRECT_, VELT_, false>), ceil_div(tasks, W_), W_ * 32,             \
+                rs_smem_bytes(W_, DIRECT_), st, p);                                                               \
+    } while (0)
+    if (!pairs_inside) {
+      AdjParams ap;
+      ap.labels = labels; ap.pair_keys = pkeys; ap.pair_cnts = pcnts; ap.status = ctx->status_word;
+      ap.B = B; ap.H = H; ap.W = W; ap.node_cap = nc; ap.table_cap = tc; ap.connectivity = cfg.connectivity;
+      ap.rows = 32; ap.n_sx = ceil_div(W, 32); ap.n_sy = ceil_div(H, ap.rows);
+      const long long atasks = (long long)B * ap.n_sx * ap.n_sy;
+      GG_LAUNCH(ctx, k_adjacency_pairs, ceil_div(atasks, 8), 256, 0, st, ap);
+      if (!direct) GG_RS_LAUNCH_NP(52, 8, 2, false, true);
+      else GG_RS_LAUNCH_NP(56, 4, 4, true, false);
+    } else
     if (!direct) GG_RS_LAUNCH(30, 8, 2, false, true);
     else if (variant == 0) GG_RS_LAUNCH(0, 8, 2, true, true);
     else if (variant == 1) GG_RS_LAUNCH(42, 4, 5, true, true);
@@ -1905,6 +2062,7 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
     else if (variant == 5) GG_RS_LAUNCH(45, 4, 5, true, false);
     else GG_RS_LAUNCH(46, 4, 4, true, false);
 #undef GG_RS_LAUNCH
+#undef GG_RS_LAUNCH_NP
   }
   {
     dim3 grid(ceil_div(nc, 256), B);
