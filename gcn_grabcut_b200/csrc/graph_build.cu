@@ -2048,7 +2048,8 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
       AdjParams ap;
       ap.labels = labels; ap.pair_keys = pkeys; ap.pair_cnts = pcnts; ap.status = ctx->status_word;
       ap.B = B; ap.H = H; ap.W = W; ap.node_cap = nc; ap.table_cap = tc; ap.connectivity = cfg.connectivity;
-      ap.rows = 32; ap.n_sx = ceil_div(W, 32); ap.n_sy = ceil_div(H, ap.rows);
+      static const int adj_rows = getenv("GG_ADJ_ROWS") ? atoi(getenv("GG_ADJ_ROWS")) : 32;
+      ap.rows = adj_rows > 0 ? adj_rows : 32; ap.n_sx = ceil_div(W, 32); ap.n_sy = ceil_div(H, ap.rows);
       const long long atasks = (long long)B * ap.n_sx * ap.n_sy;
       GG_LAUNCH(ctx, k_adjacency_pairs, ceil_div(atasks, 8), 256, 0, st, ap);
       if (!direct) GG_RS_LAUNCH_NP(52, 8, 2, false, true);
