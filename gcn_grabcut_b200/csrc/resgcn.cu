@@ -78,8 +78,11 @@ __global__ void k_node_meta(const int64_t* __restrict__ graph_off, int n_graphs,
 
 // ------------------------------------------------------------------ input stage
 // h = GELU(LN(W_in BN(x) + b)) * (1 + sigmoid(W2 GELU(W1 prior + b1) + b2)); z = w0 h
-// (model.py:516-518, 191-213, 465-476).  One warp per node, lane owns channels lane+32j.
-template <int CPL>   // channels per lane = D/32
+// (model.py:516-518, 191-213, 465-476).  One warp per group of R nodes, lane owns channels lane+32j:
+// every weight read from shared memory feeds R nodes (the kernel is bound by the shared-memory /
+// shuffle pipe: R = 1 needs 5 such instructions per 4 FMAs, R = 4 needs 8 per 16); the arithmetic of
+// a node does not depend on R.
+template <int CPL, int R>   // channels per lane = D/32, nodes per warp iteration
 __global__ void __launch_bounds__(256)
 k_input_stage(const float* __restrict__ x, const float* __restrict__ wb, NetOffsets o,
               const int* __restrict__ sizes, float* __restrict__ h, float* __restrict__ z,
@@ -98,65 +101,109 @@ k_input_stage(const float* __restrict__ x, const float* __restrict__ wb, NetOffs
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int nt = sizes[0];
   const float jk0 = wb[o.jk_w];
-  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < nt; v += warps) {
-    float xv = 0.0f, xraw = 0.0f;
-    if (lane < 19) {
-      xraw = x[(size_t)v * 19 + lane];
-      xv = xraw * wb[o.bn_scale + lane] + wb[o.bn_shift + lane];
+  const float bn_s = lane < 19 ? wb[o.bn_scale + lane] : 0.0f, bn_b = lane < 19 ? wb[o.bn_shift + lane] : 0.0f;
+  for (int v0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; v0 < nt; v0 += warps * R) {
+    float xv[R], xraw[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      xraw[r] = 0.0f;
+      if (lane < 19) xraw[r] = x[(size_t)min(v0 + r, nt - 1) * 19 + lane];
+      xv[r] = xraw[r] * bn_s + bn_b;
     }
-    float t[CPL];
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) t[j] = wb[o.b_in + lane + 32 * j];
-    for (int kk = 0; kk < 19; ++kk) {
-      const float xk = __shfl_sync(0xffffffffu, xv, kk);
-#pragma unroll
-      for (int j = 0; j < CPL; ++j) t[j] = fmaf(s_win[(lane + 32 * j) * 19 + kk], xk, t[j]);
-    }
-    float sum = 0.0f;
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) sum += t[j];
-    const float mean = warp_sum(sum) / (float)D;
-    float sq = 0.0f;
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) { const float d = t[j] - mean; sq += d * d; }
-    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + 1e-5f);
-    // prior booster: q hidden units, lane owns units lane, lane+32, ...
-    const float p0 = __shfl_sync(0xffffffffu, xraw, 16), p1 = __shfl_sync(0xffffffffu, xraw, 17),
-                p2 = __shfl_sync(0xffffffffu, xraw, 18);
-    float boost[CPL];
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) boost[j] = wb[o.pb2_b + lane + 32 * j];
-    for (int u0 = 0; u0 < q; u0 += 32) {
-      const int u = u0 + lane;
-      float hu = 0.0f;
-      if (u < q)
-        hu = gelu_fast(fmaf(s_pb0[u * 3 + 2], p2, fmaf(s_pb0[u * 3 + 1], p1,
-                      fmaf(s_pb0[u * 3], p0, wb[o.pb0_b + u]))));
-      const int lim = min(32, q - u0);
-      for (int s = 0; s < lim; ++s) {
-        const float hs = __shfl_sync(0xffffffffu, hu, s);
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) boost[j] = fmaf(s_pb2[(u0 + s) * D + lane + 32 * j], hs, boost[j]);
-      }
-    }
-    float hsum = 0.0f, hvv[CPL];
+    float t[R][CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-      const int c = lane + 32 * j;
-      const float ln = (t[j] - mean) * rstd * wb[o.ln_in_g + c] + wb[o.ln_in_b + c];
-      const float hv = gelu_fast(ln) * (1.0f + sigmoidf(boost[j]));
-      h[(size_t)v * D + c] = hv;
-      z[(size_t)v * D + c] = jk0 * hv;
-      hvv[j] = hv;
-      hsum += hv;
-    }
-    // mean / rstd of the new row for the next layer's LayerNorm (consumed by the GEMM producers)
-    const float hmean = warp_sum(hsum) / (float)D;
-    float hsq = 0.0f;
+      const float bj = wb[o.b_in + lane + 32 * j];
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) { const float d = hvv[j] - hmean; hsq += d * d; }
-    const float hrstd = 1.0f / sqrtf(warp_sum(hsq) / (float)D + 1e-5f);
-    if (lane == 0) row_stats[v] = make_float2(hmean, hrstd);
+      for (int r = 0; r < R; ++r) t[r][j] = bj;
+    }
+    for (int kk = 0; kk < 19; ++kk) {
+      float xk[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) xk[r] = __shfl_sync(0xffffffffu, xv[r], kk);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const float w = s_win[(lane + 32 * j) * 19 + kk];
+#pragma unroll
+        for (int r = 0; r < R; ++r) t[r][j] = fmaf(w, xk[r], t[r][j]);
+      }
+    }
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) sum += t[r][j];
+      mean[r] = warp_sum(sum) / (float)D;
+      float sq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) { const float d = t[r][j] - mean[r]; sq += d * d; }
+      rstd[r] = 1.0f / sqrtf(warp_sum(sq) / (float)D + 1e-5f);
+    }
+    // prior booster: q hidden units, lane owns units lane, lane+32, ...
+    float p0[R], p1[R], p2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      p0[r] = __shfl_sync(0xffffffffu, xraw[r], 16);
+      p1[r] = __shfl_sync(0xffffffffu, xraw[r], 17);
+      p2[r] = __shfl_sync(0xffffffffu, xraw[r], 18);
+    }
+    float boost[R][CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const float bj = wb[o.pb2_b + lane + 32 * j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) boost[r][j] = bj;
+    }
+    for (int u0 = 0; u0 < q; u0 += 32) {
+      const int u = u0 + lane;
+      float hu[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) hu[r] = 0.0f;
+      if (u < q) {
+        const float w0 = s_pb0[u * 3], w1 = s_pb0[u * 3 + 1], w2 = s_pb0[u * 3 + 2], bu = wb[o.pb0_b + u];
+#pragma unroll
+        for (int r = 0; r < R; ++r) hu[r] = gelu_fast(fmaf(w2, p2[r], fmaf(w1, p1[r], fmaf(w0, p0[r], bu))));
+      }
+      const int lim = min(32, q - u0);
+      for (int s = 0; s < lim; ++s) {
+        float hs[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) hs[r] = __shfl_sync(0xffffffffu, hu[r], s);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const float w = s_pb2[(u0 + s) * D + lane + 32 * j];
+#pragma unroll
+          for (int r = 0; r < R; ++r) boost[r][j] = fmaf(w, hs[r], boost[r][j]);
+        }
+      }
+    }
+    float lg[CPL], lb[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { lg[j] = wb[o.ln_in_g + lane + 32 * j]; lb[j] = wb[o.ln_in_b + lane + 32 * j]; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int v = v0 + r;
+      if (v >= nt) break;                                    // warp-uniform
+      float hsum = 0.0f, hvv[CPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int c = lane + 32 * j;
+        const float ln = (t[r][j] - mean[r]) * rstd[r] * lg[j] + lb[j];
+        const float hv = gelu_fast(ln) * (1.0f + sigmoidf(boost[r][j]));
+        h[(size_t)v * D + c] = hv;
+        z[(size_t)v * D + c] = jk0 * hv;
+        hvv[j] = hv;
+        hsum += hv;
+      }
+      // mean / rstd of the new row for the next layer's LayerNorm (consumed by the GEMM producers)
+      const float hmean = warp_sum(hsum) / (float)D;
+      float hsq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) { const float d = hvv[j] - hmean; hsq += d * d; }
+      const float hrstd = 1.0f / sqrtf(warp_sum(hsq) / (float)D + 1e-5f);
+      if (lane == 0) row_stats[v] = make_float2(hmean, hrstd);
+    }
   }
 }
 
@@ -921,9 +968,20 @@ int resgcn_forward(gg_context* ctx, Arena& ar, const float* x, const int32_t* ro
     const size_t smem = ((size_t)D * 19 + (size_t)nw.q * 3 + (size_t)D * nw.q) * sizeof(float);
     // few resident blocks per SM, many nodes per warp: the 26 KB weight image is staged once per block
     const int blocks = min(warp_blocks, ctx->sm_count * 3);
+    static const int in_r = getenv("GG_IN_R") ? atoi(getenv("GG_IN_R")) : 4;      // nodes per warp iteration (A/B knob)
     GG_CPL_SWITCH(D, {
-      GG_SMEM_ATTR_ONCE(ctx, 1 + CPL, k_input_stage<CPL>, smem);
-      GG_LAUNCH(ctx, k_input_stage<CPL>, blocks, 256, smem, st, x, wb, o, sizes, h, z, row_stats);
+      if (in_r >= 4 && CPL <= 4) {
+        GG_SMEM_ATTR_ONCE(ctx, 1 + CPL, (k_input_stage<CPL, 4>), smem);
+        GG_LAUNCH(ctx, (k_input_stage<CPL, 4>), min(blocks, ctx->sm_count * 2), 256, smem, st, x, wb, o, sizes, h, z, row_stats);
+      } else if (in_r >= 2) {
+        if (smem > 48 * 1024)
+          GG_CUDA_OK(cudaFuncSetAttribute(k_input_stage<CPL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GG_LAUNCH(ctx, (k_input_stage<CPL, 2>), blocks, 256, smem, st, x, wb, o, sizes, h, z, row_stats);
+      } else {
+        if (smem > 48 * 1024)
+          GG_CUDA_OK(cudaFuncSetAttribute(k_input_stage<CPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GG_LAUNCH(ctx, (k_input_stage<CPL, 1>), blocks, 256, smem, st, x, wb, o, sizes, h, z, row_stats);
+      }
     });
   }
   // ---- edge context -> gate

@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "pixel_math.cuh"
 #include "slic.cuh"
+#include "tc_ptx.cuh"
 
 namespace gg {
 
@@ -185,8 +186,29 @@ struct SlicGrid {
 };
 constexpr float SLIC_FIX = 4096.0f;      // fixed-point scale of the colour sums
 
+// Per-centre record the column-walk assignment copies straight into shared memory (two float4):
+//   (-2 cy/S, -2 cx/S, -2 L, -2 A), (-2 B, |c|^2, covers, 0)       positions in units of the grid step S
+// |f - c|^2 - |f|^2 = |c|^2 - 2 f.c: five FMAs per candidate.  `covers` = 1 when skimage's window of the
+// centre (+- 2 steps around its CURRENT position) contains every pixel that can consider it (the home cells
+// within one cell of the centre's own cell) -- then the window test can be skipped.
+GG_D void slic_centre_record(const SlicGrid& g, int H, int W, int k, float cy, float cx, float cl, float ca, float cb,
+                             float4* __restrict__ rec) {
+  const float inv_step = 1.0f / (float)g.step;
+  const float ys = cy * inv_step, xs = cx * inv_step;
+  const int ci = k / g.gx, cj = k - ci * g.gx;
+  const int wy0 = (int)fmaxf(cy - 2.0f * g.ty, 0.0f), wy1 = (int)fminf(cy + 2.0f * g.ty + 1.0f, (float)H);
+  const int wx0 = (int)fmaxf(cx - 2.0f * g.tx, 0.0f), wx1 = (int)fminf(cx + 2.0f * g.tx + 1.0f, (float)W);
+  const int ry0 = ci - 1 <= 0 ? 0 : g.sy - g.ty / 2 + (ci - 1) * g.ty;
+  const int ry1 = ci + 1 >= g.gy - 1 ? H : g.sy - g.ty / 2 + (ci + 2) * g.ty;
+  const int rx0 = cj - 1 <= 0 ? 0 : g.sx - g.tx / 2 + (cj - 1) * g.tx;
+  const int rx1 = cj + 1 >= g.gx - 1 ? W : g.sx - g.tx / 2 + (cj + 2) * g.tx;
+  const bool covers = wy0 <= ry0 && wy1 >= ry1 && wx0 <= rx0 && wx1 >= rx1;
+  rec[0] = make_float4(-2.0f * ys, -2.0f * xs, -2.0f * cl, -2.0f * ca);
+  rec[1] = make_float4(-2.0f * cb, fmaf(ys, ys, fmaf(xs, xs, fmaf(cl, cl, fmaf(ca, ca, cb * cb)))), covers ? 1.0f : 0.0f, 0.0f);
+}
+
 __global__ void k_slic_init(const float4* __restrict__ feat, SlicGrid g, int H, int W, float* __restrict__ cen /*[B][K][5]*/,
-                            int* __restrict__ sums /*[B][K][6]*/) {
+                            int* __restrict__ sums /*[B][K][6]*/, float4* __restrict__ cq /*[B][K][2]*/) {
   const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
   const int K = g.gy * g.gx;
   if (k >= K) return;
@@ -195,6 +217,7 @@ __global__ void k_slic_init(const float4* __restrict__ feat, SlicGrid g, int H, 
   const float4 f = feat[((size_t)b * H + y) * W + x];
   float* c = cen + ((size_t)b * K + k) * 5;
   c[0] = (float)y; c[1] = (float)x; c[2] = f.x; c[3] = f.y; c[4] = f.z;
+  slic_centre_record(g, H, W, k, (float)y, (float)x, f.x, f.y, f.z, cq + ((size_t)b * K + k) * 2);
   int* s = sums + ((size_t)b * K + k) * 6;
 #pragma unroll
   for (int q = 0; q < 6; ++q) s[q] = 0;
@@ -202,6 +225,7 @@ __global__ void k_slic_init(const float4* __restrict__ feat, SlicGrid g, int H, 
 
 constexpr int SA_TY = 32, SA_TX = 64;    // pixel tile of k_slic_assign (256 threads x 8 pixels)
 constexpr int SA_MAXC = 16;              // cells per axis that a tile can touch (tile / step + 5)
+constexpr int SA_WALK_SLOTS = 96;        // cells of a tile in the column-walk kernels (small tables: three blocks per SM)
 
 GG_D int slic_cell(int p, int start, int step, int n) {       // home cell of a coordinate (boundaries midway)
   const int num = p - start + step / 2;
@@ -210,47 +234,70 @@ GG_D int slic_cell(int p, int start, int step, int n) {       // home cell of a 
 
 // NEIGH = 2: the centres of the 5 x 5 cells around the pixel's home cell (skimage's windows reach two
 // steps); NEIGH = 1: 3 x 3 cells (the original SLIC search region).
-template <int NEIGH>
-__global__ void __launch_bounds__(256)
-k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, SlicGrid g, int H, int W,
-              int32_t* __restrict__ labels, int* __restrict__ sums) {
-  __shared__ float2 s_yx[SA_MAXC * SA_MAXC];       // centre position
-  __shared__ float4 s_col[SA_MAXC * SA_MAXC];      // centre colour
-  __shared__ int4 s_win[SA_MAXC * SA_MAXC];        // skimage's window of the centre: y_min, y_max, x_min, x_max
+// TY: rows of the pixel tile (32 or 64).  WALK: the tile's feature rows are staged in (dynamic) shared memory
+// by asynchronous copies issued before the centre records are fetched, and the tiles whose windows all cover
+// them (practically every tile) take the column-walk path below.
+template <int NEIGH, int TY, bool WALK>
+__global__ void __launch_bounds__(256, WALK ? 3 : 4)
+k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, const float4* __restrict__ cq, SlicGrid g,
+              int H, int W, int32_t* __restrict__ labels, int* __restrict__ sums) {
+  extern __shared__ __align__(128) float4 s_feat[];      // WALK: [TY][SA_TX] features of the tile
+  constexpr int SLOTS = WALK ? SA_WALK_SLOTS : SA_MAXC * SA_MAXC;
+  __shared__ __align__(128) float4 s_q[WALK ? SLOTS * 2 : 2];   // WALK: the centre records of the tile's cells
+  __shared__ float2 s_yx[SLOTS];       // centre position
+  __shared__ float4 s_col[SLOTS];      // centre colour
+  __shared__ int4 s_win[SLOTS];        // skimage's window of the centre: y_min, y_max, x_min, x_max
   // fast path: |f - c|^2 - |f|^2 = |c|^2 - 2 f.c  ->  (-2cy, -2cx, -2L, -2A), (-2B, |c|^2): five FMAs per centre
-  __shared__ float4 s_q4[SA_MAXC * SA_MAXC];
-  __shared__ float2 s_q2[SA_MAXC * SA_MAXC];
-  __shared__ int s_sum[SA_MAXC * SA_MAXC][6];
-  __shared__ int s_rowcell[SA_TY], s_colcell[SA_TX];
-  __shared__ int s_cid[SA_MAXC * SA_MAXC];         // global centre index of a slot (the label a pixel gets)
-  const int b = blockIdx.z, y0 = blockIdx.y * SA_TY, x0 = blockIdx.x * SA_TX;
+  __shared__ float4 s_q4[SLOTS];
+  __shared__ float2 s_q2[SLOTS];
+  __shared__ int s_sum[SLOTS][6];
+  __shared__ int s_rowcell[TY], s_colcell[SA_TX];
+  __shared__ int s_cid[SLOTS];         // global centre index of a slot (the label a pixel gets)
+  const int b = blockIdx.z, y0 = blockIdx.y * TY, x0 = blockIdx.x * SA_TX;
   const int K = g.gy * g.gx;
   const int ci0 = max(slic_cell(y0, g.sy, g.ty, g.gy) - NEIGH, 0);
-  const int ci1 = min(slic_cell(min(y0 + SA_TY, H) - 1, g.sy, g.ty, g.gy) + NEIGH, g.gy - 1);
+  const int ci1 = min(slic_cell(min(y0 + TY, H) - 1, g.sy, g.ty, g.gy) + NEIGH, g.gy - 1);
   const int cj0 = max(slic_cell(x0, g.sx, g.tx, g.gx) - NEIGH, 0);
   const int cj1 = min(slic_cell(min(x0 + SA_TX, W) - 1, g.sx, g.tx, g.gx) + NEIGH, g.gx - 1);
   const int nci = ci1 - ci0 + 1, ncj = cj1 - cj0 + 1;          // <= SA_MAXC by the launch check
+  const int tx = threadIdx.x & 63, ty4 = threadIdx.x >> 6;      // 64 columns x 4 row groups
+  const int x = x0 + tx;
+  if (WALK && x < W) {
+    // every thread fetches the feature rows it is going to walk itself (its column, TY / 4 consecutive rows)
+    // with 16-byte asynchronous copies into shared memory: all of them are in flight while the centre records
+    // are fetched, no register is held for them, and a thread only ever reads what it copied -- no barrier
+    const float4* src = feat + ((size_t)b * H + y0 + ty4 * (TY / 4)) * W + x;
+    const uint32_t dst = smem_u32(s_feat + (ty4 * (TY / 4)) * SA_TX + tx);
+    const int rows = min(TY / 4, H - (y0 + ty4 * (TY / 4)));
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)r * SA_TX * 16u), "l"(src + (size_t)r * W) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   const float* cb = cen + (size_t)b * K * 5;
-  const int y_hi = min(y0 + SA_TY, H), x_hi = min(x0 + SA_TX, W);
+  const int y_hi = min(y0 + TY, H), x_hi = min(x0 + SA_TX, W);
   const float inv_step = 1.0f / (float)g.step;
-  bool full = true;                              // every window covers all the pixels of the tile that consider its centre
-  for (int i = threadIdx.x; i < nci * ncj; i += blockDim.x) {
-    const int k = (ci0 + i / ncj) * g.gx + cj0 + i % ncj;
-    const float cy = cb[k * 5], cx = cb[k * 5 + 1];
-    s_cid[i] = k;
-    s_yx[i] = NEIGH == 1 ? make_float2(cy * inv_step, cx * inv_step) : make_float2(cy, cx);
-    s_col[i] = make_float4(cb[k * 5 + 2], cb[k * 5 + 3], cb[k * 5 + 4], 0.0f);
-    if (NEIGH == 1) {
-      const float ys = cy * inv_step, xs = cx * inv_step, cl = cb[k * 5 + 2], ca = cb[k * 5 + 3], cbb = cb[k * 5 + 4];
-      s_q4[i] = make_float4(-2.0f * ys, -2.0f * xs, -2.0f * cl, -2.0f * ca);
-      s_q2[i] = make_float2(-2.0f * cbb, fmaf(ys, ys, fmaf(xs, xs, fmaf(cl, cl, fmaf(ca, ca, cbb * cbb)))));
-    }
-    const int4 w = make_int4((int)fmaxf(cy - 2.0f * g.ty, 0.0f), (int)fminf(cy + 2.0f * g.ty + 1.0f, (float)H),
-                             (int)fmaxf(cx - 2.0f * g.tx, 0.0f), (int)fminf(cx + 2.0f * g.tx + 1.0f, (float)W));
-    s_win[i] = w;
-    // the pixels of this tile that can see centre k are those whose home cell is within one cell of
-    // k's cell: rows [begin(i-1), end(i+1)) x columns [begin(j-1), end(j+1)), cut to the tile
-    {
+  // tables of the general path (and of the straight-line search of the row-interleaved form): centre
+  // positions / colours / windows per slot; returns whether every window covers all the pixels of the tile
+  // that consider its centre
+  auto slot_tables = [&]() {
+    bool full = true;
+    for (int i = threadIdx.x; i < nci * ncj; i += blockDim.x) {
+      const int k = (ci0 + i / ncj) * g.gx + cj0 + i % ncj;
+      const float cy = cb[k * 5], cx = cb[k * 5 + 1];
+      s_cid[i] = k;
+      s_yx[i] = NEIGH == 1 ? make_float2(cy * inv_step, cx * inv_step) : make_float2(cy, cx);
+      s_col[i] = make_float4(cb[k * 5 + 2], cb[k * 5 + 3], cb[k * 5 + 4], 0.0f);
+      if (NEIGH == 1) {
+        const float ys = cy * inv_step, xs = cx * inv_step, cl = cb[k * 5 + 2], ca = cb[k * 5 + 3], cbb = cb[k * 5 + 4];
+        s_q4[i] = make_float4(-2.0f * ys, -2.0f * xs, -2.0f * cl, -2.0f * ca);
+        s_q2[i] = make_float2(-2.0f * cbb, fmaf(ys, ys, fmaf(xs, xs, fmaf(cl, cl, fmaf(ca, ca, cbb * cbb)))));
+      }
+      const int4 w = make_int4((int)fmaxf(cy - 2.0f * g.ty, 0.0f), (int)fminf(cy + 2.0f * g.ty + 1.0f, (float)H),
+                               (int)fmaxf(cx - 2.0f * g.tx, 0.0f), (int)fminf(cx + 2.0f * g.tx + 1.0f, (float)W));
+      s_win[i] = w;
+      // the pixels of this tile that can see centre k are those whose home cell is within one cell of
+      // k's cell: rows [begin(i-1), end(i+1)) x columns [begin(j-1), end(j+1)), cut to the tile
       const int ci = ci0 + i / ncj, cj = cj0 + i % ncj;
       const int ry0 = max(ci - 1 <= 0 ? 0 : g.sy - g.ty / 2 + (ci - 1) * g.ty, y0);
       const int ry1 = min(ci + 1 >= g.gy - 1 ? H : g.sy - g.ty / 2 + (ci + 2) * g.ty, y_hi);
@@ -258,15 +305,35 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
       const int rx1 = min(cj + 1 >= g.gx - 1 ? W : g.sx - g.tx / 2 + (cj + 2) * g.tx, x_hi);
       if (ry0 < ry1 && rx0 < rx1) full = full && w.x <= ry0 && w.y >= ry1 && w.z <= rx0 && w.w >= rx1;
     }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) s_sum[i][q] = 0;
-  }
-  if (threadIdx.x < SA_TY) s_rowcell[threadIdx.x] = slic_cell(y0 + threadIdx.x, g.sy, g.ty, g.gy);
+    return full;
+  };
+  for (int i = threadIdx.x; i < nci * ncj * 6; i += blockDim.x) (&s_sum[0][0])[i] = 0;
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + TY) s_rowcell[threadIdx.x - 128] = slic_cell(y0 + threadIdx.x - 128, g.sy, g.ty, g.gy);
   if (threadIdx.x >= 64 && threadIdx.x < 64 + SA_TX) s_colcell[threadIdx.x - 64] = slic_cell(x0 + threadIdx.x - 64, g.sx, g.tx, g.gx);
-  const bool all_full = __syncthreads_and(full) != 0;
+  bool all_full;
+  if (!WALK) {
+    all_full = __syncthreads_and(slot_tables()) != 0;
+  } else {
+    // nothing to compute per centre: k_slic_init / k_slic_update left a ready-made record
+    bool full = true;
+    for (int i = threadIdx.x; i < nci * ncj; i += blockDim.x) {
+      const int k = (ci0 + i / ncj) * g.gx + cj0 + i % ncj;
+      const float4* rec = cq + ((size_t)b * K + k) * 2;
+      const float4 r0 = rec[0], r1 = rec[1];
+      s_cid[i] = k;
+      s_q[2 * i] = r0;
+      s_q[2 * i + 1] = r1;
+      full = full && r1.z != 0.0f;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    all_full = __syncthreads_and(full) != 0;
+    if (!all_full) {                                     // rare: a centre drifted by more than half a cell
+      slot_tables();
+      __syncthreads();
+      all_full = false;
+    }
+  }
   const float w_sp = 1.0f / (float)(g.step * g.step);
-  const int tx = threadIdx.x & 63, ty4 = threadIdx.x >> 6;      // 64 columns x 4 row groups
-  const int x = x0 + tx;
   const int lane = threadIdx.x & 31;
   const int hj = s_colcell[tx];
   const int j_lo = max(hj - NEIGH, cj0), j_hi = min(hj + NEIGH, cj1);
@@ -274,14 +341,114 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
   // twice with the same distance and never wins a second time)
   const int jc0 = max(hj - 1, 0) - cj0, jc1 = hj - cj0, jc2 = min(hj + 1, g.gx - 1) - cj0;
   const float fxs = (float)x * inv_step;
+  if (WALK && NEIGH == 1 && all_full) {
+    // Column walk (the common case: every window covers the tile).  A thread owns 8 CONSECUTIVE rows of
+    // one column.  Its three candidate columns are fixed and the candidate rows change only when the home
+    // row cell does (warp-uniform, at most twice in 8 rows), so the coefficients of the 9 candidate centres
+    // live in registers -- with the column term folded into the constant, a candidate costs 4 FMAs + a
+    // compare and two selects, and no shared-memory access.  The per-centre sums are run-length
+    // aggregated down the column in registers (a thread flushes when its winner changes) and the runs
+    // still open at the end are combined across the warp before they reach shared memory.
+    constexpr int RPT = TY / 4;                             // rows per thread
+    const int rg = threadIdx.x >> 6;
+    const int yb = y0 + rg * RPT;
+    const int jc[3] = {jc0, jc1, jc2};
+    float qy[9], qL[9], qA[9], qB[9], qc[9];
+    int cslot[9];
+#pragma unroll
+    for (int s = 0; s < 9; ++s) { qy[s] = qL[s] = qA[s] = qB[s] = qc[s] = 0.0f; cslot[s] = 0; }
+    int hi_prev = -1;
+    int cur = -1, n = 0, sy = 0, sL = 0, sA = 0, sB = 0;
+#pragma unroll 1
+    for (int r = 0; r < RPT; ++r) {
+      const int y = yb + r;
+      if (y >= H) break;                                      // warp-uniform
+      const float4 f = s_feat[(rg * RPT + r) * SA_TX + tx];   // columns >= W of a cut tile: never copied, never used
+      const int hi = s_rowcell[rg * RPT + r];
+      if (hi != hi_prev) {                                    // warp-uniform
+        hi_prev = hi;
+        const int rb[3] = {(max(hi - 1, 0) - ci0) * ncj, (hi - ci0) * ncj, (min(hi + 1, g.gy - 1) - ci0) * ncj};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int slot = rb[a] + jc[c];
+            const float4 q4 = s_q[2 * slot];
+            const float4 q2 = s_q[2 * slot + 1];
+            cslot[a * 3 + c] = slot;
+            qy[a * 3 + c] = q4.x;
+            qc[a * 3 + c] = fmaf(q4.y, fxs, q2.y);
+            qL[a * 3 + c] = q4.z;
+            qA[a * 3 + c] = q4.w;
+            qB[a * 3 + c] = q2.x;
+          }
+        }
+      }
+      const bool in = x < W;
+      int best_slot = cur;
+      if (in) {
+        const float fys = (float)y * inv_step;
+        float best = __int_as_float(0x7f7fffff);
+        best_slot = cslot[0];
+        // increasing centre index; ties keep the lower index (strict <)
+#pragma unroll
+        for (int s = 0; s < 9; ++s) {
+          const float d = fmaf(qy[s], fys, fmaf(qL[s], f.x, fmaf(qA[s], f.y, fmaf(qB[s], f.z, qc[s]))));
+          if (d < best) { best = d; best_slot = cslot[s]; }
+        }
+        if (labels) labels[((size_t)b * H + y) * W + x] = s_cid[best_slot];
+      }
+      // a thread whose winner changed hands its finished run over with plain shared-memory atomics (combining
+      // the lanes that give up the same centre with match.any / redux first was measured: 4.0 -> 5.5 ms)
+      const bool chg = in && best_slot != cur;
+      if (chg && n > 0) {
+        atomicAdd(&s_sum[cur][0], n);
+        atomicAdd(&s_sum[cur][1], sy);
+        atomicAdd(&s_sum[cur][2], x * n);
+        atomicAdd(&s_sum[cur][3], sL);
+        atomicAdd(&s_sum[cur][4], sA);
+        atomicAdd(&s_sum[cur][5], sB);
+      }
+      if (chg) {
+        cur = best_slot;
+        n = sy = sL = sA = sB = 0;
+      }
+      if (in) {
+        n += 1;
+        sy += y;
+        sL += __float2int_rn(f.x * SLIC_FIX);
+        sA += __float2int_rn(f.y * SLIC_FIX);
+        sB += __float2int_rn(f.z * SLIC_FIX);
+      }
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, n > 0);
+    if (n > 0) {
+      const int first = __shfl_sync(act, cur, __ffs(act) - 1);
+      const unsigned grp = __all_sync(act, cur == first) ? act : __match_any_sync(act, cur);
+      const int v0 = __reduce_add_sync(grp, n);
+      const int v1 = __reduce_add_sync(grp, sy);
+      const int v2 = __reduce_add_sync(grp, x * n);
+      const int v3 = __reduce_add_sync(grp, sL);
+      const int v4 = __reduce_add_sync(grp, sA);
+      const int v5 = __reduce_add_sync(grp, sB);
+      if (lane == __ffs(grp) - 1) {
+        atomicAdd(&s_sum[cur][0], v0);
+        atomicAdd(&s_sum[cur][1], v1);
+        atomicAdd(&s_sum[cur][2], v2);
+        atomicAdd(&s_sum[cur][3], v3);
+        atomicAdd(&s_sum[cur][4], v4);
+        atomicAdd(&s_sum[cur][5], v5);
+      }
+    }
+  } else {
   float4 f_next = make_float4(0.f, 0.f, 0.f, 0.f);
   if (y0 + ty4 < H && x < W) f_next = feat[((size_t)b * H + y0 + ty4) * W + x];
-  for (int rr = 0; rr < SA_TY / 4; ++rr) {
+  for (int rr = 0; rr < TY / 4; ++rr) {
     const int y = y0 + ty4 + 4 * rr;
     const bool in = y < H && x < W;
     int best_slot = -1;
     const float4 f = f_next;                                  // loaded one iteration ago
-    if (rr + 1 < SA_TY / 4 && y + 4 < H && x < W) f_next = feat[((size_t)b * H + y + 4) * W + x];
+    if (rr + 1 < TY / 4 && y + 4 < H && x < W) f_next = feat[((size_t)b * H + y + 4) * W + x];
     if (in) {
       const int hi = s_rowcell[ty4 + 4 * rr];
       float best = __int_as_float(0x7f7fffff);
@@ -354,6 +521,7 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
       }
     }
   }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < nci * ncj; i += blockDim.x) {
     if (s_sum[i][0] == 0) continue;
@@ -364,8 +532,9 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, Sl
   }
 }
 
-__global__ void k_slic_update(int K, float* __restrict__ cen, int* __restrict__ sums) {
+__global__ void k_slic_update(SlicGrid g, int H, int W, float* __restrict__ cen, int* __restrict__ sums, float4* __restrict__ cq) {
   const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = g.gy * g.gx;
   if (k >= K) return;
   int* s = sums + ((size_t)b * K + k) * 6;
   float* c = cen + ((size_t)b * K + k) * 5;
@@ -375,6 +544,7 @@ __global__ void k_slic_update(int K, float* __restrict__ cen, int* __restrict__ 
     c[0] = (float)s[1] * inv; c[1] = (float)s[2] * inv;
     c[2] = (float)s[3] * inv * (1.0f / SLIC_FIX); c[3] = (float)s[4] * inv * (1.0f / SLIC_FIX);
     c[4] = (float)s[5] * inv * (1.0f / SLIC_FIX);
+    slic_centre_record(g, H, W, k, c[0], c[1], c[2], c[3], c[4], cq + ((size_t)b * K + k) * 2);
   }
 #pragma unroll
   for (int q = 0; q < 6; ++q) s[q] = 0;
@@ -587,7 +757,7 @@ size_t slic_workspace_bytes(int B, int H, int W, int n_segments) {
   const size_t HW = (size_t)H * W, K = (size_t)g.gy * g.gx;
   const size_t nb = (HW + 1023) / 1024;
   return Arena::padded((size_t)B * HW, 16) + Arena::padded((size_t)B * 2, 4) + Arena::padded((size_t)B * K * 5, 4) +
-         Arena::padded((size_t)B * K * 6, 4) + Arena::padded((size_t)B * HW, 4) * 4 + Arena::padded((size_t)B * nb, 4) + 4096;
+         Arena::padded((size_t)B * K * 6, 4) + Arena::padded((size_t)B * K * 2, 16) + Arena::padded((size_t)B * HW, 4) * 4 + Arena::padded((size_t)B * nb, 4) + 4096;
 }
 
 int slic_nominal_segments(int H, int W, int n_segments) {
@@ -610,10 +780,14 @@ int slic_labels(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, in
   // paper; default: 8.0 ms per 256 images of 320x480 for the 10 rounds), 2 = the 5 x 5 cells that skimage's
   // two-step windows can reach (11.8 ms; the same segmentation quality on the test images)
   static const int neigh = getenv("GG_SLIC_NEIGH") ? atoi(getenv("GG_SLIC_NEIGH")) : 1;
+  // 1 (default): column walk (register-resident candidates, tile staged by bulk copies; 64-row tiles when they
+  // fit), 32: the same with 32-row tiles only, 0: the row-interleaved form
+  static const int column_walk = getenv("GG_SLIC_WALK") ? atoi(getenv("GG_SLIC_WALK")) : 1;
   float4* feat = ar.take<float4>((size_t)B * HW);
   int* minmax = ar.take<int>((size_t)B * 2);
   float* cen = ar.take<float>((size_t)B * K * 5);
   int* sums = ar.take<int>((size_t)B * K * 6);
+  float4* cq = ar.take<float4>((size_t)B * K * 2);
   int* L = ar.take<int>((size_t)B * HW);
   int* size = ar.take<int>((size_t)B * HW);
   int* target = ar.take<int>((size_t)B * HW);
@@ -644,14 +818,38 @@ int slic_labels(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, in
   }
   {
     dim3 grid(ceil_div(K, 256), B);
-    GG_LAUNCH(ctx, k_slic_init, grid, 256, 0, st, feat, g, H, W, cen, sums);
-    dim3 ga(ceil_div(W, SA_TX), ceil_div(H, SA_TY), B);
+    GG_LAUNCH(ctx, k_slic_init, grid, 256, 0, st, feat, g, H, W, cen, sums, cq);
+    dim3 ga(ceil_div(W, SA_TX), ceil_div(H, SA_TY), B), ga_tall(ceil_div(W, SA_TX), ceil_div(H, 2 * SA_TY), B);
+    // 64-row tiles (16 rows per thread: the centre tables and the final flush are amortised over twice the
+    // pixels) when the cell table still fits and the image is not left with a mostly empty last tile row
+    auto walk_slots = [&](int ty) { return ((ty - 1) / g.ty + 4) * ((SA_TX - 1) / g.tx + 4); };   // cells a tile can touch
+    const bool tall = column_walk >= 1 && column_walk != 32 && walk_slots(2 * SA_TY) <= SA_WALK_SLOTS &&
+                      (H % (2 * SA_TY) == 0 || H % (2 * SA_TY) > SA_TY || H > 8 * SA_TY);
+    const bool walk = column_walk >= 1 && walk_slots(SA_TY) <= SA_WALK_SLOTS;     // else: very small grid steps
+    if (column_walk) {
+      static bool attr_set[64] = {};
+      if (!attr_set[ctx->device & 63]) {       // static + dynamic shared memory exceed 48 KB
+        GG_CUDA_OK(cudaFuncSetAttribute(k_slic_assign<1, 2 * SA_TY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(2 * SA_TY * SA_TX * sizeof(float4))));
+        GG_CUDA_OK(cudaFuncSetAttribute(k_slic_assign<1, SA_TY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(SA_TY * SA_TX * sizeof(float4))));
+        attr_set[ctx->device & 63] = true;
+      }
+    }
     for (int it = 0; it < max_iter; ++it) {
       // only the labels of the last iteration are read (the centre sums are accumulated inside the kernel)
       int32_t* lab_out = it == max_iter - 1 ? labels : nullptr;
-      if (neigh >= 2) GG_LAUNCH(ctx, k_slic_assign<2>, ga, 256, 0, st, feat, cen, g, H, W, lab_out, sums);
-      else GG_LAUNCH(ctx, k_slic_assign<1>, ga, 256, 0, st, feat, cen, g, H, W, lab_out, sums);
-      GG_LAUNCH(ctx, k_slic_update, grid, 256, 0, st, K, cen, sums);
+      if (neigh >= 2) {
+        GG_LAUNCH(ctx, (k_slic_assign<2, SA_TY, false>), ga, 256, 0, st, feat, cen, cq, g, H, W, lab_out, sums);
+      } else if (!walk) {
+        GG_LAUNCH(ctx, (k_slic_assign<1, SA_TY, false>), ga, 256, 0, st, feat, cen, cq, g, H, W, lab_out, sums);
+      } else if (tall) {
+        GG_LAUNCH(ctx, (k_slic_assign<1, 2 * SA_TY, true>), ga_tall, 256, 2 * SA_TY * SA_TX * sizeof(float4), st, feat, cen, cq, g, H, W,
+                  lab_out, sums);
+      } else {
+        GG_LAUNCH(ctx, (k_slic_assign<1, SA_TY, true>), ga, 256, SA_TY * SA_TX * sizeof(float4), st, feat, cen, cq, g, H, W, lab_out, sums);
+      }
+      GG_LAUNCH(ctx, k_slic_update, grid, 256, 0, st, g, H, W, cen, sums, cq);
     }
   }
   // connectivity (skimage: min_size = int(0.5 * H W / K))
