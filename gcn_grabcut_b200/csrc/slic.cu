@@ -414,11 +414,13 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, co
         n = sy = sL = sA = sB = 0;
       }
       if (in) {
+        // round-to-nearest fixed point without the conversion unit: 1.5 * 2^23 + v has the integer v in its
+        // low mantissa bits (|v| < 2^22), the same value as __float2int_rn(f * SLIC_FIX)
         n += 1;
         sy += y;
-        sL += __float2int_rn(f.x * SLIC_FIX);
-        sA += __float2int_rn(f.y * SLIC_FIX);
-        sB += __float2int_rn(f.z * SLIC_FIX);
+        sL += __float_as_int(fmaf(f.x, SLIC_FIX, 12582912.0f)) - 0x4B400000;
+        sA += __float_as_int(fmaf(f.y, SLIC_FIX, 12582912.0f)) - 0x4B400000;
+        sB += __float_as_int(fmaf(f.z, SLIC_FIX, 12582912.0f)) - 0x4B400000;
       }
     }
     const unsigned act = __ballot_sync(0xffffffffu, n > 0);
@@ -662,6 +664,105 @@ k_slic_cc_count(int HW, const int* __restrict__ target, int* __restrict__ block_
     if (lane == 0) block_cnt[(size_t)b * n_blocks + blockIdx.x] = v;
   }
 }
+// ---- four pixels per thread (H W % 4 == 0): the same passes with 128-bit accesses and a quarter of the
+// threads; a block of 256 threads covers the same 1024 pixels as a block of the scalar kernels, so the
+// per-block counts and the scan over them are shared.
+// target of the roots (see k_slic_cc_target) + number of kept roots per block (k_slic_cc_count) in one pass
+__global__ void __launch_bounds__(256)
+k_slic_cc_target_count_v4(int H, int W, const int* __restrict__ L, const int* __restrict__ size, int min_size,
+                          int* __restrict__ target, int* __restrict__ block_cnt, int n_blocks) {
+  __shared__ int s_w[8];
+  const int b = blockIdx.y, i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int HW = H * W;
+  const int* Lb = L + (size_t)b * HW;
+  int kept = 0;
+  if (i0 < HW) {
+    const int4 l4 = *reinterpret_cast<const int4*>(Lb + i0);
+    const int lv[4] = {l4.x, l4.y, l4.z, l4.w};
+    int tv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + q;
+      int t = -1;                                           // not a root
+      if (lv[q] == i) {
+        t = i;                                              // kept
+        if (size[(size_t)b * HW + i] < min_size && i > 0) {
+          const int y = i / W;
+          t = y > 0 ? Lb[i - W] : Lb[i - 1];                // an earlier component: chains end at a kept one
+        }
+      }
+      tv[q] = t;
+      kept += (t == i);
+    }
+    *reinterpret_cast<int4*>(target + (size_t)b * HW + i0) = make_int4(tv[0], tv[1], tv[2], tv[3]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wsum = __reduce_add_sync(0xffffffffu, kept);
+  if (lane == 0) s_w[wid] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int v = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += s_w[q];
+    block_cnt[(size_t)b * n_blocks + blockIdx.x] = v;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_slic_cc_newid_v4(int HW, const int* __restrict__ target, const int* __restrict__ block_cnt, int n_blocks,
+                   int* __restrict__ newid) {
+  __shared__ int s_w[8];
+  const int b = blockIdx.y, i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int4 t4 = make_int4(-1, -1, -1, -1);
+  if (i0 < HW) t4 = *reinterpret_cast<const int4*>(target + (size_t)b * HW + i0);
+  const int k0 = t4.x == i0, k1 = t4.y == i0 + 1, k2 = t4.z == i0 + 2, k3 = t4.w == i0 + 3;
+  const int c = k0 + k1 + k2 + k3;
+  const unsigned any = __ballot_sync(0xffffffffu, c != 0);      // kept roots are sparse: most warps hold none
+  int inc = c;
+  if (any) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+  }
+  if (lane == 31) s_w[wid] = inc;
+  __syncthreads();
+  if (c != 0) {
+    int base = block_cnt[(size_t)b * n_blocks + blockIdx.x] + inc - c;
+    for (int q = 0; q < wid; ++q) base += s_w[q];
+    int* out = newid + (size_t)b * HW + i0;
+    if (k0) out[0] = base;
+    base += k0;
+    if (k1) out[1] = base;
+    base += k1;
+    if (k2) out[2] = base;
+    base += k2;
+    if (k3) out[3] = base;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_slic_cc_relabel_v4(int HW, const int* __restrict__ L, const int* __restrict__ target, const int* __restrict__ newid,
+                     int32_t* __restrict__ labels) {
+  const int b = blockIdx.y, i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= HW) return;
+  const size_t o = (size_t)b * HW;
+  const int4 l4 = *reinterpret_cast<const int4*>(L + o + i0);
+  int r[4] = {l4.x, l4.y, l4.z, l4.w};
+  int out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (q > 0 && r[q] == l4.x) { out[q] = out[0]; continue; }   // the four pixels mostly share their component
+    int rr = r[q];
+    for (int guard = 0; guard < HW; ++guard) {            // follow the merge chain to a kept root
+      const int t = target[o + rr];
+      if (t == rr) break;
+      rr = t;
+    }
+    out[q] = newid[o + rr];
+  }
+  *reinterpret_cast<int4*>(labels + o + i0) = make_int4(out[0], out[1], out[2], out[3]);
+}
 __global__ void __launch_bounds__(1024)
 k_slic_cc_scan_blocks(int* __restrict__ block_cnt, int n_blocks, int32_t* __restrict__ n_labels) {
   __shared__ int scratch[40];
@@ -862,11 +963,19 @@ int slic_labels(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, in
     }
     GG_LAUNCH(ctx, k_slic_cc_merge, grid, 256, 0, st, labels, H, W, L);
     GG_LAUNCH(ctx, k_slic_cc_flatten, grid, 256, 0, st, HW, L, size);
-    GG_LAUNCH(ctx, k_slic_cc_target, grid, 256, 0, st, H, W, L, size, min_size, target);
-    GG_LAUNCH(ctx, k_slic_cc_count, grid1k, 1024, 0, st, HW, target, block_cnt, nb);
-    GG_LAUNCH(ctx, k_slic_cc_scan_blocks, B, 1024, 0, st, block_cnt, nb, n_labels);
-    GG_LAUNCH(ctx, k_slic_cc_newid, grid1k, 1024, 0, st, HW, target, block_cnt, nb, newid);
-    GG_LAUNCH(ctx, k_slic_cc_relabel, grid, 256, 0, st, HW, L, target, newid, labels);
+    static const bool cc_scalar = getenv("GG_SLIC_CC_SCALAR") != nullptr;
+    if (HW % 4 == 0 && !cc_scalar) {
+      GG_LAUNCH(ctx, k_slic_cc_target_count_v4, grid1k, 256, 0, st, H, W, L, size, min_size, target, block_cnt, nb);
+      GG_LAUNCH(ctx, k_slic_cc_scan_blocks, B, 1024, 0, st, block_cnt, nb, n_labels);
+      GG_LAUNCH(ctx, k_slic_cc_newid_v4, grid1k, 256, 0, st, HW, target, block_cnt, nb, newid);
+      GG_LAUNCH(ctx, k_slic_cc_relabel_v4, grid1k, 256, 0, st, HW, L, target, newid, labels);
+    } else {
+      GG_LAUNCH(ctx, k_slic_cc_target, grid, 256, 0, st, H, W, L, size, min_size, target);
+      GG_LAUNCH(ctx, k_slic_cc_count, grid1k, 1024, 0, st, HW, target, block_cnt, nb);
+      GG_LAUNCH(ctx, k_slic_cc_scan_blocks, B, 1024, 0, st, block_cnt, nb, n_labels);
+      GG_LAUNCH(ctx, k_slic_cc_newid, grid1k, 1024, 0, st, HW, target, block_cnt, nb, newid);
+      GG_LAUNCH(ctx, k_slic_cc_relabel, grid, 256, 0, st, HW, L, target, newid, labels);
+    }
   }
   return GG_OK;
 }
