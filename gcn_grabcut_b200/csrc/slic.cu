@@ -562,10 +562,26 @@ GG_D int cc_find(int* L, int i) {
   }
   return r;
 }
+// find with path halving: every other node on the way is re-pointed at its grandparent.  Only nodes that
+// were seen with a parent are written, and only with one of their ancestors, so concurrent unions
+// (atomicMin on roots) stay correct; the trees the later finds walk are about half as deep.
+GG_D int cc_find_halve(int* L, int i) {
+  volatile int* V = L;
+  int r = i, p = V[r];
+  while (p != r) {
+    const int gp = V[p];
+    if (gp == p) return p;
+    V[r] = gp;
+    r = gp;
+    p = V[r];
+  }
+  return r;
+}
+template <bool HALVE>
 GG_D void cc_union(int* L, int a, int b) {
   while (true) {
-    a = cc_find(L, a);
-    b = cc_find(L, b);
+    a = HALVE ? cc_find_halve(L, a) : cc_find(L, a);
+    b = HALVE ? cc_find_halve(L, b) : cc_find(L, b);
     if (a == b) return;
     if (a < b) { const int t = a; a = b; b = t; }
     const int old = atomicMin(&L[a], b);
@@ -600,20 +616,31 @@ k_slic_cc_init(const int32_t* __restrict__ labels, int H, int W, int* __restrict
   L[(size_t)b * HW + i] = i - (lane - run_lane);
   size[(size_t)b * HW + i] = 0;
 }
+// grid (ceil(W / 256), H, B): a block owns 256 consecutive pixels of ONE row (no division per pixel); the left
+// and upper-left neighbours come from the lane to the left (lane 0 loads them)
+template <bool HALVE>
 __global__ void __launch_bounds__(256)
 k_slic_cc_merge(const int32_t* __restrict__ labels, int H, int W, int* __restrict__ L) {
-  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int HW = H * W;
-  if (i >= HW) return;
+  const int b = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = H * W, lane = threadIdx.x & 31;
+  const bool in = x < W;
   const int32_t* lab = labels + (size_t)b * HW;
   int* Lb = L + (size_t)b * HW;
-  const int y = i / W, x = i - y * W, v = lab[i];
-  const bool left_same = x > 0 && lab[i - 1] == v;
-  if (left_same && (x & 31) == 0) cc_union(Lb, i, i - 1);            // the run continues across the segment boundary
-  if (y > 0 && lab[i - W] == v) {
+  const int i = y * W + min(x, W - 1);
+  const int v = lab[i];
+  const int up = y > 0 ? lab[i - W] : -1;
+  int left = __shfl_up_sync(0xffffffffu, v, 1), upleft = __shfl_up_sync(0xffffffffu, up, 1);
+  if (lane == 0) {
+    left = x > 0 ? lab[i - 1] : -1;
+    upleft = (x > 0 && y > 0) ? lab[i - W - 1] : -1;
+  }
+  if (!in) return;
+  const bool left_same = left == v;                                    // labels are >= 0: -1 never matches
+  if (left_same && (x & 31) == 0) cc_union<HALVE>(Lb, i, i - 1);        // the run continues across the segment boundary
+  if (up == v) {
     // the pixel to the left already joins this run to the same upper run
-    const bool covered = left_same && lab[i - W - 1] == v;
-    if (!covered) cc_union(Lb, i, i - W);
+    const bool covered = left_same && upleft == v;
+    if (!covered) cc_union<HALVE>(Lb, i, i - W);
   }
 }
 __global__ void __launch_bounds__(256)
@@ -961,7 +988,11 @@ int slic_labels(gg_context* ctx, Arena& ar, const uint8_t* bgr, int B, int H, in
       dim3 gi(ceil_div((long long)H * ((W + 31) / 32) * 32, 256), B);
       GG_LAUNCH(ctx, k_slic_cc_init, gi, 256, 0, st, labels, H, W, L, size);
     }
-    GG_LAUNCH(ctx, k_slic_cc_merge, grid, 256, 0, st, labels, H, W, L);
+    static const bool cc_halve = getenv("GG_SLIC_CC_HALVE") ? atoi(getenv("GG_SLIC_CC_HALVE")) != 0 : true;
+    GG_REQUIRE(H <= 65535 && B <= 65535, "slic: image height / batch too large for the connectivity grid");
+    dim3 grid_rows(ceil_div(W, 256), H, B);
+    if (cc_halve) GG_LAUNCH(ctx, k_slic_cc_merge<true>, grid_rows, 256, 0, st, labels, H, W, L);
+    else GG_LAUNCH(ctx, k_slic_cc_merge<false>, grid_rows, 256, 0, st, labels, H, W, L);
     GG_LAUNCH(ctx, k_slic_cc_flatten, grid, 256, 0, st, HW, L, size);
     static const bool cc_scalar = getenv("GG_SLIC_CC_SCALAR") != nullptr;
     if (HW % 4 == 0 && !cc_scalar) {

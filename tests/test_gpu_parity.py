@@ -1065,6 +1065,42 @@ def test_slic_quality_vs_oracle(gg):
     assert np.mean(ue_g) <= np.mean(ue_o) + 0.002
 
 
+def test_slic_kernel_variants_and_odd_sizes(gg, tmp_path):
+    """The SLIC kernels have shape-dependent variants: column-walk assignment with 64- or 32-row tiles
+    (feature rows staged by asynchronous copies), the row-interleaved form for very small grid steps, and
+    the connectivity passes with four pixels per thread when H*W % 4 == 0.  (a) Sizes that cut tiles and
+    take the scalar connectivity kernels keep the invariants; (b) the alternative kernels, selected through
+    the library's A/B environment switches in a fresh process, give the same segmentation: the scalar
+    connectivity passes bit for bit, the row-interleaved assignment up to float32 rounding of near ties."""
+    import os, subprocess, sys
+    from scipy import ndimage as ndi
+    from gcn_grabcut_b200.synthetic import geometric_sample
+    from oracle import slic_port
+    for (H, W, nseg, seed) in [(150, 203, 60, 5), (130, 171, 40, 9), (128, 320, 100, 2)]:
+        img, _ = geometric_sample(H, W, seed)
+        lab, cnt = gg.slic_labels(img[None], gg.SuperpixelGraphConfig(n_segments=nseg), return_counts=True)
+        lab, n = lab[0], int(cnt[0])
+        assert lab.min() == 0 and lab.max() == n - 1 and len(np.unique(lab)) == n, (H, W)
+        assert sum(ndi.label(lab == v)[1] for v in range(n)) == n, f"{H}x{W}: labels are not 4-connected"
+    imgs = np.stack([geometric_sample(320, 480, 60 + i)[0] for i in range(3)])
+    np.save(tmp_path / "imgs.npy", imgs)
+    base = gg.slic_labels(imgs, gg.SuperpixelGraphConfig(n_segments=300))
+    script = ("import sys, numpy as np; sys.path.insert(0, %r); import gcn_grabcut_b200 as gg; "
+              "imgs = np.load(sys.argv[1]); np.save(sys.argv[2], gg.slic_labels(imgs, gg.SuperpixelGraphConfig(n_segments=300)))"
+              % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    for name, env, exact in [("cc_scalar", {"GG_SLIC_CC_SCALAR": "1"}, True), ("walk32", {"GG_SLIC_WALK": "32"}, True),
+                             ("row_interleaved", {"GG_SLIC_WALK": "0"}, False)]:
+        out = tmp_path / f"{name}.npy"
+        subprocess.run([sys.executable, "-c", script, str(tmp_path / "imgs.npy"), str(out)], check=True,
+                       env={**os.environ, **env}, timeout=300)
+        other = np.load(out)
+        if exact:
+            assert np.array_equal(other, base), name
+        else:
+            agree = np.mean([np.mean(slic_port.boundary_map(a) == slic_port.boundary_map(b)) for a, b in zip(other, base)])
+            assert agree >= 0.995, (name, agree)
+
+
 def test_slic_in_the_path(gg):
     """Superpixels produced on the device inside the whole-path entry points (only the images cross
     PCIe) == gg_slic followed by the path on those label maps; GraphBuilder(image, cfg).build()
