@@ -354,66 +354,71 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, co
     const int yb = y0 + rg * RPT;
     const int jc[3] = {jc0, jc1, jc2};
     float qy[9], qL[9], qA[9], qB[9], qc[9];
-    int cslot[9];
+    int rb0 = 0, rb1 = 0, rb2 = 0;
 #pragma unroll
-    for (int s = 0; s < 9; ++s) { qy[s] = qL[s] = qA[s] = qB[s] = qc[s] = 0.0f; cslot[s] = 0; }
+    for (int s = 0; s < 9; ++s) qy[s] = qL[s] = qA[s] = qB[s] = qc[s] = 0.0f;
     int hi_prev = -1;
     int cur = -1, n = 0, sy = 0, sL = 0, sA = 0, sB = 0;
+    if (x < W) {                                              // (no warp-collective inside: columns right of a cut tile idle)
+      const int rows = min(RPT, H - yb);
+      const float4* fp = s_feat + (rg * RPT) * SA_TX + tx;    // running pointers instead of per-row index arithmetic
+      const int* rc = s_rowcell + rg * RPT;
+      int32_t* lp = labels ? labels + ((size_t)b * H + yb) * W + x : nullptr;
 #pragma unroll 1
-    for (int r = 0; r < RPT; ++r) {
-      const int y = yb + r;
-      if (y >= H) break;                                      // warp-uniform
-      const float4 f = s_feat[(rg * RPT + r) * SA_TX + tx];   // columns >= W of a cut tile: never copied, never used
-      const int hi = s_rowcell[rg * RPT + r];
-      if (hi != hi_prev) {                                    // warp-uniform
-        hi_prev = hi;
-        const int rb[3] = {(max(hi - 1, 0) - ci0) * ncj, (hi - ci0) * ncj, (min(hi + 1, g.gy - 1) - ci0) * ncj};
+      for (int r = 0; r < rows; ++r, fp += SA_TX, ++rc) {
+        const int y = yb + r;
+        const float4 f = *fp;
+        const int hi = *rc;
+        if (hi != hi_prev) {                                  // warp-uniform
+          hi_prev = hi;
+          rb0 = (max(hi - 1, 0) - ci0) * ncj; rb1 = (hi - ci0) * ncj; rb2 = (min(hi + 1, g.gy - 1) - ci0) * ncj;
+          const int rb[3] = {rb0, rb1, rb2};
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
+          for (int a = 0; a < 3; ++a) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int slot = rb[a] + jc[c];
-            const float4 q4 = s_q[2 * slot];
-            const float4 q2 = s_q[2 * slot + 1];
-            cslot[a * 3 + c] = slot;
-            qy[a * 3 + c] = q4.x;
-            qc[a * 3 + c] = fmaf(q4.y, fxs, q2.y);
-            qL[a * 3 + c] = q4.z;
-            qA[a * 3 + c] = q4.w;
-            qB[a * 3 + c] = q2.x;
+            for (int c = 0; c < 3; ++c) {
+              const int slot = rb[a] + jc[c];
+              const float4 q4 = s_q[2 * slot];
+              const float4 q2 = s_q[2 * slot + 1];
+              qy[a * 3 + c] = q4.x;
+              qc[a * 3 + c] = fmaf(q4.y, fxs, q2.y);
+              qL[a * 3 + c] = q4.z;
+              qA[a * 3 + c] = q4.w;
+              qB[a * 3 + c] = q2.x;
+            }
           }
         }
-      }
-      const bool in = x < W;
-      int best_slot = cur;
-      if (in) {
         const float fys = (float)y * inv_step;
-        float best = __int_as_float(0x7f7fffff);
-        best_slot = cslot[0];
-        // increasing centre index; ties keep the lower index (strict <)
+        // The candidate number rides in the four low mantissa bits of its distance, so the minimum over the
+        // candidates is a tree of 8 float min instructions that carries the winner along (no compare / select
+        // pairs, no slot registers); the distances are compared on their upper 28 bits (2^-19 relative: a
+        // hundredth of a pixel on the boundary position).
+        float d[9];
 #pragma unroll
         for (int s = 0; s < 9; ++s) {
-          const float d = fmaf(qy[s], fys, fmaf(qL[s], f.x, fmaf(qA[s], f.y, fmaf(qB[s], f.z, qc[s]))));
-          if (d < best) { best = d; best_slot = cslot[s]; }
+          const float v = fmaf(qy[s], fys, fmaf(qL[s], f.x, fmaf(qA[s], f.y, fmaf(qB[s], f.z, qc[s]))));
+          d[s] = __uint_as_float((__float_as_uint(v) & 0xfffffff0u) | (unsigned)s);
         }
-        if (labels) labels[((size_t)b * H + y) * W + x] = s_cid[best_slot];
-      }
-      // a thread whose winner changed hands its finished run over with plain shared-memory atomics (combining
-      // the lanes that give up the same centre with match.any / redux first was measured: 4.0 -> 5.5 ms)
-      const bool chg = in && best_slot != cur;
-      if (chg && n > 0) {
-        atomicAdd(&s_sum[cur][0], n);
-        atomicAdd(&s_sum[cur][1], sy);
-        atomicAdd(&s_sum[cur][2], x * n);
-        atomicAdd(&s_sum[cur][3], sL);
-        atomicAdd(&s_sum[cur][4], sA);
-        atomicAdd(&s_sum[cur][5], sB);
-      }
-      if (chg) {
-        cur = best_slot;
-        n = sy = sL = sA = sB = 0;
-      }
-      if (in) {
+        const float m01 = fminf(d[0], d[1]), m23 = fminf(d[2], d[3]), m45 = fminf(d[4], d[5]), m67 = fminf(d[6], d[7]);
+        const float mw = fminf(fminf(fminf(m01, m23), fminf(m45, m67)), d[8]);
+        const int bi = (int)(__float_as_uint(mw) & 15u);
+        const int ba = (bi * 11) >> 5, bc = bi - 3 * ba;        // candidate = 3 * row + column
+        const int best_slot = (ba == 0 ? rb0 : ba == 1 ? rb1 : rb2) + (bc == 0 ? jc0 : bc == 1 ? jc1 : jc2);
+        if (lp) { *lp = s_cid[best_slot]; lp += W; }
+        // a thread whose winner changed hands its finished run over with plain shared-memory atomics (combining
+        // the lanes that give up the same centre with match.any / redux first was measured: 4.0 -> 5.5 ms)
+        if (best_slot != cur) {
+          if (n > 0) {
+            atomicAdd(&s_sum[cur][0], n);
+            atomicAdd(&s_sum[cur][1], sy);
+            atomicAdd(&s_sum[cur][2], x * n);
+            atomicAdd(&s_sum[cur][3], sL);
+            atomicAdd(&s_sum[cur][4], sA);
+            atomicAdd(&s_sum[cur][5], sB);
+          }
+          cur = best_slot;
+          n = sy = sL = sA = sB = 0;
+        }
         // round-to-nearest fixed point without the conversion unit: 1.5 * 2^23 + v has the integer v in its
         // low mantissa bits (|v| < 2^22), the same value as __float2int_rn(f * SLIC_FIX)
         n += 1;
