@@ -2053,7 +2053,13 @@ int build_graphs(gg_context* ctx, Arena& ar, const uint8_t* bgr, const int32_t* 
       const long long atasks = (long long)B * ap.n_sx * ap.n_sy;
       GG_LAUNCH(ctx, k_adjacency_pairs, ceil_div(atasks, 8), 256, 0, st, ap);
       if (!direct) GG_RS_LAUNCH_NP(52, 8, 2, false, true);
-      else GG_RS_LAUNCH_NP(56, 4, 4, true, false);
+      else {
+        // blocks per SM of the direct variant without the pair bookkeeping (register cap 128 / 102 / 85)
+        static const int np_minb = getenv("GG_RS_NP_MINB") ? atoi(getenv("GG_RS_NP_MINB")) : 4;
+        if (np_minb == 5) GG_RS_LAUNCH_NP(57, 4, 5, true, false);
+        else if (np_minb == 6) GG_RS_LAUNCH_NP(58, 4, 6, true, false);
+        else GG_RS_LAUNCH_NP(56, 4, 4, true, false);
+      }
     } else
     if (!direct) GG_RS_LAUNCH(30, 8, 2, false, true);
     else if (variant == 0) GG_RS_LAUNCH(0, 8, 2, true, true);
