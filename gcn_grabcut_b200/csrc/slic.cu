@@ -183,6 +183,7 @@ k_slic_features(const uint8_t* __restrict__ bgr, const double* __restrict__ lin_
 // ---------------------------------------------------------------------------- k-means
 struct SlicGrid {
   int gy, gx, sy, ty, sx, tx, step;      // centres at (sy + i ty, sx + j tx), i < gy, j < gx
+  int general;                           // test switch: the column-walk kernels take their general path for every tile
 };
 constexpr float SLIC_FIX = 4096.0f;      // fixed-point scale of the colour sums
 
@@ -323,7 +324,7 @@ k_slic_assign(const float4* __restrict__ feat, const float* __restrict__ cen, co
       s_cid[i] = k;
       s_q[2 * i] = r0;
       s_q[2 * i + 1] = r1;
-      full = full && r1.z != 0.0f;
+      full = full && r1.z != 0.0f && g.general == 0;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     all_full = __syncthreads_and(full) != 0;
@@ -882,6 +883,8 @@ static SlicGrid make_grid(int H, int W, int n_segments) {
   g.sy = start[1]; g.ty = stepi[1]; g.sx = start[2]; g.tx = stepi[2];
   g.gy = (H - g.sy + g.ty - 1) / g.ty; g.gx = (W - g.sx + g.tx - 1) / g.tx;
   g.step = std::max(g.ty, g.tx);
+  static const int general = getenv("GG_SLIC_GENERAL") ? atoi(getenv("GG_SLIC_GENERAL")) : 0;
+  g.general = general;
   return g;
 }
 

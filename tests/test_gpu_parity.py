@@ -1089,7 +1089,10 @@ def test_slic_kernel_variants_and_odd_sizes(gg, tmp_path):
               "imgs = np.load(sys.argv[1]); np.save(sys.argv[2], gg.slic_labels(imgs, gg.SuperpixelGraphConfig(n_segments=300)))"
               % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     for name, env, exact in [("cc_scalar", {"GG_SLIC_CC_SCALAR": "1"}, True), ("walk32", {"GG_SLIC_WALK": "32"}, True),
-                             ("row_interleaved", {"GG_SLIC_WALK": "0"}, False)]:
+                             ("row_interleaved", {"GG_SLIC_WALK": "0"}, False),
+                             # the column-walk kernels' own general path (taken when a centre drifted so far that
+                             # its window no longer covers the tile), forced for every tile
+                             ("walk_general_path", {"GG_SLIC_GENERAL": "1"}, False)]:
         out = tmp_path / f"{name}.npy"
         subprocess.run([sys.executable, "-c", script, str(tmp_path / "imgs.npy"), str(out)], check=True,
                        env={**os.environ, **env}, timeout=300)
