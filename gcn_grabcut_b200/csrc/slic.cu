@@ -6,12 +6,15 @@
 //   k_slic_lab_minmax    float32 CIELAB of the image, global min / max over all three channels
 //   k_slic_features      rescale to [0,1], separable Gaussian (scipy.ndimage "reflect" border), the
 //                        second rgb2lab that skimage applies to any 3-channel input, x 1/compactness
-//   k_slic_init          centres on skimage's regular grid
-//   k_slic_assign        per pixel: the centres of the 5 x 5 grid cells around it, skimage's window
-//                        test and distance |dc|^2 + |dxy|^2 / step^2, lowest index wins ties; the
-//                        block accumulates its pixels into per-centre sums (integers: count, y, x,
+//   k_slic_init          centres on skimage's regular grid (+ the per-centre record the assignment reads)
+//   k_slic_assign        per pixel: the centres of the 3 x 3 (GG_SLIC_NEIGH=2: 5 x 5) grid cells around it,
+//                        distance |dc|^2 + |dxy|^2 / step^2.  Column-walk form (default): a thread walks 16 / 8
+//                        consecutive rows of one column, its 9 candidates in registers, feature rows staged by
+//                        cp.async; tiles with a window that does not cover them, very small grid steps and
+//                        NEIGH = 2 take the general form with skimage's window test, lowest index wins ties.
+//                        The block accumulates its pixels into per-centre sums (integers: count, y, x,
 //                        fixed-point colour -> the result does not depend on the order of the atomics)
-//   k_slic_update        centres = means
+//   k_slic_update        centres = means (+ the per-centre record)
 //   k_slic_cc_*          connectivity: union-find components of equal label (4-neighbours),
 //                        components smaller than half a nominal superpixel join the component of
 //                        the pixel above (or left of) their first pixel, consecutive relabelling in
