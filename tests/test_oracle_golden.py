@@ -249,3 +249,35 @@ def test_variant_ports_match_reference(tag):
     else:
         mine = model_port.gat_trimap_forward(state, x, ei, ea, batch)
     np.testing.assert_allclose(mine.numpy(), z[f"{tag}/logits"], atol=2e-5)
+
+
+def test_slic_port_properties():
+    """oracle/slic_port.py (the numpy restatement of skimage.segmentation.slic that gates the CUDA SLIC) has no
+    golden vectors -- scikit-image cannot run here, parity with it is unpinned -- so the restatement is held
+    to the properties scikit-image documents and the reference tests (tests/test.py:112-117): labels
+    contiguous from start_label = 0 with every label used, 4-connected segments none of which is smaller than
+    min_size = half a nominal superpixel (the first may absorb nothing and stay small), a segment count close
+    to the grid, determinism, and superpixel boundaries that follow the object boundary of a two-region image."""
+    from scipy import ndimage as ndi
+    from gcn_grabcut_b200.synthetic import geometric_sample
+    from oracle import graph_port, slic_port
+    H, W, nseg = 120, 160, 40
+    img, mask = geometric_sample(H, W, 4)
+    lab_img = graph_port.pixel_planes(img)["lab"]
+    seg = slic_port.slic(lab_img, nseg)
+    assert seg.shape == (H, W) and np.issubdtype(seg.dtype, np.integer)
+    n = int(seg.max()) + 1
+    assert seg.min() == 0 and len(np.unique(seg)) == n
+    sy, ty, sx, tx = slic_port.regular_grid_2d(H, W, nseg)
+    nominal = len(range(sy, H, ty)) * len(range(sx, W, tx))
+    assert 0.7 * nominal <= n <= 1.3 * nominal, (n, nominal)
+    assert sum(ndi.label(seg == v)[1] for v in range(n)) == n, "every label must be one 4-connected region"
+    sizes = np.bincount(seg.ravel())
+    assert (sizes[1:] >= int(0.5 * H * W / nominal)).all()
+    assert np.array_equal(seg, slic_port.slic(lab_img, nseg)), "deterministic"
+    assert slic_port.boundary_recall(seg, mask) >= 0.95
+    assert slic_port.undersegmentation_error(seg, mask) <= 0.03
+    # the quality measures themselves: a segmentation equal to the mask is perfect, one blind to it is not
+    assert slic_port.boundary_recall(mask.astype(np.int32), mask) == 1.0
+    assert slic_port.undersegmentation_error(mask.astype(np.int32), mask) == 0.0
+    assert slic_port.boundary_recall(np.zeros((H, W), np.int32), mask) == 0.0
